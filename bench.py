@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's benchmark (BASELINE.json: GCUPS and alignments/s on the
+1 M-pair batch).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the kernel over one batch of 1 000 000 pairs per GPU (weak scaling:
+rank r scores its own 1 M pairs; no collective is on the data path).  Rank 0's batch is the
+reference's own seeded stream (source.cpp:2944-2953), so every run re-checks the reference's
+checksum (FNV-1a-64 ae56a1e6a1d57492) on the scores it just timed.
+
+Prints ONE JSON line (rank 0):
+  value      whole-job GCUPS with inputs resident in HBM (cells = pairs * 128 * 128)
+  e2e        the same metric through the C-ABI host call swb200_score_batch with pinned HOST
+             buffers: H2D of both sequence arrays and D2H of the scores inside the timed region
+  roofline   integer-ALU issue roofline of the dominant kernel, measured live
+             with CUDA events on the launching stream; `hbm` sub-object = the sequence stream
+  cpu_baseline  the reference's simd4 (oracle/_ref) or the oracle port, timed on the host cores
+`--impl reference` times the reference's own CPU path (all host threads) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "smith-waterman-simd_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CELLS_PER_PAIR = 128 * 128
+PAIRS_PER_GPU = 1_000_000
+ALGO_INSTR_PER_CELL = 2.0        # 4 packed int16x2 instructions per 2 cells
+ALGO_BYTES_PER_PAIR = 128 + 128 + 4
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, mx, pw, reasons = [], [], [], set()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- peaks
+def load_peaks() -> dict:
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        peaks["hbm_gbs"] = float(m["hbm_gbs"]); peaks["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+        peaks["sm_max_mhz"] = float(m.get("sm_max_mhz", 1965.0))
+    except Exception:
+        pass
+    # integer-ALU issue peak: measured by tools/pipebench.cu on this pool (profiles/INT_PEAK.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "INT_PEAK.json")) as f:
+            ip = json.load(f)
+        peaks["alu_lanes_per_clk_per_sm"] = float(ip["alu_lanes_per_clk_per_sm"])
+        peaks["alu_src"] = "measured (profiles/INT_PEAK.json, tools/pipebench.cu)"
+    except Exception:
+        peaks["alu_lanes_per_clk_per_sm"] = 64.0
+        peaks["alu_src"] = "nominal 16 lanes/clk/SMSP (no profiles/INT_PEAK.json)"
+    return peaks
+
+
+# --------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_reference_run(a, b, matrix, gap, steps, warmup, budget_s=150.0):
+    """Times the reference's simd4 (oracle/_ref, the unmodified source) -- or the oracle port
+    when that build is absent -- with all host threads.  Returns (kind, variant, cores, ms_per_step, sample_pairs)."""
+    from oracle import oracle as O   # allowed here: cpu_baseline / --impl reference legs only
+    cores = os.cpu_count() or 1
+    n = a.shape[0]
+    if O.have_ref():
+        kind, variant = "reference", "SmithWaterman_simd4 (source.cpp:462-571), unmodified, g++ -O3 -mavx2"
+        run = lambda m: O.ref_score_batch(4, a[:m], b[:m], matrix, gap, threads=cores)
+    else:
+        O.build()
+        kind, variant = "port", "oracle/sw_oracle.c scalar restatement of source.cpp:35-60, gcc -O2"
+        run = lambda m: O.score_batch(a[:m], b[:m], matrix, gap, threads=cores)
+    probe = min(n, 20_000)
+    t = time.perf_counter(); run(probe); dt = time.perf_counter() - t
+    per_pair = dt / probe
+    # a step is the whole batch unless the whole run would blow the budget
+    sample = n
+    total = (steps + warmup) * n * per_pair
+    if total > budget_s:
+        sample = max(1000, int(n * budget_s / total))
+    for _ in range(warmup):
+        run(sample)
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter(); run(sample); times.append(time.perf_counter() - t)
+    return kind, variant, cores, 1e3 * sum(times) / len(times), sample
+
+
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import swb200
+    # inputs come from the product's generator (a .so load, no GPU needed); scoring is all reference
+    a, b = swb200.reference_stream(PAIRS_PER_GPU)
+    kind, variant, cores, ms, sample = cpu_reference_run(a, b, swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST, args.steps, args.warmup)
+    gcups = sample * CELLS_PER_PAIR / (ms * 1e-3) / 1e9
+    line = {
+        "impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "alignments_per_s": sample / (ms * 1e-3),
+        "config": {"workload": "1M seeded random 128-mer pairs (reference stream, source.cpp:2944-2953), matrix +10/-30, gap 15",
+                   "pairs_per_step": sample, "cells_per_pair": CELLS_PER_PAIR, "cpu_model": cpu_model()},
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "variant": variant,
+                         "sample": f"{sample} of 1000000 pairs per step, {args.steps} steps, {cores} threads over contiguous index ranges"},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import swb200
+    from sharding import max_over_ranks, sum_over_ranks
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ddist = dist if world > 1 else None
+
+    matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
+    ctx = swb200.Context(devices=[local_rank])
+    info = ctx.kernel_info(matrix, gap)
+    n = PAIRS_PER_GPU
+
+    # ---- this rank's batch, in PINNED host memory (the e2e leg copies from here every step)
+    pa, pb = swb200.PinnedArray((n, 128), np.uint8), swb200.PinnedArray((n, 128), np.uint8)
+    ps = swb200.PinnedArray((n,), np.int32)
+    if rank == 0:
+        swb200.reference_stream(n, out=(pa.array, pb.array))        # the reference's own stream
+    else:
+        swb200.counter_pairs(rank * n, n, out=(pa.array, pb.array))  # index range [rank*n, (rank+1)*n)
+
+    d_a = torch.from_numpy(pa.array).cuda(non_blocking=False)
+    d_b = torch.from_numpy(pb.array).cuda(non_blocking=False)
+    d_s = torch.empty(n, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ================= leg 1: device-resident (value, roofline)
+    for _ in range(args.warmup):
+        ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)   # 256 MB of sequence data per launch: larger than the 126 MB L2
+        ev[i + 1].record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches_dev = ctx.launch_count - launches0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    ms_step = max_over_ranks(ms_total / args.steps, ddist)
+    total_pairs = sum_over_ranks(n, ddist)
+    gcups = total_pairs * CELLS_PER_PAIR / (ms_step * 1e-3) / 1e9
+
+    scores = d_s.cpu().numpy()
+    verified = None
+    if rank == 0:
+        verified = (f"{swb200.fnv1a64(scores):016x}" == "ae56a1e6a1d57492") and int(scores.sum()) == 75_478_815
+
+    # ================= leg 2: end to end through the C-ABI host call (pinned host in/out)
+    for _ in range(min(args.warmup, 3)):
+        ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
+    barrier()
+    launches1 = ctx.launch_count
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)   # H2D + kernels + D2H, returns when scores are on the host
+    barrier()
+    t1 = time.perf_counter()
+    sampler.stop()
+    launches_e2e = ctx.launch_count - launches1
+    e2e_ms = max_over_ranks(1e3 * (t1 - t0) / e2e_steps, ddist)
+    e2e_gcups = total_pairs * CELLS_PER_PAIR / (e2e_ms * 1e-3) / 1e9
+    e2e_ok = bool(np.array_equal(ps.array, scores))
+    all_ok = sum_over_ranks(1.0 if e2e_ok else 0.0, ddist) == world
+
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- roofline of the dominant kernel, from this rank's live CUDA-event launch times
+    peaks = load_peaks()
+    avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    alu_peak_tinstr = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * sm_mhz * 1e6 / 1e12
+    achieved_tinstr = n * CELLS_PER_PAIR * ALGO_INSTR_PER_CELL / (avg_launch_ms * 1e-3) / 1e12
+    hbm_achieved = n * ALGO_BYTES_PER_PAIR / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "int_alu", "kernel": "sw128_kernel<FAST=%d>" % info["fast_path"],
+        "achieved": achieved_tinstr, "peak": alu_peak_tinstr, "unit": "Tinstr/s (thread-level packed int16x2 ALU instructions)",
+        "frac": achieved_tinstr / alu_peak_tinstr,
+        "algorithmic_instr_per_cell": ALGO_INSTR_PER_CELL, "cells_per_launch": n * CELLS_PER_PAIR,
+        "avg_launch_ms": avg_launch_ms, "peak_src": f"{peaks['alu_src']}: {peaks['alu_lanes_per_clk_per_sm']} lanes/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz (median SM clock sampled during the run)",
+        "traffic": None,
+        "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
+                "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "peak_src": peaks["hbm_src"],
+                "note": "evidence that the sequence stream is not limiting (SURVEY.md 8d)"},
+    }
+    try:
+        with open(os.path.join(ROOT, "profiles", "NCU_SUMMARY.json")) as f:
+            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, variant, cores, ms, sample = cpu_reference_run(pa.array, pb.array, matrix, gap, steps=3, warmup=1, budget_s=40.0)
+        cpu_baseline = {"value": sample * CELLS_PER_PAIR / (ms * 1e-3) / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+                        "variant": variant, "cpu_model": cpu_model(),
+                        "sample": f"{sample} of 1000000 pairs per pass, 3 timed passes, {cores} threads over contiguous index ranges",
+                        "ms_per_1M_pairs": ms * 1e6 / sample}
+
+    if rank == 0:
+        line = {
+            "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16x2", "data": "synthetic",
+            "alignments_per_s": total_pairs / (ms_step * 1e-3),
+            "config": {"workload": "configs[1]: 1M seeded random 128-mer pairs per GPU (rank 0 = reference stream source.cpp:2944-2953; rank r = counter stream pairs [r*1M,(r+1)*1M)), matrix +10/-30, gap 15",
+                       "pairs_per_gpu": n, "cells_per_pair": CELLS_PER_PAIR, "sharding": "contiguous index ranges, no collective",
+                       "l2": "inputs 256 MB per launch > 126 MB L2, no flush needed",
+                       "kernel": info},
+            "clocks": clocks,
+            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "ms_per_step": e2e_ms, "alignments_per_s": total_pairs / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": 2 * n * 128, "d2h_bytes_per_step": 4 * n,
+                    "api": "swb200_score_batch (C ABI, pinned host arrays, chunked H2D/kernel/D2H overlap)", "scores_equal_device_leg": all_ok},
+            "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
+            "roofline": roofline,
+            "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok},
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        log("bench.py: warmup raised to 3 (timing rules)")
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

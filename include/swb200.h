@@ -1,0 +1,167 @@
+/*
+ * swb200.h -- C ABI of the B200-native replacement for the one hot path of
+ * eukaryo/smith-waterman-simd: score-only Smith-Waterman (linear gap, 4x4 int8
+ * substitution matrix) of pairs of 128-base DNA sequences.
+ *
+ * The reference has no library boundary at all -- its kernels are free functions in one
+ * translation unit (/root/reference/source.cpp) -- so each entry point below cites the
+ * reference interface it stands in for.  INTEGRATION.md shows the binding a maintainer of
+ * the reference would add.  Plain C: pointers and sizes only, no C++ or torch types.
+ *
+ * Semantics shared by all scoring entry points (the reference's contract):
+ *   - sequences are bytes holding codes 0..3, 128 per sequence, sequences laid end to end
+ *     (what `const std::array<uint8_t,128>&` is in memory, source.cpp:36-37);
+ *   - score_matrix is 16 int8, indexed seq1_code*4 + seq2_code (source.cpp:38,50);
+ *   - gap_penalty is the linear gap cost, subtracted (source.cpp:39,51-52);
+ *   - the score is max(0, best local alignment score) as an int (source.cpp:41,53,59).
+ * Parameter domain: matrix entries in [-127,127], gap in [0,127] -- the domain on which
+ * the reference's AVX2 kernels agree with its scalar kernel.  Outside it
+ * the call returns SWB200_ERR_DOMAIN instead of a silently different number.
+ * Codes above 3 are the caller's error, as in the reference (which indexes unchecked,
+ * source.cpp:50); the library never reads out of bounds for them but the score is
+ * unspecified.  swb200_validate_codes() checks a buffer on the device.
+ *
+ * There is NO CPU fallback: every scoring call runs the sm_100a kernel or fails.
+ */
+#ifndef SWB200_H
+#define SWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWB200_SEQ_LEN 128   /* std::array<uint8_t,128>, source.cpp:36-37 */
+
+enum {
+    SWB200_OK = 0,
+    SWB200_ERR_ARG = -1,        /* null pointer, bad handle, misaligned device pointer */
+    SWB200_ERR_DOMAIN = -2,     /* matrix entry == -128 or gap outside [0,127] */
+    SWB200_ERR_NO_DEVICE = -3,  /* no CUDA device / not an sm_100 device */
+    SWB200_ERR_CUDA = -4,       /* a CUDA call failed; swb200_last_error() has the text */
+    SWB200_ERR_NOMEM = -5,
+    SWB200_ERR_TICKET = -6      /* unknown or already-waited ticket */
+};
+
+typedef struct swb200_ctx swb200_ctx;
+
+/* ---- lifetime --------------------------------------------------------------------- */
+
+/* Number of usable (compute capability 10.x) CUDA devices, or a negative error. */
+int swb200_device_count(void);
+
+/* Creates a context on `n_devices` GPUs.  devices == NULL means 0..n_devices-1;
+ * n_devices == 0 means all visible.  The context owns streams, device staging buffers
+ * and one worker per GPU; host arrays always stay the caller's.
+ * (No reference counterpart: the reference keeps no state, source.cpp:35-60.) */
+int swb200_init(swb200_ctx** ctx, const int* devices, int n_devices);
+void swb200_shutdown(swb200_ctx* ctx);
+int swb200_n_devices(const swb200_ctx* ctx);
+
+/* Text of the last failure on this context (or of the last failed swb200_init when ctx == NULL). */
+const char* swb200_last_error(const swb200_ctx* ctx);
+const char* swb200_strerror(int code);
+
+/* ---- the batch packer's host side ------------------------------------------------- */
+
+/* Page-locked host memory: copies from/to it overlap with kernels.  Pageable host
+ * arrays are accepted everywhere, they are just slower to move. */
+int swb200_alloc_pinned(void** ptr, size_t bytes);
+int swb200_free_pinned(void* ptr);
+
+/* ---- scoring ---------------------------------------------------------------------- */
+
+/* Replaces ONE call of
+ *   int SmithWaterman_simdN(const std::array<uint8_t,128>& seq1, const std::array<uint8_t,128>& seq2,
+ *                           const std::array<int8_t,16>& score_matrix, const int8_t gap_penalty)
+ * (source.cpp:462-466; identical signatures at 35-39, 62, 210, 341, 573, 666, 758, 852, 953).
+ * The score is written to *score. */
+int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
+                      const int8_t* score_matrix, int8_t gap_penalty, int32_t* score);
+
+/* Replaces the loop `for (pair p) scores[p] = SmithWaterman_simdN(a[p], b[p], sm, gap)`
+ * that the reference's harnesses run (source.cpp:2947-2970, 3049-3051, 3209-3235).
+ * The batched-call precedent in the reference is SmithWaterman_8b111x32mark1
+ * (source.cpp:1227-1234: 32 row-major 128-mers in, results into a `dest` array).
+ * HOST arrays: seq1[n][128], seq2[n][128], scores[n].  Pairs are split in contiguous
+ * index ranges over the context's GPUs; each GPU streams its range in chunks
+ * (H2D, kernel, D2H overlapped) and writes its slice of `scores` directly. */
+int swb200_score_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
+                       const int8_t* score_matrix, int8_t gap_penalty,
+                       int32_t* scores, uint64_t n);
+
+/* Same, inputs as the reference's 2-bit packing: 32 bytes per sequence,
+ * code(i*4+j) = (byte[i] >> 2j) & 3   (source.cpp:1580-1583, `unpack`).
+ * seq1_packed[n][32], seq2_packed[n][32].  Unpacking happens on the device. */
+int swb200_score_batch_packed(swb200_ctx* ctx, const uint8_t* seq1_packed, const uint8_t* seq2_packed,
+                              const int8_t* score_matrix, int8_t gap_penalty,
+                              int32_t* scores, uint64_t n);
+
+/* Asynchronous form of swb200_score_batch for streaming callers: returns at once with a
+ * ticket; the arrays must stay valid and untouched until swb200_wait(ticket) returns. */
+typedef uint64_t swb200_ticket;
+int swb200_submit(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
+                  const int8_t* score_matrix, int8_t gap_penalty,
+                  int32_t* scores, uint64_t n, swb200_ticket* ticket);
+int swb200_wait(swb200_ctx* ctx, swb200_ticket ticket);
+
+/* DEVICE arrays on GPU `device_index` of the context (16-byte aligned), enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = the legacy default stream); returns without
+ * synchronising.  This is the kernel launch alone. */
+int swb200_score_batch_device(swb200_ctx* ctx, int device_index,
+                              const uint8_t* d_seq1, const uint8_t* d_seq2,
+                              const int8_t* score_matrix, int8_t gap_penalty,
+                              int32_t* d_scores, uint64_t n, void* cuda_stream);
+int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index,
+                                     const uint8_t* d_seq1_packed, const uint8_t* d_seq2_packed,
+                                     const int8_t* score_matrix, int8_t gap_penalty,
+                                     int32_t* d_scores, uint64_t n, void* cuda_stream);
+
+/* Counts bytes > 3 in a DEVICE buffer (the reference never checks, source.cpp:50). */
+int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_t* d_codes,
+                                 uint64_t n_bytes, uint64_t* n_bad, void* cuda_stream);
+
+/* ---- introspection for the benchmark harness --------------------------------------- */
+
+typedef struct swb200_kernel_info {
+    int fast_path;          /* 1: anti-diagonal offset DP (2 instr/word); 0: general form */
+    int regs_per_thread;
+    int threads_per_block;
+    int blocks_per_sm;      /* resident, by the occupancy calculator */
+    int smem_bytes_per_block;
+    int sm_count;
+    int sm_clock_khz;       /* cudaDevAttrClockRate */
+} swb200_kernel_info;
+
+/* Which kernel swb200_score_batch* would launch for this matrix/gap, and its resources. */
+int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* score_matrix,
+                           int8_t gap_penalty, swb200_kernel_info* info);
+
+/* Kernel launches issued by this context since creation (all GPUs). */
+uint64_t swb200_launch_count(const swb200_ctx* ctx);
+
+/* Test hook: 1 forces the general (non-offset) kernel even where the fast one is exact. */
+int swb200_set_force_general(swb200_ctx* ctx, int on);
+
+/* ---- synthetic inputs and checksum for the verification / benchmark harness ---------- */
+
+/* Pairs [0,n) of the reference's own test stream (source.cpp:2944-2953: mt19937_64(seed),
+ * one draw per base taken as draw>>62, a[i] and b[i] alternately).  Host arrays [n][128]. */
+int swb200_gen_reference_stream(uint64_t seed, uint64_t n, uint8_t* seq1, uint8_t* seq2);
+
+/* Pairs [first, first+n) of a counter-based stream (pair k depends only on (seed,k)), so
+ * any index range can be generated by any thread, rank or shard.  Byte codes [n][128] or
+ * the reference's 2-bit packing [n][32] (source.cpp:1580-1583). */
+int swb200_gen_counter_pairs(uint64_t seed, uint64_t first, uint64_t n, uint8_t* seq1, uint8_t* seq2, int threads);
+int swb200_gen_counter_pairs_packed(uint64_t seed, uint64_t first, uint64_t n,
+                                    uint8_t* seq1_packed, uint8_t* seq2_packed, int threads);
+
+/* FNV-1a-64 over int32 scores: h = 1469598103934665603; h = (h ^ (uint32)s) * 1099511628211. */
+uint64_t swb200_fnv1a64_i32(const int32_t* scores, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWB200_H */

@@ -1,0 +1,163 @@
+"""ctypes loader for the test oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (smith-waterman-simd_b200/) never does.
+
+Two libraries:
+  * libsworacle.so  -- oracle/sw_oracle.c, the plain-C restatement of
+    /root/reference/source.cpp:35-60 (+ generator 2944-2953, unpack 1580-1583).
+  * _ref/libswref.so -- oracle/ref_wrap.cpp, the unmodified reference compiled where it
+    lies; present when it was built in the authoring container (it travels to the GPU box
+    as a built file).  `have_ref()` says whether it is loadable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT = os.path.join(HERE, "libsworacle.so")
+_REF = os.path.join(HERE, "_ref", "libswref.so")
+
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the oracle (and, when /root/reference exists, oracle/_ref)."""
+    subprocess.run(["make", "-C", HERE], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        if not os.path.exists(_PORT):
+            build()
+        lib = C.CDLL(_PORT)
+        lib.swo_score.restype = C.c_int32
+        lib.swo_score.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _i8p, C.c_int]
+        lib.swo_score_batch.restype = None
+        lib.swo_score_batch.argtypes = [_u8p, _u8p, C.c_int, _i8p, C.c_int, _i32p, C.c_uint64]
+        lib.swo_score_batch_mt.restype = None
+        lib.swo_score_batch_mt.argtypes = [_u8p, _u8p, C.c_int, _i8p, C.c_int, _i32p, C.c_uint64, C.c_int]
+        lib.swo_reference_stream.restype = None
+        lib.swo_reference_stream.argtypes = [C.c_uint64, C.c_uint64, _u8p, _u8p]
+        lib.swo_fnv1a64_scores.restype = C.c_uint64
+        lib.swo_fnv1a64_scores.argtypes = [_i32p, C.c_uint64]
+        lib.swo_unpack2bit.restype = None
+        lib.swo_unpack2bit.argtypes = [_u8p, _u8p, C.c_uint64]
+        lib.swo_pack2bit.restype = None
+        lib.swo_pack2bit.argtypes = [_u8p, _u8p, C.c_uint64]
+        _port = lib
+    return _port
+
+
+def have_ref() -> bool:
+    try:
+        ref()
+        return True
+    except OSError:
+        return False
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF) and os.path.exists("/root/reference/source.cpp"):
+            build()
+        lib = C.CDLL(_REF)
+        lib.swref_score_batch.restype = C.c_int
+        lib.swref_score_batch.argtypes = [C.c_int, _u8p, _u8p, _i8p, C.c_int, _i32p, C.c_uint64, C.c_int]
+        lib.swref_score_repeat.restype = C.c_int
+        lib.swref_score_repeat.argtypes = [C.c_int, _u8p, _u8p, _i8p, C.c_int, C.c_uint64]
+        lib.swref_reference_stream.restype = None
+        lib.swref_reference_stream.argtypes = [C.c_uint64, C.c_uint64, _u8p, _u8p]
+        lib.swref_unpack.restype = None
+        lib.swref_unpack.argtypes = [_u8p, _u8p]
+        lib.swref_hardware_threads.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _mat(score_matrix) -> np.ndarray:
+    m = np.ascontiguousarray(np.asarray(score_matrix, dtype=np.int8).reshape(16))
+    return m
+
+
+def score_batch(seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap: int, threads: int = 1) -> np.ndarray:
+    """Restatement (sw_oracle.c). seq1/seq2: uint8 [n][L] codes 0..3."""
+    seq1 = np.ascontiguousarray(seq1, dtype=np.uint8)
+    seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
+    assert seq1.shape == seq2.shape and seq1.ndim == 2
+    n, L = seq1.shape
+    out = np.empty(n, dtype=np.int32)
+    m = _mat(score_matrix)
+    port().swo_score_batch_mt(_p(seq1, _u8p), _p(seq2, _u8p), L, _p(m, _i8p), int(gap), _p(out, _i32p), n, threads)
+    return out
+
+
+def ref_score_batch(variant: int, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap: int, threads: int = 1) -> np.ndarray:
+    """The reference itself. variant 0 = scalar, 1..9 = SmithWaterman_simd..simd9. L must be 128."""
+    seq1 = np.ascontiguousarray(seq1, dtype=np.uint8)
+    seq2 = np.ascontiguousarray(seq2, dtype=np.uint8)
+    assert seq1.shape == seq2.shape and seq1.ndim == 2 and seq1.shape[1] == 128
+    n = seq1.shape[0]
+    out = np.empty(n, dtype=np.int32)
+    m = _mat(score_matrix)
+    rc = ref().swref_score_batch(variant, _p(seq1, _u8p), _p(seq2, _u8p), _p(m, _i8p), int(gap), _p(out, _i32p), n, threads)
+    if rc != 0:
+        raise ValueError(f"unknown reference variant {variant}")
+    return out
+
+
+def reference_stream(n: int, seed: int = 10000, use_ref: bool = False):
+    """Pairs [0,n) of the reference's test stream (source.cpp:2944-2953)."""
+    a = np.empty((n, 128), dtype=np.uint8)
+    b = np.empty((n, 128), dtype=np.uint8)
+    if use_ref:
+        ref().swref_reference_stream(seed, n, _p(a, _u8p), _p(b, _u8p))
+    else:
+        port().swo_reference_stream(seed, n, _p(a, _u8p), _p(b, _u8p))
+    return a, b
+
+
+def fnv1a64(scores: np.ndarray) -> int:
+    scores = np.ascontiguousarray(scores, dtype=np.int32)
+    return int(port().swo_fnv1a64_scores(_p(scores, _i32p), scores.size))
+
+
+def pack2bit(codes: np.ndarray) -> np.ndarray:
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    n = codes.shape[0]
+    assert codes.shape[1] == 128
+    out = np.empty((n, 32), dtype=np.uint8)
+    port().swo_pack2bit(_p(codes, _u8p), _p(out, _u8p), n)
+    return out
+
+
+def unpack2bit(packed: np.ndarray) -> np.ndarray:
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    n = packed.shape[0]
+    assert packed.shape[1] == 32
+    out = np.empty((n, 128), dtype=np.uint8)
+    port().swo_unpack2bit(_p(packed, _u8p), _p(out, _u8p), n)
+    return out
+
+
+MATRIX_SPEEDTEST = [10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10]  # source.cpp:3041-3045
+GAP_SPEEDTEST = 15                                                                           # source.cpp:3046
+MATRIX_111 = [1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1]                    # source.cpp:3202-3206
+GAP_111 = 1                                                                                  # source.cpp:3207

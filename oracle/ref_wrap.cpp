@@ -1,0 +1,118 @@
+// ref_wrap.cpp -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// Compiles the UNMODIFIED reference translation unit where it lies
+// (/root/reference/source.cpp, found through -I by oracle/Makefile) and exports
+// its scalar and AVX2 kernels behind a C ABI, so that tests can pin
+// oracle/sw_oracle.c and the CUDA path against the reference itself, and so that
+// bench.py can time the reference's own CPU path (`--impl reference`,
+// cpu_baseline.kind == "reference").  No reference source is copied into this
+// repository: the only coupling is the #include below.  Built WITHOUT -DNDEBUG,
+// as the reference's own asserts expect.
+//
+// Entry points wrap:
+//   SmithWaterman        source.cpp:35-60     (scalar; the oracle of record)
+//   SmithWaterman_simd   source.cpp:62-208    ... SmithWaterman_simd9 source.cpp:953-1071
+//   unpack               source.cpp:1580-1583
+//   mt19937_64(seed) + uniform_int_distribution<int>(0,3), a/b interleaved: source.cpp:2944-2953
+#define main swref_reference_main
+#include "source.cpp"
+#undef main
+
+#include <thread>
+
+namespace {
+using Seq = std::array<uint8_t, 128>;
+using Mat = std::array<int8_t, 16>;
+typedef int (*KernelFn)(const Seq&, const Seq&, const Mat&, const int8_t);
+
+KernelFn pick(int variant)
+{
+    switch (variant) {
+    case 0: return SmithWaterman;
+    case 1: return SmithWaterman_simd;
+    case 2: return SmithWaterman_simd2;
+    case 3: return SmithWaterman_simd3;
+    case 4: return SmithWaterman_simd4;
+    case 5: return SmithWaterman_simd5;
+    case 6: return SmithWaterman_simd6;
+    case 7: return SmithWaterman_simd7;
+    case 8: return SmithWaterman_simd8;
+    case 9: return SmithWaterman_simd9;
+    default: return nullptr;
+    }
+}
+
+void run_range(KernelFn fn, const uint8_t* s1, const uint8_t* s2, const int8_t* sm, int gap,
+               int32_t* out, uint64_t lo, uint64_t hi)
+{
+    Mat m;
+    std::memcpy(m.data(), sm, 16);
+    Seq a, b;
+    for (uint64_t p = lo; p < hi; ++p) {
+        std::memcpy(a.data(), s1 + p * 128, 128);
+        std::memcpy(b.data(), s2 + p * 128, 128);
+        out[p] = fn(a, b, m, (int8_t)gap);
+    }
+}
+} // namespace
+
+extern "C" {
+
+// variant: 0 = scalar, 1..9 = SmithWaterman_simd .. SmithWaterman_simd9.  Returns -1 for an unknown variant.
+int swref_score_batch(int variant, const uint8_t* seq1, const uint8_t* seq2, const int8_t* score_matrix,
+                      int gap_penalty, int32_t* scores, uint64_t n, int threads)
+{
+    KernelFn fn = pick(variant);
+    if (!fn) return -1;
+    if (threads <= 1) {
+        run_range(fn, seq1, seq2, score_matrix, gap_penalty, scores, 0, n);
+        return 0;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back(run_range, fn, seq1, seq2, score_matrix, gap_penalty, scores,
+                          n * (uint64_t)t / (uint64_t)threads, n * (uint64_t)(t + 1) / (uint64_t)threads);
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+// The reference's own way of timing (source.cpp:3047-3055): ONE pair, `calls` times.  Returns the last score.
+int swref_score_repeat(int variant, const uint8_t* seq1, const uint8_t* seq2, const int8_t* score_matrix,
+                       int gap_penalty, uint64_t calls)
+{
+    KernelFn fn = pick(variant);
+    if (!fn) return -1;
+    Mat m; std::memcpy(m.data(), score_matrix, 16);
+    Seq a, b;
+    std::memcpy(a.data(), seq1, 128);
+    std::memcpy(b.data(), seq2, 128);
+    volatile int score = 0;
+    for (uint64_t i = 0; i < calls; ++i) score = fn(a, b, m, (int8_t)gap_penalty);
+    return score;
+}
+
+// The reference's generator exactly as written (std::uniform_int_distribution), source.cpp:2944-2953.
+void swref_reference_stream(uint64_t seed, uint64_t n, uint8_t* seq1, uint8_t* seq2)
+{
+    std::mt19937_64 rnd(seed);
+    std::uniform_int_distribution<int> dna(0, 3);
+    for (uint64_t p = 0; p < n; ++p)
+        for (int i = 0; i < 128; ++i) {
+            seq1[p * 128 + i] = (uint8_t)dna(rnd);
+            seq2[p * 128 + i] = (uint8_t)dna(rnd);
+        }
+}
+
+// source.cpp:1580-1583
+void swref_unpack(const uint8_t* src32, uint8_t* dest128)
+{
+    std::array<uint8_t, 32> s;
+    std::array<uint8_t, 128> d;
+    std::memcpy(s.data(), src32, 32);
+    unpack(s, d);
+    std::memcpy(dest128, d.data(), 128);
+}
+
+int swref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+} // extern "C"

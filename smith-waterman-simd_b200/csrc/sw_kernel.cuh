@@ -1,0 +1,62 @@
+// sw_kernel.cuh -- the sm_100a kernel around sw_core.cuh.
+//
+// Work decomposition: thread t of the grid scores pairs 2t (low halves) and 2t+1 (high
+// halves) completely; there is no inter-thread communication.  A block of NT threads owns
+// NT*128 words of shared memory: thread-interleaved FIFOs (word c of thread x at
+// [c*NT + x], so a warp's access is one conflict-free 128-byte wavefront) that carry each
+// strip's bottom row to the next strip, plus the 4-word profile table.
+//
+// HBM layout read by the kernel: seq1 and seq2 as the reference passes them
+// (std::array<uint8_t,128>, source.cpp:36-37) laid end to end: [n][128] bytes, codes 0..3.
+// Each thread pulls 16 bases of each target per 16 steps with two 8-byte loads, one
+// iteration ahead; 260 bytes of HBM traffic per pair against 16 384 cell updates.
+#pragma once
+#include <cuda_runtime.h>
+#include "sw_core.cuh"
+
+namespace swb {
+
+template <int NT>
+struct SmemFifo {
+    uint32_t* f;   // &fifo[0*NT + threadIdx.x]
+    __device__ __forceinline__ uint32_t pop(int c) const { return f[c * NT]; }
+    __device__ __forceinline__ void push(int c, uint32_t v) { f[c * NT] = v; }
+};
+
+struct SmemTable {
+    const uint32_t* t;
+    __device__ __forceinline__ uint32_t operator()(uint32_t byte_off) const
+    {
+        return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t) + byte_off);
+    }
+};
+
+template <int NT>
+constexpr size_t sw128_smem_bytes() { return (size_t)(SW_L * NT + 4) * sizeof(uint32_t); }
+
+template <bool FAST, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+sw128_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
+             int32_t* __restrict__ scores, unsigned long long n, const SwParams prm)
+{
+    extern __shared__ uint32_t smem[];
+    uint32_t* t4s = smem + SW_L * NT;
+    if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
+    __syncthreads();
+
+    const unsigned long long p = 2ull * ((unsigned long long)blockIdx.x * NT + threadIdx.x);
+    if (p >= n) return;
+    const unsigned long long q = (p + 1 < n) ? p + 1 : p;   // odd tail: the high half repeats the low pair
+
+    SmemFifo<NT> fifo{smem + threadIdx.x};
+    SmemTable t4{t4s};
+    int32_t lo, hi;
+    sw128_two_pairs<FAST>(seq1 + p * SW_L, seq1 + q * SW_L, seq2 + p * SW_L, seq2 + q * SW_L, fifo, t4, prm, lo, hi);
+    if (q != p) {
+        *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
+    } else {
+        scores[p] = lo;
+    }
+}
+
+} // namespace swb

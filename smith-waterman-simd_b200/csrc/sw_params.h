@@ -1,0 +1,54 @@
+// sw_params.h -- host-side derivation of the kernel constants from the reference's
+// arguments `score_matrix` (4x4 int8, index seq1*4+seq2, source.cpp:38,50) and
+// `gap_penalty` (int8, source.cpp:39).  Plain C++, no CUDA.
+#pragma once
+#include <stdint.h>
+#include "sw_core.cuh"
+
+namespace swb {
+
+enum SwDomain { SW_DOMAIN_OK = 0, SW_DOMAIN_BAD_MATRIX = 1, SW_DOMAIN_BAD_GAP = 2 };
+
+// The domain on which the reference's SIMD kernels equal its scalar one:
+// every matrix entry in [-127,127] (an entry of -128 wraps in source.cpp:492) and gap in
+// [0,127].  Outside it the reference itself is inconsistent, so the batch entry refuses.
+inline int sw_check_domain(const int8_t sm[16], int gap)
+{
+    for (int i = 0; i < 16; ++i) if (sm[i] == -128) return SW_DOMAIN_BAD_MATRIX;
+    if (gap < 0 || gap > 127) return SW_DOMAIN_BAD_GAP;
+    return SW_DOMAIN_OK;
+}
+
+inline uint32_t sw_pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+
+inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general = 0)
+{
+    SwParams p;
+    int smax = 0;
+    for (int i = 0; i < 16; ++i) if (sm[i] > smax) smax = sm[i];
+    // Fast path (anti-diagonal offset DP) is exact iff every shifted score fits a
+    // non-negative signed byte and no packed value leaves int16 over the 1040 steps:
+    //   e = max(S,-2g)+2g <= 127,  128*smax + g*(16*SW_ITERS+2) <= 32767,  -111g >= -32768.
+    const int steps = 16 * SW_ITERS;
+    const bool fast = !force_general && (smax + 2 * gap <= 127) &&
+                      (128 * smax + gap * (steps + 2) <= 32767) && (111 * gap <= 32768);
+    p.fast = fast ? 1 : 0;
+    p.gap = gap;
+    for (int a = 0; a < 4; ++a) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; ++b) {
+            int e = sm[a * 4 + b];
+            if (fast) { if (e < -2 * gap) e = -2 * gap; e += 2 * gap; }
+            w |= ((uint32_t)e & 0xffu) << (8 * b);
+        }
+        p.t4[a] = w;
+    }
+    p.dummy = fast ? 0u : 0x81818181u;   // fast: e = 0 (a step worth two gaps); general: S = -127
+    p.G = sw_pack2(gap);
+    p.NG = sw_pack2(-gap);
+    p.N2G = sw_pack2(-2 * gap);
+    p.K = fast ? sw_pack2((SW_L - SW_R) * gap) : 0u;
+    return p;
+}
+
+} // namespace swb

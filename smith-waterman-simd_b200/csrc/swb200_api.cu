@@ -1,0 +1,493 @@
+// swb200_api.cu -- the C ABI of include/swb200.h: context, batch packer (pinned staging,
+// chunked H2D / kernel / D2H overlap), index-range sharding over the GPUs of one box with
+// a plain host-side gather (no collective: pairs are independent), and the
+// kernel launches.  There is no CPU scoring path in this file or anywhere in the product.
+#include "../../include/swb200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sw_kernel.cuh"
+#include "sw_params.h"
+
+namespace {
+
+using namespace swb;
+
+constexpr int kNT = 128;         // threads per block: 64 KiB of FIFO
+constexpr int kMinBlocks = 3;    // resident blocks per SM the register budget is set for
+constexpr int kSlots = 3;        // chunks in flight per GPU
+constexpr uint64_t kChunkPairs = 1ull << 17;   // 131072 pairs = 16 MiB per sequence array per chunk
+
+thread_local std::string g_init_error;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t* d_seq1 = nullptr;       // [kChunkPairs][128]
+    uint8_t* d_seq2 = nullptr;
+    uint8_t* d_pk1 = nullptr;        // [kChunkPairs][32]  2-bit packed staging
+    uint8_t* d_pk2 = nullptr;
+    int32_t* d_scores = nullptr;     // [kChunkPairs]
+    bool busy = false;
+};
+
+struct Device {
+    int id = -1;
+    cudaDeviceProp prop{};
+    Slot slots[kSlots];
+    std::mutex mu;                   // one host batch at a time per GPU
+    unsigned long long* d_bad = nullptr;
+};
+
+} // namespace
+
+struct swb200_ctx {
+    std::vector<Device*> devs;
+    std::string err;
+    std::atomic<uint64_t> launches{0};
+    int force_general = 0;
+    std::mutex tickets_mu;
+    std::map<uint64_t, std::pair<std::thread, int*>> tickets;
+    uint64_t next_ticket = 1;
+};
+
+namespace {
+
+int fail(swb200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+    return code;
+}
+
+#define SWB_CUDA(ctx, call)                                                        \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return fail((ctx), SWB200_ERR_CUDA, #call, e_);     \
+    } while (0)
+
+// 2-bit packed -> byte codes, the reference's `unpack` (source.cpp:1580-1583):
+// dest[i*4+j] = (src[i] >> 2j) & 3.  One thread expands 4 packed bytes into 16 codes.
+__global__ void unpack2bit_kernel(const uint32_t* __restrict__ src, uint4* __restrict__ dst, unsigned long long n_words)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t w = __ldg(src + i);
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const uint32_t x = (w >> (8 * b)) & 0xffu;
+        o[b] = (x & 3u) | (((x >> 2) & 3u) << 8) | (((x >> 4) & 3u) << 16) | (((x >> 6) & 3u) << 24);
+    }
+    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void count_bad_codes_kernel(const uint8_t* __restrict__ codes, unsigned long long n, unsigned long long* n_bad)
+{
+    unsigned long long local = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        local += (codes[i] > 3u);
+    local = __reduce_add_sync(0xffffffffu, (unsigned)local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_bad, local);
+}
+
+template <bool FAST>
+cudaError_t launch_sw128(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t threads = (n + 1) / 2;
+    const unsigned grid = (unsigned)((threads + kNT - 1) / kNT);
+    sw128_kernel<FAST, kNT, kMinBlocks><<<grid, kNT, sw128_smem_bytes<kNT>(), st>>>(d1, d2, dsc, n, prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_for(const SwParams& prm, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st)
+{
+    return prm.fast ? launch_sw128<true>(d1, d2, dsc, n, prm, st) : launch_sw128<false>(d1, d2, dsc, n, prm, st);
+}
+
+cudaError_t launch_unpack(const uint8_t* d_packed, uint8_t* d_codes, uint64_t n_seqs, cudaStream_t st)
+{
+    if (n_seqs == 0) return cudaSuccess;
+    const unsigned long long n_words = n_seqs * 8ull;   // 32 packed bytes = 8 words per sequence
+    const unsigned grid = (unsigned)((n_words + 255) / 256);
+    unpack2bit_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(d_packed), reinterpret_cast<uint4*>(d_codes), n_words);
+    return cudaGetLastError();
+}
+
+int setup_device(swb200_ctx* ctx, Device* d)
+{
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    SWB_CUDA(ctx, cudaGetDeviceProperties(&d->prop, d->id));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<true, kNT, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw128_smem_bytes<kNT>()));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<false, kNT, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw128_smem_bytes<kNT>()));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<true, kNT, kMinBlocks>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<false, kNT, kMinBlocks>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
+    for (Slot& s : d->slots) {
+        SWB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        SWB_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    return SWB200_OK;
+}
+
+// Device staging is allocated on first host-batch use, so a context that only ever
+// launches on caller-owned device arrays holds no large buffers.
+int ensure_staging(swb200_ctx* ctx, Device* d, bool packed)
+{
+    for (Slot& s : d->slots) {
+        if (!s.d_seq1) {
+            SWB_CUDA(ctx, cudaMalloc(&s.d_seq1, kChunkPairs * SWB200_SEQ_LEN));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_seq2, kChunkPairs * SWB200_SEQ_LEN));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_scores, kChunkPairs * sizeof(int32_t)));
+        }
+        if (packed && !s.d_pk1) {
+            SWB_CUDA(ctx, cudaMalloc(&s.d_pk1, kChunkPairs * 32));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_pk2, kChunkPairs * 32));
+        }
+    }
+    return SWB200_OK;
+}
+
+// One GPU's share [lo, hi) of a host batch: chunks of kChunkPairs cycle through kSlots
+// streams, so chunk c+1's H2D and chunk c-1's D2H run under chunk c's kernel.
+int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed,
+              const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi)
+{
+    if (hi <= lo) return SWB200_OK;
+    std::lock_guard<std::mutex> lock(d->mu);
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    int rc = ensure_staging(ctx, d, packed);
+    if (rc != SWB200_OK) return rc;
+    const size_t in_stride = packed ? 32 : SWB200_SEQ_LEN;
+    int si = 0;
+    for (uint64_t c0 = lo; c0 < hi; c0 += kChunkPairs, si = (si + 1) % kSlots) {
+        Slot& s = d->slots[si];
+        const uint64_t m = (hi - c0 < kChunkPairs) ? hi - c0 : kChunkPairs;
+        if (s.busy) SWB_CUDA(ctx, cudaEventSynchronize(s.done));
+        uint8_t* in1 = packed ? s.d_pk1 : s.d_seq1;
+        uint8_t* in2 = packed ? s.d_pk2 : s.d_seq2;
+        SWB_CUDA(ctx, cudaMemcpyAsync(in1, seq1 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(in2, seq2 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
+        if (packed) {
+            SWB_CUDA(ctx, launch_unpack(s.d_pk1, s.d_seq1, m, s.stream));
+            SWB_CUDA(ctx, launch_unpack(s.d_pk2, s.d_seq2, m, s.stream));
+            ctx->launches += 2;
+        }
+        SWB_CUDA(ctx, launch_for(prm, s.d_seq1, s.d_seq2, s.d_scores, m, s.stream));
+        ctx->launches += 1;
+        SWB_CUDA(ctx, cudaMemcpyAsync(scores + c0, s.d_scores, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        SWB_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+        s.busy = true;
+    }
+    for (Slot& s : d->slots)
+        if (s.busy) { SWB_CUDA(ctx, cudaEventSynchronize(s.done)); s.busy = false; }
+    return SWB200_OK;
+}
+
+int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, int gap, const void* out, uint64_t n)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    if (!sm) return fail(ctx, SWB200_ERR_ARG, "score_matrix is NULL");
+    if (n != 0 && (!a || !b || !out)) return fail(ctx, SWB200_ERR_ARG, "NULL array with n > 0");
+    const int dom = sw_check_domain(sm, gap);
+    if (dom == SW_DOMAIN_BAD_MATRIX) return fail(ctx, SWB200_ERR_DOMAIN, "score_matrix entry -128 is outside the reference's domain [-127,127]");
+    if (dom == SW_DOMAIN_BAD_GAP) return fail(ctx, SWB200_ERR_DOMAIN, "gap_penalty outside [0,127]");
+    return SWB200_OK;
+}
+
+int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool packed,
+               const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n)
+{
+    int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
+    if (rc != SWB200_OK || n == 0) return rc;
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    const size_t G = ctx->devs.size();
+    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, prm, scores, 0, n);
+    // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
+    // every GPU DMA-writes its own slice of `scores`: that is the whole gather.
+    std::vector<std::thread> pool;
+    std::vector<int> rcs(G, SWB200_OK);
+    for (size_t k = 0; k < G; ++k) {
+        const uint64_t lo = n * k / G, hi = n * (k + 1) / G;
+        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, prm, scores, lo, hi); });
+    }
+    for (auto& t : pool) t.join();
+    for (int r : rcs) if (r != SWB200_OK) return r;
+    return SWB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int swb200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail(nullptr, SWB200_ERR_NO_DEVICE, "cudaGetDeviceCount", e); return SWB200_ERR_NO_DEVICE; }
+    int usable = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++usable;
+    }
+    return usable;
+}
+
+int swb200_init(swb200_ctx** out, const int* devices, int n_devices)
+{
+    if (!out || n_devices < 0) return fail(nullptr, SWB200_ERR_ARG, "swb200_init: bad arguments");
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0)
+        return fail(nullptr, SWB200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)", e);
+    if (n_devices == 0) n_devices = visible;
+    if (n_devices > visible) return fail(nullptr, SWB200_ERR_NO_DEVICE, "more devices requested than visible");
+    swb200_ctx* ctx = new swb200_ctx;
+    for (int k = 0; k < n_devices; ++k) {
+        Device* d = new Device;
+        d->id = devices ? devices[k] : k;
+        ctx->devs.push_back(d);
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d->id);
+        int rc = (major == 10) ? setup_device(ctx, d)
+                               : fail(ctx, SWB200_ERR_NO_DEVICE, "device is not compute capability 10.x (kernels are sm_100a only)");
+        if (rc != SWB200_OK) {
+            g_init_error = ctx->err;
+            swb200_shutdown(ctx);
+            return rc;
+        }
+    }
+    *out = ctx;
+    return SWB200_OK;
+}
+
+void swb200_shutdown(swb200_ctx* ctx)
+{
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lock(ctx->tickets_mu);
+        for (auto& kv : ctx->tickets) { if (kv.second.first.joinable()) kv.second.first.join(); delete kv.second.second; }
+        ctx->tickets.clear();
+    }
+    for (Device* d : ctx->devs) {
+        cudaSetDevice(d->id);
+        for (Slot& s : d->slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            cudaFree(s.d_seq1); cudaFree(s.d_seq2); cudaFree(s.d_pk1); cudaFree(s.d_pk2); cudaFree(s.d_scores);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        cudaFree(d->d_bad);
+        delete d;
+    }
+    delete ctx;
+}
+
+int swb200_n_devices(const swb200_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+const char* swb200_last_error(const swb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+const char* swb200_strerror(int code)
+{
+    switch (code) {
+    case SWB200_OK: return "ok";
+    case SWB200_ERR_ARG: return "bad argument";
+    case SWB200_ERR_DOMAIN: return "score matrix or gap penalty outside the reference's domain";
+    case SWB200_ERR_NO_DEVICE: return "no usable sm_100 device";
+    case SWB200_ERR_CUDA: return "CUDA call failed";
+    case SWB200_ERR_NOMEM: return "out of memory";
+    case SWB200_ERR_TICKET: return "unknown ticket";
+    default: return "unknown error";
+    }
+}
+
+int swb200_alloc_pinned(void** ptr, size_t bytes)
+{
+    if (!ptr) return SWB200_ERR_ARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, SWB200_ERR_NOMEM, "cudaHostAlloc", e);
+    return SWB200_OK;
+}
+
+int swb200_free_pinned(void* ptr)
+{
+    if (!ptr) return SWB200_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? SWB200_OK : SWB200_ERR_CUDA;
+}
+
+int swb200_score_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n)
+{
+    return score_host(ctx, seq1, seq2, false, sm, gap, scores, n);
+}
+
+int swb200_score_batch_packed(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n)
+{
+    return score_host(ctx, seq1, seq2, true, sm, gap, scores, n);
+}
+
+int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* score)
+{
+    return score_host(ctx, seq1, seq2, false, sm, gap, score, 1);
+}
+
+int swb200_submit(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap,
+                  int32_t* scores, uint64_t n, swb200_ticket* ticket)
+{
+    if (!ticket) return ctx ? fail(ctx, SWB200_ERR_ARG, "ticket is NULL") : SWB200_ERR_ARG;
+    int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
+    if (rc != SWB200_OK) return rc;
+    int8_t sm_copy[16];
+    memcpy(sm_copy, sm, 16);
+    int* result = new int(SWB200_OK);
+    std::lock_guard<std::mutex> lock(ctx->tickets_mu);
+    const uint64_t id = ctx->next_ticket++;
+    std::thread th([=] {
+        int8_t m[16];
+        memcpy(m, sm_copy, 16);
+        *result = score_host(ctx, seq1, seq2, false, m, gap, scores, n);
+    });
+    ctx->tickets.emplace(id, std::make_pair(std::move(th), result));
+    *ticket = id;
+    return SWB200_OK;
+}
+
+int swb200_wait(swb200_ctx* ctx, swb200_ticket ticket)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    std::thread th;
+    int* result = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ctx->tickets_mu);
+        auto it = ctx->tickets.find(ticket);
+        if (it == ctx->tickets.end()) return fail(ctx, SWB200_ERR_TICKET, "unknown or already-waited ticket");
+        th = std::move(it->second.first);
+        result = it->second.second;
+        ctx->tickets.erase(it);
+    }
+    th.join();
+    const int rc = *result;
+    delete result;
+    return rc;
+}
+
+static int device_args(swb200_ctx* ctx, int device_index, const void* a, const void* b, const void* out, uint64_t n)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    if (n && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15u)) return fail(ctx, SWB200_ERR_ARG, "device arrays must be 16-byte aligned");
+    return SWB200_OK;
+}
+
+int swb200_score_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2,
+                              const int8_t* sm, int8_t gap, int32_t* d_scores, uint64_t n, void* cuda_stream)
+{
+    int rc = check_args(ctx, d_seq1, d_seq2, sm, gap, d_scores, n);
+    if (rc == SWB200_OK) rc = device_args(ctx, device_index, d_seq1, d_seq2, d_scores, n);
+    if (rc != SWB200_OK || n == 0) return rc;
+    SWB_CUDA(ctx, cudaSetDevice(ctx->devs[device_index]->id));
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    SWB_CUDA(ctx, launch_for(prm, d_seq1, d_seq2, d_scores, n, (cudaStream_t)cuda_stream));
+    ctx->launches += 1;
+    return SWB200_OK;
+}
+
+int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const uint8_t* d_pk1, const uint8_t* d_pk2,
+                                     const int8_t* sm, int8_t gap, int32_t* d_scores, uint64_t n, void* cuda_stream)
+{
+    int rc = check_args(ctx, d_pk1, d_pk2, sm, gap, d_scores, n);
+    if (rc == SWB200_OK) rc = device_args(ctx, device_index, d_pk1, d_pk2, d_scores, n);
+    if (rc != SWB200_OK || n == 0) return rc;
+    Device* d = ctx->devs[device_index];
+    std::lock_guard<std::mutex> lock(d->mu);
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    rc = ensure_staging(ctx, d, false);
+    if (rc != SWB200_OK) return rc;
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    // Stream-ordered: unpack a chunk into slot 0's byte staging, score it, next chunk.
+    Slot& s = d->slots[0];
+    for (uint64_t c0 = 0; c0 < n; c0 += kChunkPairs) {
+        const uint64_t m = (n - c0 < kChunkPairs) ? n - c0 : kChunkPairs;
+        SWB_CUDA(ctx, launch_unpack(d_pk1 + c0 * 32, s.d_seq1, m, st));
+        SWB_CUDA(ctx, launch_unpack(d_pk2 + c0 * 32, s.d_seq2, m, st));
+        SWB_CUDA(ctx, launch_for(prm, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
+        ctx->launches += 3;
+    }
+    return SWB200_OK;
+}
+
+int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_t* d_codes, uint64_t n_bytes,
+                                 uint64_t* n_bad, void* cuda_stream)
+{
+    if (!ctx || !n_bad) return SWB200_ERR_ARG;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    Device* d = ctx->devs[device_index];
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    SWB_CUDA(ctx, cudaMemsetAsync(d->d_bad, 0, sizeof(unsigned long long), st));
+    if (n_bytes) {
+        count_bad_codes_kernel<<<d->prop.multiProcessorCount * 8, 256, 0, st>>>(d_codes, n_bytes, d->d_bad);
+        SWB_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    unsigned long long h = 0;
+    SWB_CUDA(ctx, cudaMemcpyAsync(&h, d->d_bad, sizeof h, cudaMemcpyDeviceToHost, st));
+    SWB_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_bad = h;
+    return SWB200_OK;
+}
+
+int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, int8_t gap, swb200_kernel_info* info)
+{
+    if (!ctx || !info || !sm) return SWB200_ERR_ARG;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return fail(ctx, SWB200_ERR_DOMAIN, "matrix/gap outside the domain");
+    Device* d = ctx->devs[device_index];
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    cudaFuncAttributes fa{};
+    int blocks = 0;
+    if (prm.fast) {
+        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sw128_kernel<true, kNT, kMinBlocks>));
+        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sw128_kernel<true, kNT, kMinBlocks>, kNT, sw128_smem_bytes<kNT>()));
+    } else {
+        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sw128_kernel<false, kNT, kMinBlocks>));
+        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sw128_kernel<false, kNT, kMinBlocks>, kNT, sw128_smem_bytes<kNT>()));
+    }
+    info->fast_path = prm.fast;
+    info->regs_per_thread = fa.numRegs;
+    info->threads_per_block = kNT;
+    info->blocks_per_sm = blocks;
+    info->smem_bytes_per_block = (int)sw128_smem_bytes<kNT>();
+    info->sm_count = d->prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->id);
+    info->sm_clock_khz = khz;
+    return SWB200_OK;
+}
+
+uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int swb200_set_force_general(swb200_ctx* ctx, int on)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    ctx->force_general = on ? 1 : 0;
+    return SWB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,332 @@
+"""Python host side of swb200: a ctypes binding of include/swb200.h.
+
+It mirrors the reference's interface for the hot path -- the per-pair call
+`SmithWaterman_simdN(seq1, seq2, score_matrix, gap_penalty) -> int`
+(/root/reference/source.cpp:462-466) and the batch loop its harnesses run
+(source.cpp:2947-2970) -- on top of the C ABI.  torch is used for device memory and
+streams only.  Nothing here computes a score on the CPU: if libswb200.so or a B200 is
+missing, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libswb200.so")
+SEQ_LEN = 128
+
+# reference harness constants
+MATRIX_SPEEDTEST = (10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10)  # source.cpp:3041-3045
+GAP_SPEEDTEST = 15                                                                           # source.cpp:3046
+MATRIX_111 = (1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1)                    # source.cpp:3202-3206
+GAP_111 = 1                                                                                  # source.cpp:3207
+
+# every symbol include/swb200.h declares (tests check the .so exports each one)
+ABI_SYMBOLS = (
+    "swb200_device_count", "swb200_init", "swb200_shutdown", "swb200_n_devices", "swb200_last_error",
+    "swb200_strerror", "swb200_alloc_pinned", "swb200_free_pinned", "swb200_score_pair",
+    "swb200_score_batch", "swb200_score_batch_packed", "swb200_submit", "swb200_wait",
+    "swb200_score_batch_device", "swb200_score_batch_packed_device", "swb200_validate_codes_device",
+    "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
+    "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
+    "swb200_fnv1a64_i32",
+)
+
+ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
+
+
+class SwbError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"swb200 error {code}: {text}")
+        self.code = code
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [("fast_path", C.c_int), ("regs_per_thread", C.c_int), ("threads_per_block", C.c_int),
+                ("blocks_per_sm", C.c_int), ("smem_bytes_per_block", C.c_int), ("sm_count", C.c_int),
+                ("sm_clock_khz", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libswb200.so (no CUDA call is made by loading)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `python smith-waterman-simd_b200/build.py` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    lib.swb200_device_count.restype = i32
+    lib.swb200_init.restype = i32
+    lib.swb200_init.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32]
+    lib.swb200_shutdown.restype = None
+    lib.swb200_shutdown.argtypes = [vp]
+    lib.swb200_n_devices.restype = i32
+    lib.swb200_n_devices.argtypes = [vp]
+    lib.swb200_last_error.restype = C.c_char_p
+    lib.swb200_last_error.argtypes = [vp]
+    lib.swb200_strerror.restype = C.c_char_p
+    lib.swb200_strerror.argtypes = [i32]
+    lib.swb200_alloc_pinned.restype = i32
+    lib.swb200_alloc_pinned.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.swb200_free_pinned.restype = i32
+    lib.swb200_free_pinned.argtypes = [vp]
+    lib.swb200_score_pair.restype = i32
+    lib.swb200_score_pair.argtypes = [vp, vp, vp, vp, C.c_int8, vp]
+    for name in ("swb200_score_batch", "swb200_score_batch_packed"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64]
+    lib.swb200_submit.restype = i32
+    lib.swb200_submit.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64, C.POINTER(u64)]
+    lib.swb200_wait.restype = i32
+    lib.swb200_wait.argtypes = [vp, u64]
+    for name in ("swb200_score_batch_device", "swb200_score_batch_packed_device"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, i32, vp, vp, vp, C.c_int8, vp, u64, vp]
+    lib.swb200_validate_codes_device.restype = i32
+    lib.swb200_validate_codes_device.argtypes = [vp, i32, vp, u64, C.POINTER(u64), vp]
+    lib.swb200_kernel_info_for.restype = i32
+    lib.swb200_kernel_info_for.argtypes = [vp, i32, vp, C.c_int8, C.POINTER(KernelInfo)]
+    lib.swb200_launch_count.restype = u64
+    lib.swb200_launch_count.argtypes = [vp]
+    lib.swb200_set_force_general.restype = i32
+    lib.swb200_set_force_general.argtypes = [vp, i32]
+    lib.swb200_gen_reference_stream.restype = i32
+    lib.swb200_gen_reference_stream.argtypes = [u64, u64, vp, vp]
+    for name in ("swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [u64, u64, u64, vp, vp, i32]
+    lib.swb200_fnv1a64_i32.restype = u64
+    lib.swb200_fnv1a64_i32.argtypes = [vp, u64]
+    _lib = lib
+    return lib
+
+
+def _matrix(score_matrix) -> np.ndarray:
+    m = np.ascontiguousarray(np.asarray(score_matrix).reshape(-1))
+    if m.size != 16:
+        raise ValueError("score_matrix must have 16 entries (4x4, index seq1*4+seq2)")
+    if m.min() < -128 or m.max() > 127:
+        raise ValueError("score_matrix entries must fit int8")
+    return m.astype(np.int8)
+
+
+def _gap(gap_penalty) -> int:
+    g = int(gap_penalty)
+    if g < -128 or g > 127:
+        raise SwbError(ERR_DOMAIN, "gap_penalty does not fit the reference's int8 argument")
+    return g
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory from swb200_alloc_pinned."""
+
+    def __init__(self, shape, dtype):
+        lib = load_library()
+        self._lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = lib.swb200_alloc_pinned(C.byref(p), self.nbytes)
+        if rc != 0:
+            raise SwbError(rc, lib.swb200_last_error(None).decode())
+        self._ptr = p
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            self._lib.swb200_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """Owns the library handle: streams, staging buffers and the per-GPU workers."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, n_devices: int = 1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._lib.swb200_init(C.byref(self._h), arr, len(devices))
+        else:
+            rc = self._lib.swb200_init(C.byref(self._h), None, n_devices)
+        if rc != 0:
+            raise SwbError(rc, self._lib.swb200_last_error(None).decode() or self._lib.swb200_strerror(rc).decode())
+
+    # -- plumbing
+    def close(self):
+        if self._h:
+            self._lib.swb200_shutdown(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SwbError(rc, self._lib.swb200_last_error(self._h).decode() or self._lib.swb200_strerror(rc).decode())
+
+    @property
+    def n_devices(self) -> int:
+        return self._lib.swb200_n_devices(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.swb200_launch_count(self._h))
+
+    def set_force_general(self, on: bool):
+        self._check(self._lib.swb200_set_force_general(self._h, int(on)))
+
+    def kernel_info(self, score_matrix, gap_penalty, device_index: int = 0) -> dict:
+        m = _matrix(score_matrix)
+        info = KernelInfo()
+        self._check(self._lib.swb200_kernel_info_for(self._h, device_index, m.ctypes.data, _gap(gap_penalty), C.byref(info)))
+        return {k: getattr(info, k) for k, _ in KernelInfo._fields_}
+
+    # -- the reference's per-pair call (source.cpp:462-466)
+    def smith_waterman(self, seq1, seq2, score_matrix, gap_penalty) -> int:
+        a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(-1)
+        b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(-1)
+        if a.size != SEQ_LEN or b.size != SEQ_LEN:
+            raise ValueError("sequences must hold exactly 128 codes (std::array<uint8_t,128>)")
+        m = _matrix(score_matrix)
+        out = np.zeros(1, dtype=np.int32)
+        self._check(self._lib.swb200_score_pair(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data))
+        return int(out[0])
+
+    # -- the batch loop (source.cpp:2947-2970), host arrays
+    def score_batch(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty,
+                    out: Optional[np.ndarray] = None, packed: bool = False) -> np.ndarray:
+        width = 32 if packed else SEQ_LEN
+        a = np.ascontiguousarray(seq1, dtype=np.uint8)
+        b = np.ascontiguousarray(seq2, dtype=np.uint8)
+        if a.ndim != 2 or a.shape[1] != width or a.shape != b.shape:
+            raise ValueError(f"seq1 and seq2 must both be uint8 [n][{width}]")
+        n = a.shape[0]
+        m = _matrix(score_matrix)
+        if out is None:
+            out = np.empty(n, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size >= n and out.flags.c_contiguous
+        fn = self._lib.swb200_score_batch_packed if packed else self._lib.swb200_score_batch
+        self._check(fn(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n))
+        return out[:n]
+
+    def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray) -> int:
+        assert seq1.flags.c_contiguous and seq2.flags.c_contiguous and out.flags.c_contiguous
+        assert seq1.dtype == np.uint8 and seq2.dtype == np.uint8 and out.dtype == np.int32
+        m = _matrix(score_matrix)
+        t = C.c_uint64()
+        self._check(self._lib.swb200_submit(self._h, seq1.ctypes.data, seq2.ctypes.data, m.ctypes.data, _gap(gap_penalty),
+                                            out.ctypes.data, seq1.shape[0], C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int):
+        self._check(self._lib.swb200_wait(self._h, ticket))
+
+    # -- device-resident arrays (torch tensors on the context's GPU `device_index`)
+    def score_batch_device(self, d_seq1, d_seq2, score_matrix, gap_penalty, d_scores, n: Optional[int] = None,
+                           device_index: int = 0, stream: Optional[int] = None, packed: bool = False):
+        import torch
+        if n is None:
+            n = d_seq1.shape[0]
+        m = _matrix(score_matrix)
+        if stream is None:
+            stream = torch.cuda.current_stream(d_seq1.device).cuda_stream
+        fn = self._lib.swb200_score_batch_packed_device if packed else self._lib.swb200_score_batch_device
+        self._check(fn(self._h, device_index, d_seq1.data_ptr(), d_seq2.data_ptr(), m.ctypes.data, _gap(gap_penalty),
+                       d_scores.data_ptr(), n, stream))
+        return d_scores
+
+    def count_bad_codes_device(self, d_codes, device_index: int = 0) -> int:
+        import torch
+        bad = C.c_uint64()
+        stream = torch.cuda.current_stream(d_codes.device).cuda_stream
+        self._check(self._lib.swb200_validate_codes_device(self._h, device_index, d_codes.data_ptr(), d_codes.numel(), C.byref(bad), stream))
+        return int(bad.value)
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(n_devices=1)
+    return _default_ctx
+
+
+def SmithWaterman_b200(seq1, seq2, score_matrix, gap_penalty) -> int:
+    """Drop-in for the reference's per-pair call (same argument order and meaning)."""
+    return default_context().smith_waterman(seq1, seq2, score_matrix, gap_penalty)
+
+
+# ------------------------------------------------------------------ synthetic pairs
+def reference_stream(n: int, seed: int = 10000, out=None):
+    """Pairs [0,n) of the reference's own test stream (source.cpp:2944-2953)."""
+    lib = load_library()
+    a, b = out if out is not None else (np.empty((n, SEQ_LEN), np.uint8), np.empty((n, SEQ_LEN), np.uint8))
+    rc = lib.swb200_gen_reference_stream(seed, n, a.ctypes.data, b.ctypes.data)
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_reference_stream")
+    return a, b
+
+
+def counter_pairs(first: int, n: int, seed: int = 10000, packed: bool = False, out=None, threads: int = 0):
+    """Pairs [first, first+n) of the counter-based stream: pair k depends only on (seed, k),
+    so any index range can be produced by any worker or rank."""
+    lib = load_library()
+    width = 32 if packed else SEQ_LEN
+    a, b = out if out is not None else (np.empty((n, width), np.uint8), np.empty((n, width), np.uint8))
+    assert a.shape == (n, width) and b.shape == (n, width) and a.flags.c_contiguous and b.flags.c_contiguous
+    fn = lib.swb200_gen_counter_pairs_packed if packed else lib.swb200_gen_counter_pairs
+    rc = fn(seed, first, n, a.ctypes.data, b.ctypes.data, threads or min(os.cpu_count() or 1, 16))
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_counter_pairs")
+    return a, b
+
+
+def fnv1a64(scores: np.ndarray) -> int:
+    s = np.ascontiguousarray(scores, dtype=np.int32)
+    return int(load_library().swb200_fnv1a64_i32(s.ctypes.data, s.size))
+
+
+def counter_pairs_numpy(first: int, n: int, seed: int = 10000):
+    """The same stream restated in numpy (used by tests to pin the C++ generator)."""
+    k = (np.arange(first, first + n, dtype=np.uint64)[:, None] * np.uint64(8) + np.arange(8, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        x = k + np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+        x = (x + np.uint64(0x9E3779B97F4A7C15))
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, None, :]
+    codes = ((x[:, :, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(n, 256)
+    return np.ascontiguousarray(codes[:, :128]), np.ascontiguousarray(codes[:, 128:])

@@ -1,0 +1,40 @@
+// tests/emu/emu_main.cpp -- TEST TOOL.  Compiles the kernel's per-thread algorithm
+// (csrc/sw_core.cuh) for the HOST with emulated packed instructions and runs it over a
+// batch, so that the algorithm (offset frames, wrap, FIFO re-basing, selectors) can be
+// validated against the oracle in a container without a GPU.  Never shipped, never
+// loaded by the product; the product's only compute path is the CUDA kernel.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "sw_params.h"
+
+using namespace swb;
+
+struct HostFifo {
+    uint32_t w[SW_L];
+    uint32_t pop(int c) const { return w[c & (SW_L - 1)]; }
+    void push(int c, uint32_t v) { w[c & (SW_L - 1)] = v; }
+};
+struct HostTable {
+    const uint32_t* t;
+    uint32_t operator()(uint32_t byte_off) const { return t[byte_off >> 2]; }
+};
+
+extern "C" int swemu_score_batch(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap,
+                                 int32_t* scores, uint64_t n, int force_general)
+{
+    if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return -1;
+    const SwParams prm = sw_make_params(sm, gap, force_general);
+    HostTable t4{prm.t4};
+    for (uint64_t p = 0; p < n; p += 2) {
+        const uint64_t q = (p + 1 < n) ? p + 1 : p;
+        HostFifo fifo;
+        int32_t lo, hi;
+        if (prm.fast) sw128_two_pairs<true>(seq1 + p * 128, seq1 + q * 128, seq2 + p * 128, seq2 + q * 128, fifo, t4, prm, lo, hi);
+        else          sw128_two_pairs<false>(seq1 + p * 128, seq1 + q * 128, seq2 + p * 128, seq2 + q * 128, fifo, t4, prm, lo, hi);
+        scores[p] = lo;
+        if (q != p) scores[q] = hi;
+    }
+    return prm.fast;
+}

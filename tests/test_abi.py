@@ -1,0 +1,108 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/swb200.h declares; host-side argument handling fails loudly.  No compute call is
+made here (there is no GPU and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "swb200.h")
+
+
+@pytest.fixture(scope="module")
+def lib(swb):
+    import build as swb_build   # smith-waterman-simd_b200/build.py
+    swb_build.build()
+    return swb.load_library()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(swb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(swb):
+    assert declared_symbols() == sorted(swb.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_symbols():
+        assert getattr(lib, name) is not None, name
+    out = subprocess.run(["nm", "-D", "--defined-only", lib._name], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (swb200_[a-z0-9_]+)", out))
+    assert exported == set(declared_symbols())
+
+
+def test_library_is_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib._name], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_kernel_uses_packed_int16_instructions(lib):
+    out = subprocess.run(["cuobjdump", "-sass", lib._name], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = out.stdout
+    for mnemonic in ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "PRMT"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA" not in sass and "UTC" not in sass   # no tensor cores: this is not a contraction
+
+
+def test_strerror_and_no_device_is_loud(lib, swb):
+    assert lib.swb200_strerror(0) == b"ok"
+    assert b"domain" in lib.swb200_strerror(swb.ERR_DOMAIN)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the no-device error path is for the CPU container")
+    with pytest.raises(swb.SwbError) as e:
+        swb.Context(n_devices=1)
+    assert e.value.code == swb.ERR_NO_DEVICE
+    with pytest.raises(swb.SwbError):
+        swb.SmithWaterman_b200(np.zeros(128, np.uint8), np.zeros(128, np.uint8), swb.MATRIX_SPEEDTEST, 15)
+
+
+def test_host_argument_checks(swb):
+    with pytest.raises(ValueError):
+        swb._matrix([1, 2, 3])
+    with pytest.raises(ValueError):
+        swb._matrix([300] * 16)
+    with pytest.raises(swb.SwbError):
+        swb._gap(200)
+
+
+def test_counter_pairs_are_index_addressable(swb):
+    a, b = swb.counter_pairs(0, 1000)
+    a2, b2 = swb.counter_pairs(250, 500)
+    assert np.array_equal(a[250:750], a2) and np.array_equal(b[250:750], b2)
+    assert a.max() == 3 and a.min() == 0
+    hist = np.bincount(np.concatenate([a.ravel(), b.ravel()]), minlength=4) / (a.size + b.size)
+    assert np.all(np.abs(hist - 0.25) < 0.01)
+    assert not np.array_equal(a, b)
+
+
+def test_params_derivation_matches_documented_domain():
+    # sw_params.h through the host emulator build: rc = 1 fast, 0 general, -1 refused
+    lib_path = os.path.join(ROOT, "tests", "emu", "libswemu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{os.path.join(ROOT, 'smith-waterman-simd_b200', 'csrc')}",
+                    "-o", lib_path, os.path.join(ROOT, "tests", "emu", "emu_main.cpp")], check=True)
+    emu = C.CDLL(lib_path)
+    emu.swemu_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    z = np.zeros((2, 128), np.uint8)
+    out = np.zeros(2, np.int32)
+
+    def path(sm, g):
+        m = np.asarray(sm, dtype=np.int8)
+        return emu.swemu_score_batch(z.ctypes.data, z.ctypes.data, m.ctypes.data, g, out.ctypes.data, 2, 0)
+    mm = lambda m, x: [m if i == j else x for i in range(4) for j in range(4)]
+    assert path(mm(10, -30), 15) == 1 and path(mm(1, -1), 1) == 1
+    assert path(mm(127, -127), 127) == 0
+    assert path(mm(10, -128), 15) == -1      # -128 is outside the reference's domain (source.cpp:492)
+    assert path(mm(10, -30), -1) == -1

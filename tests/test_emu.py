@@ -1,0 +1,71 @@
+"""CPU tests of the KERNEL'S ALGORITHM: csrc/sw_core.cuh compiled for the host with emulated
+packed instructions (tests/emu) must equal the oracle.  This validates the offset frames,
+the strip wrap, the FIFO re-basing and the PRMT selectors without a GPU; the GPU parity
+tests (test_parity_gpu.py) then validate the real instructions."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_SRC = os.path.join(ROOT, "tests", "emu", "emu_main.cpp")
+EMU_LIB = os.path.join(ROOT, "tests", "emu", "libswemu.so")
+CSRC = os.path.join(ROOT, "smith-waterman-simd_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{CSRC}", "-o", EMU_LIB, EMU_SRC], check=True)
+    lib = C.CDLL(EMU_LIB)
+    lib.swemu_score_batch.restype = C.c_int
+    lib.swemu_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+
+    def run(a, b, sm, gap, force_general=0):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        m = np.asarray(sm, dtype=np.int8)
+        out = np.empty(a.shape[0], dtype=np.int32)
+        rc = lib.swemu_score_batch(a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], force_general)
+        assert rc >= 0
+        return rc, out
+    return run
+
+
+def test_emu_structured_all_param_sets(emu, golden):
+    z = golden["structured_npz"]
+    fast_seen = general_seen = 0
+    for ps in golden["structured"]["param_sets"]:
+        exp = z[ps["name"]].astype(np.int32)
+        for force_general in (0, 1):
+            path, got = emu(z["seq1"], z["seq2"], ps["matrix"], ps["gap"], force_general)
+            assert np.array_equal(got, exp), (ps["name"], "fast" if path else "general")
+            fast_seen += path
+            general_seen += 1 - path
+    assert fast_seen >= 5 and general_seen >= 5   # both kernels' algorithms were exercised
+
+
+def test_emu_reference_stream(emu, oracle):
+    a, b = oracle.reference_stream(4097)   # odd count: the last thread scores one pair
+    for sm, g in ((oracle.MATRIX_SPEEDTEST, 15), (oracle.MATRIX_111, 1)):
+        exp = oracle.score_batch(a, b, sm, g, threads=os.cpu_count())
+        _, got = emu(a, b, sm, g)
+        assert np.array_equal(got, exp)
+
+
+def test_emu_fast_path_domain_boundary(emu, oracle):
+    # parameter sets on both sides of the fast/general switch in sw_params.h
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 4, (64, 128), dtype=np.uint8)
+    b = a.copy()
+    b[:, 40:] = rng.integers(0, 4, (64, 88), dtype=np.uint8)
+    b[:8] = a[:8]
+
+    def mm(m, x):
+        return [m if i == j else x for i in range(4) for j in range(4)]
+    for sm, g, want_fast in ((mm(11, -90), 30, 1), (mm(12, -90), 30, 0), (mm(97, -100), 15, 1), (mm(98, -100), 15, 0),
+                             (mm(1, -127), 31, 1), (mm(1, -127), 32, 0), (mm(127, -127), 0, 1)):
+        path, got = emu(a, b, sm, g)
+        assert path == want_fast, (sm[0], g)
+        assert np.array_equal(got, oracle.score_batch(a, b, sm, g)), (sm[0], g)

@@ -1,0 +1,93 @@
+"""CPU tests: the oracle is pinned against the reference's known answers,
+against the committed golden fixtures, and -- where oracle/_ref was built -- against the
+unmodified reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+N_STREAM = 100_000
+
+
+@pytest.fixture(scope="module")
+def stream(oracle):
+    return oracle.reference_stream(N_STREAM)
+
+
+def test_stream_matches_survey_head(oracle, stream, golden):
+    a, b = stream
+    rs = golden["reference_stream"]
+    assert a[0, :8].tolist() == rs["pair0_seq1_head"] == [2, 2, 2, 0, 1, 2, 2, 3]
+    assert b[0, :8].tolist() == rs["pair0_seq2_head"] == [0, 3, 2, 0, 3, 0, 0, 3]
+    assert a.max() <= 3 and b.max() <= 3
+
+
+def test_known_answers_speedtest_matrix(oracle, stream, golden):
+    # first 16 scores, and sum/min/max/argmax/FNV of the first 100 000
+    a, b = stream
+    s = oracle.score_batch(a, b, oracle.MATRIX_SPEEDTEST, oracle.GAP_SPEEDTEST, threads=os.cpu_count())
+    assert s[:16].tolist() == [80, 80, 70, 95, 70, 80, 80, 75, 80, 70, 75, 65, 65, 80, 100, 70]
+    assert int(s.sum()) == 7_550_735 and int(s.min()) == 50 and int(s.max()) == 195
+    assert int(np.argmax(s)) == 28971
+    assert f"{oracle.fnv1a64(s):016x}" == "ca3723235bbaa0fc"
+    g = golden["reference_stream"]["sets"]["speedtest_10_-30_15"]["100000"]
+    assert g == {"sum": 7550735, "min": 50, "max": 195, "argmax": 28971, "fnv1a64": "ca3723235bbaa0fc"}
+
+
+def test_known_answers_111_matrix(oracle, stream, golden):
+    a, b = stream
+    s = oracle.score_batch(a, b, oracle.MATRIX_111, oracle.GAP_111, threads=os.cpu_count())
+    g = golden["reference_stream"]["sets"]["x32_1_-1_1"]
+    assert s[:16].tolist() == g["first16"]
+    assert int(s.sum()) == g["100000"]["sum"]
+    assert f"{oracle.fnv1a64(s):016x}" == g["100000"]["fnv1a64"]
+
+
+def test_first4096_fixture(oracle, stream):
+    a, b = stream
+    for name, sm, gp in (("speedtest_10_-30_15", oracle.MATRIX_SPEEDTEST, 15), ("x32_1_-1_1", oracle.MATRIX_111, 1)):
+        exp = np.load(os.path.join(os.path.dirname(__file__), "golden", f"stream_first4096_{name}.npy")).astype(np.int32)
+        got = oracle.score_batch(a[:4096], b[:4096], sm, gp)
+        assert np.array_equal(got, exp)
+
+
+def test_structured_fixture_all_param_sets(oracle, golden):
+    z = golden["structured_npz"]
+    a, b = z["seq1"], z["seq2"]
+    for ps in golden["structured"]["param_sets"]:
+        got = oracle.score_batch(a, b, ps["matrix"], ps["gap"], threads=os.cpu_count())
+        assert np.array_equal(got, z[ps["name"]].astype(np.int32)), ps["name"]
+
+
+def test_port_equals_reference_build(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here (no /root/reference and no prebuilt file)")
+    a, b = oracle.reference_stream(3000)
+    a2, b2 = oracle.reference_stream(3000, use_ref=True)   # std::uniform_int_distribution itself
+    assert np.array_equal(a, a2) and np.array_equal(b, b2)
+    exp = oracle.ref_score_batch(0, a, b, oracle.MATRIX_SPEEDTEST, 15)
+    assert np.array_equal(oracle.score_batch(a, b, oracle.MATRIX_SPEEDTEST, 15), exp)
+    for v in range(1, 10):   # the reference's own differential test, source.cpp:2961-2979
+        assert np.array_equal(oracle.ref_score_batch(v, a, b, oracle.MATRIX_SPEEDTEST, 15), exp), v
+
+
+def test_pack_unpack_roundtrip(oracle):
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 4, (257, 128), dtype=np.uint8)
+    packed = oracle.pack2bit(codes)
+    assert packed.shape == (257, 32)
+    assert np.array_equal(oracle.unpack2bit(packed), codes)
+    # layout of source.cpp:1580-1583: dest[i*4+j] = (src[i] >> 2j) & 3
+    i, j = 5, 2
+    assert codes[0, i * 4 + j] == (packed[0, i] >> (2 * j)) & 3
+    if oracle.have_ref():
+        import ctypes as C
+        out = np.empty(128, dtype=np.uint8)
+        oracle.ref().swref_unpack(packed[7].ctypes.data_as(C.POINTER(C.c_uint8)), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert np.array_equal(out, codes[7])
+
+
+def test_rectangular_and_long(oracle):
+    # the templated-length restatement used by the length sweep (config 4): L=256 identical pair
+    a = np.tile(np.arange(4, dtype=np.uint8), 64)[None, :]
+    assert oracle.score_batch(a, a, oracle.MATRIX_SPEEDTEST, 15)[0] == 2560

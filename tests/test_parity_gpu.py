@@ -1,0 +1,205 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every score comes out of the CUDA
+kernel THROUGH THE C ABI (libswb200.so via ctypes) and is compared bit-exactly with
+  * the committed golden fixtures (generated from the unmodified reference),
+  * the oracle (oracle/sw_oracle.c) on the same seeded inputs,
+  * the reference build itself (oracle/_ref) where it travelled with the snapshot,
+and, at the full 1 M-pair size of BASELINE.json's configs[1], with the checksum the
+reference's scalar kernel produces (FNV-1a-64 ae56a1e6a1d57492)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NCPU = os.cpu_count() or 1
+
+
+def mm(match, mismatch):
+    return [match if i == j else mismatch for i in range(4) for j in range(4)]
+
+
+def test_extension_is_loaded_and_targets_b200(ctx, swb):
+    import torch
+    assert torch.cuda.is_available()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    info = ctx.kernel_info(swb.MATRIX_SPEEDTEST, swb.GAP_SPEEDTEST)
+    assert info["fast_path"] == 1 and info["sm_count"] >= 100 and info["blocks_per_sm"] >= 1
+    assert ctx.kernel_info(mm(127, -127), 127)["fast_path"] == 0
+
+
+def test_per_pair_call_matches_known_answers(ctx, swb, oracle):
+    # the reference's per-pair signature (source.cpp:462-466) on the first pairs of its stream
+    a, b = oracle.reference_stream(16)
+    got = [ctx.smith_waterman(a[i], b[i], swb.MATRIX_SPEEDTEST, swb.GAP_SPEEDTEST) for i in range(16)]
+    assert got == [80, 80, 70, 95, 70, 80, 80, 75, 80, 70, 75, 65, 65, 80, 100, 70]
+    assert swb.SmithWaterman_b200(a[3], b[3], swb.MATRIX_SPEEDTEST, 15) == 95
+
+
+def test_first4096_golden_both_matrices(ctx, swb, oracle):
+    a, b = oracle.reference_stream(4096)
+    for name, sm, g in (("speedtest_10_-30_15", swb.MATRIX_SPEEDTEST, 15), ("x32_1_-1_1", swb.MATRIX_111, 1)):
+        exp = np.load(os.path.join(os.path.dirname(__file__), "golden", f"stream_first4096_{name}.npy")).astype(np.int32)
+        assert np.array_equal(ctx.score_batch(a, b, sm, g), exp), name
+
+
+def test_structured_golden_all_param_sets_both_kernels(ctx, golden):
+    z = golden["structured_npz"]
+    launches0 = ctx.launch_count
+    try:
+        for force_general in (False, True):
+            ctx.set_force_general(force_general)
+            for ps in golden["structured"]["param_sets"]:
+                got = ctx.score_batch(z["seq1"], z["seq2"], ps["matrix"], ps["gap"])
+                assert np.array_equal(got, z[ps["name"]].astype(np.int32)), (ps["name"], force_general)
+    finally:
+        ctx.set_force_general(False)
+    assert ctx.launch_count - launches0 == 2 * len(golden["structured"]["param_sets"])
+
+
+def test_full_1m_batch_checksum(ctx, swb, oracle, golden):
+    # BASELINE.json configs[1]: the 1 M-pair batch, bit-exact vs reference scalar/simd4/simd9
+    n = 1_000_000
+    a, b = oracle.reference_stream(n)
+    for name, sm, g in (("speedtest_10_-30_15", swb.MATRIX_SPEEDTEST, 15), ("x32_1_-1_1", swb.MATRIX_111, 1)):
+        s = ctx.score_batch(a, b, sm, g)
+        gold = golden["reference_stream"]["sets"][name]["1000000"]
+        assert int(s.sum()) == gold["sum"] and int(s.min()) == gold["min"] and int(s.max()) == gold["max"]
+        assert int(np.argmax(s)) == gold["argmax"]
+        assert f"{oracle.fnv1a64(s):016x}" == gold["fnv1a64"]
+    assert golden["reference_stream"]["sets"]["speedtest_10_-30_15"]["1000000"]["fnv1a64"] == "ae56a1e6a1d57492"
+    # element-wise against the reference's own AVX2 kernels where the build travelled
+    if oracle.have_ref():
+        s = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+        for variant in (4, 9):
+            assert np.array_equal(s, oracle.ref_score_batch(variant, a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)), variant
+
+
+def test_general_kernel_on_stream(ctx, swb, oracle):
+    a, b = oracle.reference_stream(20_000)
+    exp = oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)
+    ctx.set_force_general(True)
+    try:
+        assert np.array_equal(ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15), exp)
+    finally:
+        ctx.set_force_general(False)
+    # out-of-fast-domain parameters take the general kernel on their own
+    sm = mm(127, -127)
+    assert np.array_equal(ctx.score_batch(a[:5000], b[:5000], sm, 127), oracle.score_batch(a[:5000], b[:5000], sm, 127, threads=NCPU))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 127, 128, 255, 256, 257, 1023])
+def test_ragged_batch_sizes(ctx, swb, oracle, n):
+    a, b = swb.counter_pairs(77, n)
+    got = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    assert got.shape == (n,)
+    if n:
+        assert np.array_equal(got, oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15))
+
+
+def test_multi_chunk_batch_with_pinned_buffers(ctx, swb, oracle):
+    # > 2 chunks of 131072 pairs so that every staging slot is reused; pinned in, pinned out
+    n = 3 * 131072 + 12345
+    a, b = swb.counter_pairs(5_000_000, n)
+    pa, pb, ps = swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n,), np.int32)
+    pa.array[:] = a
+    pb.array[:] = b
+    got = ctx.score_batch(pa.array, pb.array, swb.MATRIX_SPEEDTEST, 15, out=ps.array)
+    sample = np.r_[0:4096, n - 4096:n, np.arange(0, n, 997)]
+    assert np.array_equal(got[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+    # property at full size: the batch result is a pure function of each pair (order-independent)
+    perm = np.random.default_rng(5).permutation(n)[:200_000]
+    again = ctx.score_batch(a[perm], b[perm], swb.MATRIX_SPEEDTEST, 15)
+    assert np.array_equal(again, got[perm])
+    for p in (pa, pb, ps):
+        p.free()
+
+
+def test_domain_properties_at_scale(ctx, swb):
+    # size-independent properties on 300 000 pairs (no oracle needed)
+    n = 300_000
+    a, b = swb.counter_pairs(123, n)
+    s = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    # identical sequences: 128 matches
+    assert np.all(ctx.score_batch(a, a, swb.MATRIX_SPEEDTEST, 15) == 1280)
+    # symmetric matrix: swapping the roles of seq1 and seq2 transposes the table
+    assert np.array_equal(ctx.score_batch(b, a, swb.MATRIX_SPEEDTEST, 15), s)
+    # reversing both sequences reverses every alignment
+    assert np.array_equal(ctx.score_batch(a[:, ::-1].copy(), b[:, ::-1].copy(), swb.MATRIX_SPEEDTEST, 15), s)
+    # scaling matrix and gap by k scales the score by k (also crosses fast -> general kernel)
+    assert np.array_equal(ctx.score_batch(a, b, mm(2, -6), 3) * 5, s)
+    assert np.array_equal(ctx.score_batch(a, b, mm(40, -120), 60), s * 4)
+    # relabelling the alphabet with a permutation leaves a match/mismatch score unchanged
+    perm = np.array([2, 0, 3, 1], dtype=np.uint8)
+    assert np.array_equal(ctx.score_batch(perm[a], perm[b], swb.MATRIX_SPEEDTEST, 15), s)
+    # bounds
+    assert s.min() >= 0 and s.max() <= 1280
+
+
+def test_packed_2bit_input(ctx, swb, oracle):
+    n = 50_001
+    a, b = swb.counter_pairs(9, n)
+    pa, pb = oracle.pack2bit(a), oracle.pack2bit(b)
+    got = ctx.score_batch(pa, pb, swb.MATRIX_SPEEDTEST, 15, packed=True)
+    assert np.array_equal(got, ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15))
+    assert np.array_equal(got[:3000], oracle.score_batch(a[:3000], b[:3000], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
+def test_device_resident_entry(ctx, swb, oracle):
+    import torch
+    n = 40_000
+    a, b = swb.counter_pairs(31337, n)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.score_batch_device(da, db, swb.MATRIX_111, 1, ds)
+    torch.cuda.synchronize()
+    assert np.array_equal(ds.cpu().numpy(), oracle.score_batch(a, b, swb.MATRIX_111, 1, threads=NCPU))
+    # packed device entry
+    dpa, dpb = torch.from_numpy(oracle.pack2bit(a)).cuda(), torch.from_numpy(oracle.pack2bit(b)).cuda()
+    ds2 = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.score_batch_device(dpa, dpb, swb.MATRIX_111, 1, ds2, n=n, packed=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ds, ds2)
+    assert ctx.count_bad_codes_device(da) == 0
+    da[17, 5] = 9
+    assert ctx.count_bad_codes_device(da) == 1
+
+
+def test_submit_wait_streaming(ctx, swb, oracle):
+    n = 30_000
+    batches = [swb.counter_pairs(k * n, n) for k in range(3)]
+    outs = [np.empty(n, np.int32) for _ in batches]
+    tickets = [ctx.submit(a, b, swb.MATRIX_SPEEDTEST, 15, o) for (a, b), o in zip(batches, outs)]
+    for t in tickets:
+        ctx.wait(t)
+    for (a, b), o in zip(batches, outs):
+        assert np.array_equal(o[:2000], oracle.score_batch(a[:2000], b[:2000], swb.MATRIX_SPEEDTEST, 15))
+    with pytest.raises(swb.SwbError) as e:
+        ctx.wait(tickets[0])
+    assert e.value.code == swb.ERR_TICKET
+
+
+def test_errors_are_codes_not_aborts(ctx, swb):
+    a, b = swb.counter_pairs(0, 4)
+    with pytest.raises(swb.SwbError) as e:
+        ctx.score_batch(a, b, mm(10, -128), 15)
+    assert e.value.code == swb.ERR_DOMAIN
+    with pytest.raises(swb.SwbError) as e:
+        ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, -1)
+    assert e.value.code == swb.ERR_DOMAIN
+    with pytest.raises(ValueError):
+        ctx.smith_waterman(a[0][:100], b[0], swb.MATRIX_SPEEDTEST, 15)
+    # the context is still usable afterwards
+    assert ctx.score_batch(a, a, swb.MATRIX_SPEEDTEST, 15).tolist() == [1280] * 4
+
+
+def test_all_visible_gpus_shard_by_index_range(swb, oracle):
+    import torch
+    g = torch.cuda.device_count()
+    n = 300_001
+    a, b = swb.counter_pairs(42, n)
+    with swb.Context(n_devices=g) as c:
+        assert c.n_devices == g
+        got = c.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    sample = np.r_[0:2000, n - 2000:n, np.arange(0, n, 499)]
+    assert np.array_equal(got[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))

@@ -1,0 +1,165 @@
+// pipebench: measures the issue rate of the packed-int16 instructions the
+// Smith-Waterman kernel is built from, on whatever GPU it runs on.  The result
+// is the DENOMINATOR of the integer-pipe roofline ("INT peak
+// must be measured on the box").  Not part of the product path.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipebench pipebench.cu
+//   ./pipebench            -> one JSON line per instruction mix
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); return 1;}}while(0)
+
+// Every op is `asm volatile` so that NVVM can neither fold a chain of them
+// nor hoist a loop-invariant one; ptxas still fuses add+max into VIADDMNMX.
+__device__ __forceinline__ unsigned f_viaddmnmx(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .b32 t; add.s16x2 t,%1,%2; max.s16x2 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_viaddmnmx32(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .s32 t; add.s32 t,%1,%2; max.s32 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_vimnmx3(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .b32 t; max.s16x2 t,%1,%2; max.s16x2 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_vimnmx(unsigned a,unsigned b){unsigned d; asm volatile("max.s16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
+__device__ __forceinline__ unsigned f_viadd(unsigned a,unsigned b){unsigned d; asm volatile("add.s16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
+__device__ __forceinline__ unsigned f_prmt(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("prmt.b32 %0,%1,%2,%3;":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_imad(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("mad.lo.u32 %0,%1,%2,%3;":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_lop3(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("lop3.b32 %0,%1,%2,%3,0x6a;":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_iadd3(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .u32 t; add.u32 t,%1,%2; add.u32 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_lds(unsigned addr){unsigned d; asm volatile("ld.volatile.shared.u32 %0,[%1];":"=r"(d):"r"(addr)); return d;}
+__device__ __forceinline__ unsigned f_shfl(unsigned a){unsigned d; asm volatile("shfl.sync.up.b32 %0,%1,1,0,0xffffffff;":"=r"(d):"r"(a)); return d;}
+
+constexpr int NCH = 8;      // independent chains per thread
+constexpr int UNROLL = 8;   // body repetitions per loop iteration
+
+// Each mix executes, per chain and per body repetition, a fixed multiset of
+// instructions.  alu_per = ALU-pipe candidates, other_per = the rest.
+template<int MIX>
+__global__ void __launch_bounds__(256) bench(unsigned* out, const unsigned* in, int iters, long long* cycles)
+{
+    __shared__ unsigned tab[32*64];
+    for (int i = threadIdx.x; i < 32*64; i += blockDim.x) tab[i] = (MIX == 9) ? (unsigned)((((i >> 5) * 37 + 11) & 63) * 128) : in[i & 15] + i;
+    __syncthreads();
+    unsigned x[NCH], y[NCH];
+    const unsigned p = in[0], q = in[1], r = in[2], m17 = in[3] | 1;
+    #pragma unroll
+    for (int c = 0; c < NCH; ++c) { x[c] = in[4 + c] + threadIdx.x; y[c] = (MIX == 9) ? (unsigned)(c * 128 + (in[5] & 0x1f80)) & 0x1f80 : (in[5 + c] ^ threadIdx.x); }
+    const unsigned tabaddr = (unsigned)__cvta_generic_to_shared(tab) + (threadIdx.x & 31) * 4;
+    const unsigned one = in[63];
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        #pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            #pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (MIX == 0) { x[c] = f_viaddmnmx(x[c], p, q); }
+                if (MIX == 1) { x[c] = f_vimnmx3(x[c], p, y[c]); y[c] = f_vimnmx3(y[c], q, x[c]); }
+                if (MIX == 2) { x[c] = f_prmt(x[c], p, q); }
+                if (MIX == 3) { x[c] = f_viadd(x[c], y[c]); y[c] = f_viadd(y[c], x[c]); }
+                if (MIX == 4) { x[c] = f_imad(x[c], m17, q); }
+                if (MIX == 5) { x[c] = f_lop3(x[c], p, q); }
+                if (MIX == 6) { // the fast-path cell: PRMT + VIADDMNMX + VIMNMX3
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viaddmnmx(x[c], s, y[c]);
+                    y[c] = x[c];
+                    x[c] = f_vimnmx3(t, y[c], r);
+                }
+                if (MIX == 7) { // cell + one IMAD (FMA pipe) per 3 ALU
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viaddmnmx(x[c], s, y[c]);
+                    y[c] = f_imad(y[c], m17, x[c]);
+                    x[c] = f_vimnmx3(t, y[c], r);
+                }
+                if (MIX == 8) { // cell + one conflict-free LDS per 3 ALU
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viaddmnmx(x[c], s, y[c]);
+                    unsigned l = f_lds(tabaddr + (unsigned)((u * NCH + c) & 63) * 128u);
+                    y[c] = x[c];
+                    x[c] = f_vimnmx3(t, l, r);
+                }
+                if (MIX == 9) { // LDS-lookup cell: IMAD(addr) + LDS + VIADDMNMX + VIMNMX3
+                    unsigned a = f_imad(y[c], one, tabaddr);   // address add on the FMA pipe
+                    unsigned s = f_lds(a);
+                    y[c] = s;
+                    unsigned t = f_viaddmnmx(x[c], s, p);
+                    x[c] = f_vimnmx3(t, x[c], r);
+                }
+                if (MIX == 10) { // cell + SHFL per 3 ALU
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viaddmnmx(x[c], s, y[c]);
+                    unsigned l = f_shfl(x[c]);
+                    y[c] = x[c];
+                    x[c] = f_vimnmx3(t, l, r);
+                }
+                if (MIX == 11) { x[c] = f_viaddmnmx(x[c], p, q); y[c] = f_imad(y[c], m17, q); } // 1 ALU : 1 FMA
+                if (MIX == 12) { x[c] = f_iadd3(x[c], p, q); }
+                if (MIX == 13) { x[c] = f_viaddmnmx32(x[c], p, q); }
+                if (MIX == 14) { x[c] = f_vimnmx3(x[c], p, q); y[c] = f_imad(y[c], m17, q); y[c] = f_imad(y[c], m17, p);} // 1 ALU : 2 FMA
+            }
+        }
+    }
+    long long t1 = clock64();
+    unsigned acc = 0;
+    #pragma unroll
+    for (int c = 0; c < NCH; ++c) acc ^= x[c] ^ y[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+struct MixInfo { const char* name; int alu; int other; };
+static const MixInfo MI[] = {
+    {"VIADDMNMX.S16x2", 1, 0}, {"VIMNMX3.S16x2", 2, 0}, {"PRMT", 1, 0}, {"VIADD.16x2", 2, 0},
+    {"IMAD", 0, 1}, {"LOP3", 1, 0}, {"cell: PRMT+VIADDMNMX+VIMNMX3", 3, 0}, {"cell + IMAD", 3, 1},
+    {"cell + LDS", 3, 1}, {"LDS-lookup cell: IMAD+LDS+VIADDMNMX+VIMNMX3", 2, 2}, {"cell + SHFL", 3, 1},
+    {"VIADDMNMX + IMAD", 1, 1}, {"IADD3 x2", 2, 0}, {"VIADDMNMX.S32", 1, 0}, {"VIMNMX3 + 2 IMAD", 1, 2},
+};
+
+template<int MIX> int run(int sms, int wps, unsigned* d_out, unsigned* d_in, long long* d_cyc, int clock_khz)
+{
+    const int iters = 2000;
+    const int threads = 256;
+    const int blocks = sms * wps * 4 * 32 / threads;   // wps warps per SMSP
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    bench<MIX><<<blocks, threads>>>(d_out, d_in, 200, d_cyc);
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    bench<MIX><<<blocks, threads>>>(d_out, d_in, iters, d_cyc);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    static long long hc[8192];
+    cudaMemcpy(hc, d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+    long long mx = 0; double avg = 0; for (int i = 0; i < blocks; ++i) { if (hc[i] > mx) mx = hc[i]; avg += hc[i]; } avg /= blocks;
+    const double per_thread = (double)iters * UNROLL * NCH;
+    const double tot = per_thread * (MI[MIX].alu + MI[MIX].other);
+    const double warp_instr_per_sm = tot * wps * 4;
+    // lanes per clock per SM, using the block-cycle counter (SM clock domain)
+    const double lanes_clk = warp_instr_per_sm * 32 / avg;
+    const double alu_lanes_clk = per_thread * MI[MIX].alu * wps * 4 * 32 / avg;
+    const double ginstr_s = tot * (double)blocks * threads / (ms * 1e-3) / 1e9;
+    printf("{\"mix\": \"%s\", \"warps_per_smsp\": %d, \"ms\": %.4f, \"avg_cycles\": %.0f, \"max_cycles\": %lld, "
+           "\"lanes_per_clk_per_sm\": %.2f, \"alu_lanes_per_clk_per_sm\": %.2f, \"thread_ginstr_per_s\": %.1f, \"eff_mhz\": %.0f}\n",
+           MI[MIX].name, wps, ms, avg, mx, lanes_clk, alu_lanes_clk, ginstr_s, avg / (ms * 1e-3) / 1e6);
+    fflush(stdout);
+    return 0;
+}
+
+int main()
+{
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, prop.multiProcessorCount, clk);
+    unsigned *d_out, *d_in; long long* d_cyc;
+    CK(cudaMalloc(&d_out, 64 << 20)); CK(cudaMalloc(&d_in, 4096)); CK(cudaMalloc(&d_cyc, 8192 * 8));
+    unsigned h[64]; for (int i = 0; i < 64; ++i) h[i] = 0x00030001u * (i + 1) + 0x3210;
+    h[63] = 1;
+    cudaMemcpy(d_in, h, sizeof(h), cudaMemcpyHostToDevice);
+    const int sms = prop.multiProcessorCount;
+    for (int wps : {1, 2, 4, 8}) {
+        run<0>(sms, wps, d_out, d_in, d_cyc, clk); run<1>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<2>(sms, wps, d_out, d_in, d_cyc, clk); run<3>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<4>(sms, wps, d_out, d_in, d_cyc, clk); run<5>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<6>(sms, wps, d_out, d_in, d_cyc, clk); run<7>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<8>(sms, wps, d_out, d_in, d_cyc, clk); run<9>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<10>(sms, wps, d_out, d_in, d_cyc, clk); run<11>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<12>(sms, wps, d_out, d_in, d_cyc, clk); run<13>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<14>(sms, wps, d_out, d_in, d_cyc, clk);
+    }
+    return 0;
+}
