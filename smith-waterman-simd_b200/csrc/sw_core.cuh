@@ -91,13 +91,19 @@ SWB_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 struct SwParams {
     uint32_t t4[4];    // t4[a] = bytes e(a,0..3): fast path e = max(S,-2g)+2g (0..127); general path e = S
     uint32_t dummy;    // profile word of an inert row (its cells never exceed a real neighbour)
-    uint32_t G;        // fast: (g,g)            general: unused
-    uint32_t NG;       // general: (-g,-g)       fast: unused
-    uint32_t N2G;      // fast: (-2g,-2g)
-    uint32_t K;        // fast: (112g,112g) FIFO re-basing; general: 0
+    uint32_t G;        // fast: (g,g)
+    uint32_t NG;       // general: (-g,-g)
+    uint32_t C;        // fast: (128g,128g), subtracted from every live value once per strip (frame renormalisation)
+    uint32_t one;      // 1          } multipliers the compiler cannot fold: `a*one + b` stays an IMAD, i.e. the
+    uint32_t mone;     // 0xffffffff } frame bookkeeping adds run on the FMA pipe while the ALU pipe is saturated
     int32_t  gap;      // g
     int32_t  fast;     // 1 = anti-diagonal offset DP is exact for this matrix/gap
 };
+
+// a + b and a - b for frame bookkeeping: exact as plain 32-bit operations because both halves
+// of every operand are non-negative and no half can carry or borrow (see SwState).
+SWB_HD uint32_t fadd(uint32_t a, uint32_t b, const SwParams& p) { return a * p.one + b; }
+SWB_HD uint32_t fsub(uint32_t a, uint32_t b, const SwParams& p) { return b * p.mone + a; }
 
 constexpr int SW_L = 128;          // sequence length (source.cpp:36-37)
 constexpr int SW_R = 16;           // strip height = cells per anti-diagonal step per thread
@@ -106,6 +112,12 @@ constexpr int SW_ITERS = SW_STRIPS * (SW_L / 16) + 1;   // 16-step iterations in
 
 // Thread-private state.  Everything is indexed by compile-time constants after unrolling,
 // so it lives in registers.
+//
+// Fast-path frame: at step T (counted from the last renormalisation) a register holds
+// H + Z_T with Z_T = g*(T+2) in both halves; every value is >= 0, so the frame bookkeeping
+// (Z += G, FIFO re-basing, renormalisation) is done with PLAIN 32-bit adds -- no carry can
+// cross the halves -- which the compiler is free to issue on the FMA pipe (IMAD.IADD)
+// instead of the saturated ALU pipe.  The FIFO itself holds frame-free true H values.
 struct SwState {
     uint32_t h1[SW_R];    // row k at step T-1  (left of the cell being computed; up of row k+1)
     uint32_t h2[SW_R];    // row k at step T-2  (diag of row k+1)
@@ -113,85 +125,15 @@ struct SwState {
     uint32_t prB[SW_R];   // S[a_hi[k]][0..3] as 4 bytes   (pair in the high half)
     uint32_t sel[SW_R];   // PRMT selectors of the 16 most recent columns
     uint32_t up0, dg0;    // row 0's up / diag (from the FIFO)
-    uint32_t Z;           // fast: packed g*(T+2) = the value of a true zero at step T
+    uint32_t Z, Zp;       // fast: Z_T and Z_{T-1}
     uint32_t B;           // running best (fast: in the frame of the current step)
+    uint32_t bq_lo[2], bq_hi[2];   // target bases of the next iteration's columns 0..7 (loaded 8 steps ahead)
 };
 
 // byte `idx` (0..3) of word w, times 4 (a word offset into t4[]), masked to a valid code
 SWB_HD uint32_t code_x4(uint32_t w, int idx)
 {
     return (idx == 0) ? ((w << 2) & 0xcu) : ((w >> (8 * idx - 2)) & 0xcu);
-}
-
-// One 16-step iteration.  WRAP = this iteration starts at a step that is a multiple of 128:
-// at sub-step u, row u leaves its strip and enters column 0 of the next one.
-//   Fifo: pop(c) / push(c, v) with c the column 0..127.
-//   bw_lo/bw_hi: the 16 target bases (bytes) of this iteration's columns, 4 words each.
-//   aw_lo/aw_hi: (WRAP only) the 16 query bases of the strip being entered.
-template <bool FAST, bool WRAP, class Fifo, class Table>
-SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
-                      const uint32_t (&bw_lo)[4], const uint32_t (&bw_hi)[4],
-                      const uint32_t (&aw_lo)[4], const uint32_t (&aw_hi)[4], bool next_is_dummy)
-{
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        // --- selector of the column entering the window: bytes (b_lo, b_hi) -> nibbles
-        //     (b_lo, 8|b_lo, 4|b_hi, 12|b_hi): low half <- byte b_lo of prA sign-extended,
-        //     high half <- byte b_hi of prB sign-extended.
-        {
-            const uint32_t pick = 0x4440u | (uint32_t)(u & 3) | ((uint32_t)(u & 3) << 4);
-            const uint32_t w = prmt(bw_lo[u >> 2], bw_hi[u >> 2], pick);   // bytes 2,3 are don't-care: PRMT reads selector bits 0..15 only
-            st.sel[u] = w * 17u + 0xC480u;                                  // IMAD: the FMA pipe, not the ALU pipe
-        }
-        if (WRAP) {   // row u enters the next strip: new query profile
-            if (next_is_dummy) {
-                st.prA[u] = prm.dummy;
-                st.prB[u] = prm.dummy;
-            } else {
-                st.prA[u] = t4(code_x4(aw_lo[u >> 2], u & 3));
-                st.prB[u] = t4(code_x4(aw_hi[u >> 2], u & 3));
-            }
-        }
-        // --- row 0's upper neighbours come from the previous strip's bottom row
-        const uint32_t popped = fifo.pop(WRAP ? u : col0 + u);
-        st.dg0 = st.up0;
-        st.up0 = FAST ? vadd2(popped, prm.K) : popped;
-        const uint32_t Zm2 = FAST ? vadd2(st.Z, prm.N2G) : 0u;   // true zero two steps ago (WRAP only)
-
-        uint32_t hn[SW_R];
-#pragma unroll
-        for (int k = 0; k < SW_R; ++k) {
-            const uint32_t s = prmt(st.prA[k], st.prB[k], st.sel[(u - k) & 15]);
-            uint32_t up = (k == 0) ? st.up0 : st.h1[k - 1];
-            uint32_t dg = (k == 0) ? st.dg0 : st.h2[k - 1];
-            uint32_t lf = st.h1[k];
-            if (WRAP && k == u) {   // column 0 of a strip: H[i][-1] = H[i-1][-1] = 0  (source.cpp:44 zero-initialised table)
-                lf = 0u;
-                dg = FAST ? Zm2 : 0u;
-            }
-            if (FAST) {
-                const uint32_t t = vaddmax2(dg, s, up);
-                hn[k] = vmax3(t, lf, st.Z);
-            } else {
-                const uint32_t t = vadd2(vmax2(up, lf), prm.NG);
-                hn[k] = vaddmax2_relu(dg, s, t);
-            }
-        }
-        // --- bottom row to the FIFO (column of row 15 at this step)
-        //     (a WRAP iteration always starts at column 0; elsewhere col0 >= 16 and nothing wraps,
-        //     so every FIFO address below is `per-iteration base + compile-time offset`)
-        fifo.push(WRAP ? ((u - (SW_R - 1)) & (SW_L - 1)) : (col0 + u - (SW_R - 1)), hn[SW_R - 1]);
-        // --- running best
-        if (FAST) st.B = vaddmax2(st.B, prm.G, hn[0]);
-        else      st.B = vmax2(st.B, hn[0]);
-#pragma unroll
-        for (int k = 1; k + 1 < SW_R; k += 2) st.B = vmax3(st.B, hn[k], hn[k + 1]);
-        st.B = vmax2(st.B, hn[SW_R - 1]);
-        // --- advance
-#pragma unroll
-        for (int k = 0; k < SW_R; ++k) { st.h2[k] = st.h1[k]; st.h1[k] = hn[k]; }
-        if (FAST) st.Z = vadd2(st.Z, prm.G);
-    }
 }
 
 // 8 bytes from a byte pointer that is 8-byte aligned
@@ -212,11 +154,98 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
     ld8(p + 8, w[2], w[3]);
 }
 
-// Scores two pairs: (a_lo,b_lo) in the low halves, (a_hi,b_hi) in the high halves.
-// All four pointers address 128 byte-coded bases (0..3), 8-byte aligned.
+// One 16-step iteration.  WRAP = this iteration starts at a step that is a multiple of 128:
+// at sub-step u, row u leaves its strip and enters column 0 of the next one.
+//   Fifo: pop(c) / push(c, v) with c the column 0..127.
+//   b_lo: the low pair's target; the high pair's is at b_lo + dq.  This iteration covers
+//         columns col0..col0+15; columns col0+8.. are loaded here at u = 0, the next
+//         iteration's first eight at u = 8 (always 8 steps ahead of their first use).
+//   aw_lo/aw_hi: (WRAP only) the 16 query bases of the strip being entered.
+template <bool FAST, bool WRAP, class Fifo, class Table>
+SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
+                      const uint8_t* b_lo, uint32_t dq,
+                      const uint32_t (&aw_lo)[4], const uint32_t (&aw_hi)[4], bool next_is_dummy)
+{
+    uint32_t bw_lo[4], bw_hi[4];
+    bw_lo[0] = st.bq_lo[0]; bw_lo[1] = st.bq_lo[1]; bw_hi[0] = st.bq_hi[0]; bw_hi[1] = st.bq_hi[1];
+    {
+        const uint8_t* p = b_lo + (WRAP ? 0 : col0) + 8;
+        ld8(p, bw_lo[2], bw_lo[3]);
+        ld8(p + dq, bw_hi[2], bw_hi[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        if (u == 8) {
+            const uint8_t* p = b_lo + (((WRAP ? 0 : col0) + 16) & (SW_L - 1));
+            ld8(p, st.bq_lo[0], st.bq_lo[1]);
+            ld8(p + dq, st.bq_hi[0], st.bq_hi[1]);
+        }
+        // --- selector of the column entering the window: bytes (b_lo, b_hi) -> nibbles
+        //     (b_lo, 8|b_lo, 4|b_hi, 12|b_hi): low half <- byte b_lo of prA sign-extended,
+        //     high half <- byte b_hi of prB sign-extended.
+        {
+            const uint32_t pick = 0x4440u | (uint32_t)(u & 3) | ((uint32_t)(u & 3) << 4);
+            const uint32_t w = prmt(bw_lo[u >> 2], bw_hi[u >> 2], pick);   // bytes 2,3 are don't-care: PRMT reads selector bits 0..15 only
+            st.sel[u] = w * 17u + 0xC480u;                                  // IMAD: the FMA pipe, not the ALU pipe
+        }
+        if (WRAP) {   // row u enters the next strip: new query profile
+            if (next_is_dummy) {
+                st.prA[u] = prm.dummy;
+                st.prB[u] = prm.dummy;
+            } else {
+                st.prA[u] = t4(code_x4(aw_lo[u >> 2], u & 3));
+                st.prB[u] = t4(code_x4(aw_hi[u >> 2], u & 3));
+            }
+        }
+        // --- row 0's upper neighbours come from the previous strip's bottom row (frame-free in the FIFO)
+        const uint32_t popped = fifo.pop(WRAP ? u : col0 + u);
+        st.dg0 = st.up0;
+        st.up0 = FAST ? fadd(popped, st.Zp, prm) : popped;   // plain add: both halves >= 0, no carry across
+        const uint32_t Zm2 = (FAST && WRAP) ? fsub(st.Zp, prm.G, prm) : 0u;   // true zero two steps ago
+
+        uint32_t hn[SW_R];
+#pragma unroll
+        for (int k = 0; k < SW_R; ++k) {
+            const uint32_t s = prmt(st.prA[k], st.prB[k], st.sel[(u - k) & 15]);
+            uint32_t up = (k == 0) ? st.up0 : st.h1[k - 1];
+            uint32_t dg = (k == 0) ? st.dg0 : st.h2[k - 1];
+            uint32_t lf = st.h1[k];
+            if (WRAP && k == u) {   // column 0 of a strip: H[i][-1] = H[i-1][-1] = 0  (source.cpp:44 zero-initialised table)
+                lf = 0u;
+                dg = FAST ? Zm2 : 0u;
+            }
+            if (FAST) {
+                const uint32_t t = vaddmax2(dg, s, up);
+                hn[k] = vmax3(t, lf, st.Z);
+            } else {
+                const uint32_t t = vadd2(vmax2(up, lf), prm.NG);
+                hn[k] = vaddmax2_relu(dg, s, t);
+            }
+        }
+        // --- bottom row to the FIFO (column of row 15 at this step), as a true H value.
+        //     (a WRAP iteration always starts at column 0; elsewhere col0 >= 16 and nothing wraps,
+        //     so every FIFO address is `per-iteration base + compile-time offset`)
+        fifo.push(WRAP ? ((u - (SW_R - 1)) & (SW_L - 1)) : (col0 + u - (SW_R - 1)),
+                  FAST ? fsub(hn[SW_R - 1], st.Z, prm) : hn[SW_R - 1]);   // plain subtract: hn >= Z in both halves
+        // --- running best
+        if (FAST) st.B = vaddmax2(st.B, prm.G, hn[0]);
+        else      st.B = vmax2(st.B, hn[0]);
+#pragma unroll
+        for (int k = 1; k + 1 < SW_R; k += 2) st.B = vmax3(st.B, hn[k], hn[k + 1]);
+        st.B = vmax2(st.B, hn[SW_R - 1]);
+        // --- advance
+#pragma unroll
+        for (int k = 0; k < SW_R; ++k) { st.h2[k] = st.h1[k]; st.h1[k] = hn[k]; }
+        if (FAST) { st.Zp = st.Z; st.Z = fadd(st.Z, prm.G, prm); }
+    }
+}
+
+// Scores two pairs: (a_lo,b_lo) in the low halves, (a_lo+dq, b_lo+dq) in the high halves
+// (dq = 128 for the neighbouring pair, 0 when the batch's last pair stands alone).
+// Both pointers address 128 byte-coded bases (0..3), 8-byte aligned.
 // The FIFO must hold 128 words for this thread; it is (re)initialised here.
 template <bool FAST, class Fifo, class Table>
-SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* a_hi, const uint8_t* b_lo, const uint8_t* b_hi,
+SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
                             Fifo& fifo, const Table& t4, const SwParams& prm, int32_t& score_lo, int32_t& score_hi)
 {
     SwState st;
@@ -225,52 +254,43 @@ SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* a_hi, const uint
         st.h1[k] = 0u; st.h2[k] = 0u; st.sel[k] = 0u;
         st.prA[k] = prm.dummy; st.prB[k] = prm.dummy;
     }
-    // Top boundary H[0][*] = 0 (source.cpp:44).  Fast path: the word popped for column c at
-    // step T=c must read g*(c+1) after re-basing by K = 112g, i.e. g*(c-111).
-    {
-        const uint32_t step = FAST ? prm.G : 0u;
-        uint32_t v = 0u;
-        if (FAST) { const int32_t f = -111 * prm.gap; v = ((uint32_t)f & 0xffffu) * 0x10001u; }
-        for (int c = 0; c < SW_L; ++c) { fifo.push(c, v); v = vadd2(v, step); }
-    }
-    st.Z = FAST ? vadd2(prm.G, prm.G) : 0u;   // g*(0+2)
+    // Top boundary H[0][*] = 0 (source.cpp:44)
+    for (int c = 0; c < SW_L; ++c) fifo.push(c, 0u);
+    st.Z = FAST ? prm.G + prm.G : 0u;         // Z_0 = g*(0+2)
+    st.Zp = FAST ? prm.G : 0u;                // Z_{-1}
     st.B = FAST ? prm.G : 0u;                 // best = 0 in the frame of step -1
-    st.up0 = FAST ? prm.G : 0u;               // true zero at step -1 (only ever read as a diag of column 0, then overridden)
+    st.up0 = FAST ? prm.G : 0u;               // a true zero at step -1 (read once, as a diag of column 0, and overridden)
     st.dg0 = 0u;
 
-    uint32_t bn_lo[4], bn_hi[4], an_lo[4], an_hi[4];
-    ld16(b_lo, bn_lo); ld16(b_hi, bn_hi);
-    ld16(a_lo, an_lo); ld16(a_hi, an_hi);
+    uint32_t an_lo[4], an_hi[4];
+    ld8(b_lo, st.bq_lo[0], st.bq_lo[1]);
+    ld8(b_lo + dq, st.bq_hi[0], st.bq_hi[1]);
+    ld16(a_lo, an_lo); ld16(a_lo + dq, an_hi);
 
-    for (int it = 0; it < SW_ITERS; ++it) {
-        const int col0 = 16 * (it & 7);
-        uint32_t bw_lo[4], bw_hi[4];
+    for (int strip = 0; strip <= SW_STRIPS; ++strip) {
+        if (FAST && strip > 0) {
+            // Renormalise the frame: T restarts at 0, every live value drops by 128g
+            // (all are >= Z_{T-2} = 128g here, so the plain subtraction cannot borrow).
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { bw_lo[q] = bn_lo[q]; bw_hi[q] = bn_hi[q]; }
-        {   // prefetch the next iteration's target bases
-            const int nc = 16 * ((it + 1) & 7);
-            ld16(b_lo + nc, bn_lo); ld16(b_hi + nc, bn_hi);
+            for (int k = 0; k < SW_R; ++k) { st.h1[k] = fsub(st.h1[k], prm.C, prm); st.h2[k] = fsub(st.h2[k], prm.C, prm); }
+            st.Z = fsub(st.Z, prm.C, prm); st.Zp = fsub(st.Zp, prm.C, prm);
+            st.B = fsub(st.B, prm.C, prm); st.up0 = fsub(st.up0, prm.C, prm);
         }
-        if ((it & 7) == 0) {
-            const int strip = it >> 3;
-            uint32_t aw_lo[4], aw_hi[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { aw_lo[q] = an_lo[q]; aw_hi[q] = an_hi[q]; }
-            {   // prefetch the following strip's query bases (clamped: the last two reads are unused)
+        sw_iter16<FAST, true>(st, fifo, t4, prm, 0, b_lo, dq, an_lo, an_hi, strip >= SW_STRIPS);
+        if (strip == SW_STRIPS) break;
+#pragma unroll 1
+        for (int j = 1; j < SW_L / 16; ++j) {
+            if (j == SW_L / 16 - 1) {   // one iteration ahead of the wrap that consumes them
                 const int ns = (strip + 1 < SW_STRIPS) ? strip + 1 : SW_STRIPS - 1;
-                ld16(a_lo + 16 * ns, an_lo); ld16(a_hi + 16 * ns, an_hi);
+                ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dq, an_hi);
             }
-            sw_iter16<FAST, true>(st, fifo, t4, prm, col0, bw_lo, bw_hi, aw_lo, aw_hi, strip >= SW_STRIPS);
-        } else {
-            sw_iter16<FAST, false>(st, fifo, t4, prm, col0, bw_lo, bw_hi, bw_lo, bw_hi, false);
+            sw_iter16<FAST, false>(st, fifo, t4, prm, 16 * j, b_lo, dq, an_lo, an_hi, false);
         }
     }
     if (FAST) {
-        // B is in the frame of the last step T = 16*SW_ITERS-1; st.Z is one step further.
-        const int32_t zl = (int32_t)(int16_t)(st.Z & 0xffffu) - prm.gap;
-        const int32_t zh = (int32_t)(int16_t)(st.Z >> 16) - prm.gap;
-        score_lo = (int32_t)(int16_t)(st.B & 0xffffu) - zl;
-        score_hi = (int32_t)(int16_t)(st.B >> 16) - zh;
+        // B is in the frame of the last step; st.Zp is that step's Z.
+        score_lo = (int32_t)(int16_t)(st.B & 0xffffu) - (int32_t)(int16_t)(st.Zp & 0xffffu);
+        score_hi = (int32_t)(int16_t)(st.B >> 16) - (int32_t)(int16_t)(st.Zp >> 16);
     } else {
         score_lo = (int32_t)(int16_t)(st.B & 0xffffu);
         score_hi = (int32_t)(int16_t)(st.B >> 16);

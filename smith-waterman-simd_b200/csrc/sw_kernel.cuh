@@ -51,7 +51,7 @@ sw128_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
     SmemFifo<NT> fifo{smem + threadIdx.x};
     SmemTable t4{t4s};
     int32_t lo, hi;
-    sw128_two_pairs<FAST>(seq1 + p * SW_L, seq1 + q * SW_L, seq2 + p * SW_L, seq2 + q * SW_L, fifo, t4, prm, lo, hi);
+    sw128_two_pairs<FAST>(seq1 + p * SW_L, seq2 + p * SW_L, (q != p) ? (uint32_t)SW_L : 0u, fifo, t4, prm, lo, hi);
     if (q != p) {
         *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
     } else {

@@ -26,12 +26,11 @@ inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general =
     SwParams p;
     int smax = 0;
     for (int i = 0; i < 16; ++i) if (sm[i] > smax) smax = sm[i];
-    // Fast path (anti-diagonal offset DP) is exact iff every shifted score fits a
-    // non-negative signed byte and no packed value leaves int16 over the 1040 steps:
-    //   e = max(S,-2g)+2g <= 127,  128*smax + g*(16*SW_ITERS+2) <= 32767,  -111g >= -32768.
-    const int steps = 16 * SW_ITERS;
-    const bool fast = !force_general && (smax + 2 * gap <= 127) &&
-                      (128 * smax + gap * (steps + 2) <= 32767) && (111 * gap <= 32768);
+    // Fast path (anti-diagonal offset DP) is exact iff every shifted score
+    // e = max(S,-2g)+2g fits a non-negative signed byte, i.e. smax + 2g <= 127.  The frame is
+    // renormalised every 128 steps, so the largest packed value is 128*smax + 130g
+    // <= 128*(127-2g) + 130g <= 16256: int16 never overflows on this domain.
+    const bool fast = !force_general && (smax + 2 * gap <= 127);
     p.fast = fast ? 1 : 0;
     p.gap = gap;
     for (int a = 0; a < 4; ++a) {
@@ -46,8 +45,9 @@ inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general =
     p.dummy = fast ? 0u : 0x81818181u;   // fast: e = 0 (a step worth two gaps); general: S = -127
     p.G = sw_pack2(gap);
     p.NG = sw_pack2(-gap);
-    p.N2G = sw_pack2(-2 * gap);
-    p.K = fast ? sw_pack2((SW_L - SW_R) * gap) : 0u;
+    p.C = sw_pack2(SW_L * gap);
+    p.one = 1u;
+    p.mone = 0xffffffffu;
     return p;
 }
 

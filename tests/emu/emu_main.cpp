@@ -31,8 +31,9 @@ extern "C" int swemu_score_batch(const uint8_t* seq1, const uint8_t* seq2, const
         const uint64_t q = (p + 1 < n) ? p + 1 : p;
         HostFifo fifo;
         int32_t lo, hi;
-        if (prm.fast) sw128_two_pairs<true>(seq1 + p * 128, seq1 + q * 128, seq2 + p * 128, seq2 + q * 128, fifo, t4, prm, lo, hi);
-        else          sw128_two_pairs<false>(seq1 + p * 128, seq1 + q * 128, seq2 + p * 128, seq2 + q * 128, fifo, t4, prm, lo, hi);
+        const uint32_t dq = (q != p) ? 128u : 0u;
+        if (prm.fast) sw128_two_pairs<true>(seq1 + p * 128, seq2 + p * 128, dq, fifo, t4, prm, lo, hi);
+        else          sw128_two_pairs<false>(seq1 + p * 128, seq2 + p * 128, dq, fifo, t4, prm, lo, hi);
         scores[p] = lo;
         if (q != p) scores[q] = hi;
     }

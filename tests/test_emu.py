@@ -64,8 +64,8 @@ def test_emu_fast_path_domain_boundary(emu, oracle):
 
     def mm(m, x):
         return [m if i == j else x for i in range(4) for j in range(4)]
-    for sm, g, want_fast in ((mm(11, -90), 30, 1), (mm(12, -90), 30, 0), (mm(97, -100), 15, 1), (mm(98, -100), 15, 0),
-                             (mm(1, -127), 31, 1), (mm(1, -127), 32, 0), (mm(127, -127), 0, 1)):
+    for sm, g, want_fast in ((mm(67, -90), 30, 1), (mm(68, -90), 30, 0), (mm(97, -100), 15, 1), (mm(98, -100), 15, 0),
+                             (mm(1, -127), 63, 1), (mm(0, -127), 64, 0), (mm(127, -127), 0, 1)):
         path, got = emu(a, b, sm, g)
         assert path == want_fast, (sm[0], g)
         assert np.array_equal(got, oracle.score_batch(a, b, sm, g)), (sm[0], g)

@@ -1,0 +1,76 @@
+// kbench: times template variants of the Smith-Waterman kernel on one GPU (development tool,
+// not part of the product path).  Inputs: the reference's seeded stream (1 M pairs), so each
+// variant's scores are checked against the reference checksum ae56a1e6a1d57492 / sum 75478815.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I../smith-waterman-simd_b200/csrc \
+//        -o kbench kbench.cu ../smith-waterman-simd_b200/csrc/pairgen.cpp
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../include/swb200.h"
+#include "sw_kernel.cuh"
+#include "sw_params.h"
+
+using namespace swb;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+static uint8_t *d1, *d2; static int32_t* dsc; static std::vector<int32_t> hsc;
+static uint64_t N = 1000000;
+static bool g_quick = false;   // `kbench ncu`: one warm-up + one timed launch of the two shipped kernels
+
+template <bool FAST, int NT, int MINB>
+void run(const char* name, const SwParams& prm, uint64_t want_fnv, long long want_sum)
+{
+    auto kern = sw128_kernel<FAST, NT, MINB>;
+    const size_t smem = sw128_smem_bytes<NT>();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    const unsigned grid = (unsigned)(((N + 1) / 2 + NT - 1) / NT);
+    CK(cudaMemset(dsc, 0xff, N * 4));
+    for (int i = 0; i < (g_quick ? 1 : 3); ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = g_quick ? 1 : 10;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+    CK(cudaMemcpy(hsc.data(), dsc, N * 4, cudaMemcpyDeviceToHost));
+    long long sum = 0; for (uint64_t i = 0; i < N; ++i) sum += hsc[i];
+    const uint64_t fnv = swb200_fnv1a64_i32(hsc.data(), N);
+    printf("{\"variant\": \"%s\", \"fast\": %d, \"nt\": %d, \"minb\": %d, \"regs\": %d, \"occ_blocks\": %d, \"smem\": %zu, \"ms\": %.4f, \"gcups\": %.1f, \"ok\": %s}\n",
+           name, (int)FAST, NT, MINB, fa.numRegs, occ, smem, ms, N * 16384.0 / (ms * 1e-3) / 1e9,
+           (fnv == want_fnv && sum == want_sum) ? "true" : "false");
+    fflush(stdout);
+}
+
+int main(int argc, char** argv)
+{
+    std::vector<uint8_t> a(N * 128), b(N * 128);
+    swb200_gen_reference_stream(10000, N, a.data(), b.data());
+    hsc.resize(N);
+    CK(cudaMalloc(&d1, N * 128)); CK(cudaMalloc(&d2, N * 128)); CK(cudaMalloc(&dsc, N * 4));
+    CK(cudaMemcpy(d1, a.data(), N * 128, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d2, b.data(), N * 128, cudaMemcpyHostToDevice));
+    const int8_t sm[16] = {10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10};
+    const SwParams fast = sw_make_params(sm, 15, 0), gen = sw_make_params(sm, 15, 1);
+    const uint64_t F = 0xae56a1e6a1d57492ull; const long long S = 75478815;
+    g_quick = argc > 1;
+    run<true, 128, 3>("fast nt128 x3", fast, F, S);
+    if (g_quick) { run<false, 128, 3>("general nt128 x3", gen, F, S); return 0; }
+    run<true, 96, 4>("fast nt96 x4", fast, F, S);
+    run<true, 64, 6>("fast nt64 x6", fast, F, S);
+    run<true, 192, 2>("fast nt192 x2", fast, F, S);
+    run<true, 384, 1>("fast nt384 x1", fast, F, S);
+    run<true, 128, 2>("fast nt128 x2 (255 regs)", fast, F, S);
+    run<true, 64, 7>("fast nt64 x7 (146 regs)", fast, F, S);
+    run<true, 32, 12>("fast nt32 x12", fast, F, S);
+    run<false, 128, 3>("general nt128 x3", gen, F, S);
+    run<false, 64, 6>("general nt64 x6", gen, F, S);
+    return 0;
+}

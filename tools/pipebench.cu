@@ -14,6 +14,8 @@
 // Every op is `asm volatile` so that NVVM can neither fold a chain of them
 // nor hoist a loop-invariant one; ptxas still fuses add+max into VIADDMNMX.
 __device__ __forceinline__ unsigned f_viaddmnmx(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .b32 t; add.s16x2 t,%1,%2; max.s16x2 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_viaddmnmx_relu(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .b32 t; add.s16x2 t,%1,%2; max.s16x2.relu %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_hmnmx2(unsigned a,unsigned b){unsigned d; asm volatile("max.f16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
 __device__ __forceinline__ unsigned f_viaddmnmx32(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .s32 t; add.s32 t,%1,%2; max.s32 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
 __device__ __forceinline__ unsigned f_vimnmx3(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .b32 t; max.s16x2 t,%1,%2; max.s16x2 %0,t,%3;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
 __device__ __forceinline__ unsigned f_vimnmx(unsigned a,unsigned b){unsigned d; asm volatile("max.s16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
@@ -90,6 +92,30 @@ __global__ void __launch_bounds__(256) bench(unsigned* out, const unsigned* in, 
                 if (MIX == 11) { x[c] = f_viaddmnmx(x[c], p, q); y[c] = f_imad(y[c], m17, q); } // 1 ALU : 1 FMA
                 if (MIX == 12) { x[c] = f_iadd3(x[c], p, q); }
                 if (MIX == 13) { x[c] = f_viaddmnmx32(x[c], p, q); }
+                if (MIX == 15) { x[c] = f_vimnmx(x[c], y[c]); y[c] = f_viadd(y[c], x[c]); }            // 2-src max + 2-src add
+                if (MIX == 16) { x[c] = f_viadd(x[c], p); y[c] = f_viaddmnmx(y[c], q, x[c]); }          // VIADD(R,R) + VIADDMNMX
+                if (MIX == 17) { x[c] = f_prmt(x[c], p, y[c]); y[c] = f_vimnmx3(y[c], q, x[c]); }       // PRMT + VIMNMX3
+                if (MIX == 18) { x[c] = f_prmt(x[c], p, y[c]); y[c] = f_viaddmnmx(y[c], q, x[c]); }     // PRMT + VIADDMNMX
+                if (MIX == 19) { x[c] = f_viaddmnmx(x[c], p, y[c]); y[c] = f_vimnmx3(y[c], q, x[c]); }  // VIADDMNMX + VIMNMX3
+                if (MIX == 20) { // general-path cell: PRMT + VIMNMX + VIADD + VIADDMNMX.RELU
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viadd(f_vimnmx(x[c], y[c]), r);
+                    y[c] = x[c];
+                    x[c] = f_viaddmnmx_relu(y[c], s, t);
+                }
+                if (MIX == 21) { x[c] = f_vimnmx(x[c], y[c]); y[c] = f_prmt(y[c], p, x[c]); }            // VIMNMX(2-src) + PRMT
+                if (MIX == 22) { x[c] = f_viadd(x[c], y[c]); y[c] = f_prmt(y[c], p, x[c]); }             // VIADD.16x2 + PRMT
+                if (MIX == 23) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_hmnmx2(y[c], p); }                 // HMNMX2 alone
+                if (MIX == 24) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_prmt(y[c], p, x[c]); }             // HMNMX2 + PRMT
+                if (MIX == 25) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_imad(y[c], m17, x[c]); }           // HMNMX2 + IMAD
+                if (MIX == 26) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_viadd(y[c], x[c]); }               // HMNMX2 + VIADD.16x2
+                if (MIX == 27) { // split cell: PRMT + VIADDMNMX on the ALU pipe, the 3-input max as two HMNMX2
+                    unsigned s = f_prmt(p, q, y[c]);
+                    unsigned t = f_viaddmnmx(x[c], s, y[c]);
+                    y[c] = x[c];
+                    x[c] = f_hmnmx2(f_hmnmx2(t, y[c]), r);
+                }
+                if (MIX == 28) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_viaddmnmx(y[c], p, x[c]); }        // HMNMX2 + VIADDMNMX
                 if (MIX == 14) { x[c] = f_vimnmx3(x[c], p, q); y[c] = f_imad(y[c], m17, q); y[c] = f_imad(y[c], m17, p);} // 1 ALU : 2 FMA
             }
         }
@@ -102,12 +128,31 @@ __global__ void __launch_bounds__(256) bench(unsigned* out, const unsigned* in, 
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// Does max.f16x2 on raw bits equal the integer maximum for every pair of values in
+// [0, 0x7BFF] (non-negative, finite fp16 bit patterns, subnormals included)?  Exhaustive.
+__global__ void hmnmx2_selftest(unsigned long long* bad)
+{
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 0x7BFF
+    if (a > 0x7BFFu) return;
+    unsigned long long local = 0;
+    for (unsigned b = 0; b <= 0x7BFFu; ++b) {
+        const unsigned packed_a = a | (b << 16), packed_b = b | (a << 16);
+        const unsigned got = f_hmnmx2(packed_a, packed_b);
+        const unsigned m = a > b ? a : b;
+        local += (got != (m | (m << 16)));
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 struct MixInfo { const char* name; int alu; int other; };
 static const MixInfo MI[] = {
     {"VIADDMNMX.S16x2", 1, 0}, {"VIMNMX3.S16x2", 2, 0}, {"PRMT", 1, 0}, {"VIADD.16x2", 2, 0},
     {"IMAD", 0, 1}, {"LOP3", 1, 0}, {"cell: PRMT+VIADDMNMX+VIMNMX3", 3, 0}, {"cell + IMAD", 3, 1},
     {"cell + LDS", 3, 1}, {"LDS-lookup cell: IMAD+LDS+VIADDMNMX+VIMNMX3", 2, 2}, {"cell + SHFL", 3, 1},
     {"VIADDMNMX + IMAD", 1, 1}, {"IADD3 (a+b+c)", 1, 0}, {"VIADDMNMX.S32", 1, 0}, {"VIMNMX3 + 2 IMAD", 1, 2},
+    {"VIMNMX(2src) + VIADD.16x2(2src)", 2, 0}, {"VIADD.16x2 + VIADDMNMX", 2, 0}, {"PRMT + VIMNMX3", 2, 0}, {"PRMT + VIADDMNMX", 2, 0},
+    {"VIADDMNMX + VIMNMX3", 2, 0}, {"general cell: PRMT+VIMNMX+VIADD+VIADDMNMX.RELU", 4, 0}, {"VIMNMX(2src) + PRMT", 2, 0}, {"VIADD.16x2 + PRMT", 2, 0},
+    {"HMNMX2 x2", 0, 2}, {"HMNMX2 + PRMT", 1, 1}, {"HMNMX2 + IMAD", 0, 2}, {"HMNMX2 + VIADD.16x2", 0, 2}, {"split cell: PRMT+VIADDMNMX (ALU) + 2 HMNMX2", 2, 2}, {"HMNMX2 + VIADDMNMX", 1, 1},
 };
 
 template<int MIX> int run(int sms, int wps, unsigned* d_out, unsigned* d_in, long long* d_cyc, int clock_khz)
@@ -153,6 +198,12 @@ int main()
     unsigned h[64]; for (int i = 0; i < 64; ++i) h[i] = 0x00030001u * (i + 1) + 0x3210;
     h[63] = 1;
     cudaMemcpy(d_in, h, sizeof(h), cudaMemcpyHostToDevice);
+    {
+        unsigned long long* d_bad; CK(cudaMalloc(&d_bad, 8)); CK(cudaMemset(d_bad, 0, 8));
+        hmnmx2_selftest<<<(0x7C00 + 255) / 256, 256>>>(d_bad);
+        unsigned long long hb = 1; CK(cudaMemcpy(&hb, d_bad, 8, cudaMemcpyDeviceToHost));
+        printf("{\"selftest\": \"HMNMX2 (max.f16x2) == integer max on all pairs of [0,0x7BFF]\", \"mismatches\": %llu}\n", hb);
+    }
     const int sms = prop.multiProcessorCount;
     for (int wps : {2, 4, 8}) {
         run<0>(sms, wps, d_out, d_in, d_cyc, clk); run<1>(sms, wps, d_out, d_in, d_cyc, clk);
@@ -163,6 +214,13 @@ int main()
         run<10>(sms, wps, d_out, d_in, d_cyc, clk); run<11>(sms, wps, d_out, d_in, d_cyc, clk);
         run<12>(sms, wps, d_out, d_in, d_cyc, clk); run<13>(sms, wps, d_out, d_in, d_cyc, clk);
         run<14>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<15>(sms, wps, d_out, d_in, d_cyc, clk); run<16>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<17>(sms, wps, d_out, d_in, d_cyc, clk); run<18>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<19>(sms, wps, d_out, d_in, d_cyc, clk); run<20>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<21>(sms, wps, d_out, d_in, d_cyc, clk); run<22>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<23>(sms, wps, d_out, d_in, d_cyc, clk); run<24>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<25>(sms, wps, d_out, d_in, d_cyc, clk); run<26>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<27>(sms, wps, d_out, d_in, d_cyc, clk); run<28>(sms, wps, d_out, d_in, d_cyc, clk);
     }
     return 0;
 }
