@@ -1,0 +1,89 @@
+// smith_waterman_b200.hpp -- C++ host side above the C ABI (include/swb200.h), mirroring the
+// reference's interface for the hot path so that the new functions can sit next to
+// SmithWaterman_simd .. SmithWaterman_simd9 in the reference's own harnesses
+// (TestSimdSmithWaterman source.cpp:2943-2982, SpeedTest source.cpp:3032-3147).
+//
+//   int SmithWaterman_b200(seq1, seq2, score_matrix, gap_penalty)
+//       -- the exact signature of source.cpp:462-466; forwards to swb200_score_pair.
+//   void SmithWaterman_b200_batch(seq1s, seq2s, score_matrix, gap_penalty, dest)
+//       -- the batched form (precedent: SmithWaterman_8b111x32mark1, source.cpp:1227-1234:
+//          row-major 128-mers in, results into `dest`).
+//
+// Error behaviour: the reference has none (no validation, no return codes).  Here a failed
+// call throws std::runtime_error carrying the library's message -- there is no CPU fallback
+// to hide behind.  Header-only; link with -lswb200.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/swb200.h"
+
+namespace swb200 {
+
+class Context {
+public:
+    explicit Context(int n_devices = 1)
+    {
+        const int rc = swb200_init(&ctx_, nullptr, n_devices);
+        if (rc != SWB200_OK) throw std::runtime_error(std::string("swb200_init: ") + swb200_last_error(nullptr));
+    }
+    ~Context() { swb200_shutdown(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    swb200_ctx* get() const { return ctx_; }
+    void check(int rc) const
+    {
+        if (rc != SWB200_OK) throw std::runtime_error(std::string("swb200: ") + swb200_last_error(ctx_));
+    }
+private:
+    swb200_ctx* ctx_ = nullptr;
+};
+
+// One process-wide context on GPU 0, created on first use (the reference's kernels are
+// stateless free functions; this keeps the call sites identical).
+inline Context& default_context()
+{
+    static Context ctx(1);
+    return ctx;
+}
+
+} // namespace swb200
+
+// Drop-in for SmithWaterman_simdN (source.cpp:462-466): same arguments, same return value.
+// The per-pair call serialises on a mutex; use the batch form for throughput.
+inline int SmithWaterman_b200(
+    const std::array<uint8_t, 128>& seq1,
+    const std::array<uint8_t, 128>& seq2,
+    const std::array<int8_t, 16>& score_matrix,
+    const int8_t gap_penalty)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    swb200::Context& c = swb200::default_context();
+    int32_t score = 0;
+    c.check(swb200_score_pair(c.get(), seq1.data(), seq2.data(), score_matrix.data(), gap_penalty, &score));
+    return score;
+}
+
+// n pairs at once: seq1s[p], seq2s[p] are the reference's std::array<uint8_t,128>, which are
+// contiguous 128-byte objects, so a vector of them is exactly the [n][128] layout of the ABI.
+inline void SmithWaterman_b200_batch(
+    const std::vector<std::array<uint8_t, 128>>& seq1s,
+    const std::vector<std::array<uint8_t, 128>>& seq2s,
+    const std::array<int8_t, 16>& score_matrix,
+    const int8_t gap_penalty,
+    std::vector<int>& dest,
+    swb200::Context* ctx = nullptr)
+{
+    if (seq1s.size() != seq2s.size()) throw std::invalid_argument("SmithWaterman_b200_batch: size mismatch");
+    static_assert(sizeof(std::array<uint8_t, 128>) == 128, "std::array<uint8_t,128> must be 128 contiguous bytes");
+    static_assert(sizeof(int) == sizeof(int32_t), "int must be 32 bits");
+    swb200::Context& c = ctx ? *ctx : swb200::default_context();
+    dest.resize(seq1s.size());
+    c.check(swb200_score_batch(c.get(), seq1s.empty() ? nullptr : seq1s[0].data(), seq2s.empty() ? nullptr : seq2s[0].data(),
+                               score_matrix.data(), gap_penalty, reinterpret_cast<int32_t*>(dest.data()), seq1s.size()));
+}

@@ -80,12 +80,25 @@ def test_host_argument_checks(swb):
 
 def test_counter_pairs_are_index_addressable(swb):
     a, b = swb.counter_pairs(0, 1000)
+    an, bn = swb.counter_pairs_numpy(0, 1000)          # independent restatement of the C++ generator
+    assert np.array_equal(a, an) and np.array_equal(b, bn)
     a2, b2 = swb.counter_pairs(250, 500)
     assert np.array_equal(a[250:750], a2) and np.array_equal(b[250:750], b2)
     assert a.max() == 3 and a.min() == 0
     hist = np.bincount(np.concatenate([a.ravel(), b.ravel()]), minlength=4) / (a.size + b.size)
     assert np.all(np.abs(hist - 0.25) < 0.01)
     assert not np.array_equal(a, b)
+    pa, pb = swb.counter_pairs(250, 500, packed=True)  # 2-bit layout of source.cpp:1580-1583
+    unpacked = ((pa[:, :, None] >> (2 * np.arange(4, dtype=np.uint8))[None, None, :]) & 3).reshape(500, 128)
+    assert np.array_equal(unpacked, a2)
+
+
+def test_reference_stream_generator_matches_oracle(swb, oracle):
+    a, b = swb.reference_stream(3000)
+    ao, bo = oracle.reference_stream(3000)
+    assert np.array_equal(a, ao) and np.array_equal(b, bo)
+    s = oracle.score_batch(a[:16], b[:16], oracle.MATRIX_SPEEDTEST, 15)
+    assert swb.fnv1a64(s) == oracle.fnv1a64(s)
 
 
 def test_params_derivation_matches_documented_domain():
