@@ -342,6 +342,68 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- streaming / 100M-pair mode
+def run_stream_arm(args):
+    """BASELINE.json configs[2]/[4]: `--workload stream --pairs 100000000` -- the pair-index space
+    [0, pairs) is split in contiguous ranges over the ranks (STRONG scaling: total work fixed);
+    every rank generates its pairs on host threads into pinned ring buffers and streams them
+    through swb200_submit/_wait.  End-to-end alignments/s, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import swb200
+    from sharding import max_over_ranks, shard_range, sum_over_ranks
+    from streaming import StreamRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ddist = dist if world > 1 else None
+    matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
+    ctx = swb200.Context(devices=[local_rank])
+    lo, hi = shard_range(args.pairs, rank, world)
+    threads = max(1, (os.cpu_count() or 8) // world - 1)
+    runner = StreamRunner(ctx, batch_pairs=args.batch_pairs, n_buffers=3, packed=args.packed, gen_threads=threads)
+    runner.run(lo, min(hi - lo, 2 * args.batch_pairs), matrix, gap)      # warm-up: first-touch of pinned buffers, staging allocation
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = ctx.launch_count
+    rep = runner.run(lo, hi - lo, matrix, gap)
+    torch.cuda.synchronize()
+    wall = max_over_ranks(rep.wall_s, ddist)
+    total = sum_over_ranks(rep.pairs, ddist)
+    score_sum = sum_over_ranks(rep.score_sum, ddist)
+    gen_s = max_over_ranks(rep.produce_s, ddist)
+    wait_s = max_over_ranks(rep.wait_s, ddist)
+    launches = sum_over_ranks(ctx.launch_count - launches0, ddist)
+    if rank == 0:
+        line = {
+            "metric": "alignments_per_s_streaming_e2e", "value": total / wall, "unit": "alignments/s", "gcups": total * CELLS_PER_PAIR / wall / 1e9,
+            "n_gpus": world, "steps": 1, "warmup": 1, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+            "config": {"workload": f"streaming: {args.pairs} counter-stream pairs sharded by contiguous index range over {world} rank(s); host threads -> pinned ring buffers -> swb200_submit{'_packed' if args.packed else ''}",
+                       "pairs": args.pairs, "batch_pairs": args.batch_pairs, "wire_format": "2-bit packed (source.cpp:1580-1583), 64 B/pair" if args.packed else "byte codes, 256 B/pair",
+                       "gen_threads_per_rank": threads, "host_cores": os.cpu_count()},
+            "e2e": {"value": total / wall, "unit": "alignments/s", "h2d_bytes_per_step": int(sum_over_ranks(rep.bytes_h2d, ddist)) if world > 1 else rep.bytes_h2d,
+                    "d2h_bytes_per_step": int(sum_over_ranks(rep.bytes_d2h, ddist)) if world > 1 else rep.bytes_d2h},
+            "breakdown": {"wall_s": wall, "host_generation_s_max_rank": gen_s, "blocked_on_gpu_pipeline_s_max_rank": wait_s,
+                          "bottleneck": "host generation" if gen_s > 0.8 * wall else "PCIe/kernel pipeline"},
+            "gpu_launches": int(launches), "score_sum": int(score_sum), "mean_score": score_sum / total,
+        }
+        print(json.dumps(line), flush=True)
+    runner.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,12 +411,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["batch1m", "stream"], default="batch1m",
+                    help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")
+    ap.add_argument("--pairs", type=int, default=100_000_000)
+    ap.add_argument("--batch-pairs", type=int, default=1 << 21)
+    ap.add_argument("--packed", action="store_true", help="stream the 2-bit packed wire format (64 B/pair)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("bench.py: warmup raised to 3 (timing rules)")
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "stream":
+        run_stream_arm(args)
     else:
         run_b200_arm(args)
 

@@ -105,6 +105,9 @@ typedef uint64_t swb200_ticket;
 int swb200_submit(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
                   const int8_t* score_matrix, int8_t gap_penalty,
                   int32_t* scores, uint64_t n, swb200_ticket* ticket);
+int swb200_submit_packed(swb200_ctx* ctx, const uint8_t* seq1_packed, const uint8_t* seq2_packed,
+                         const int8_t* score_matrix, int8_t gap_penalty,
+                         int32_t* scores, uint64_t n, swb200_ticket* ticket);
 int swb200_wait(swb200_ctx* ctx, swb200_ticket ticket);
 
 /* DEVICE arrays on GPU `device_index` of the context (16-byte aligned), enqueued on

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -345,25 +346,33 @@ int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
     return score_host(ctx, seq1, seq2, false, sm, gap, score, 1);
 }
 
-int swb200_submit(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap,
-                  int32_t* scores, uint64_t n, swb200_ticket* ticket)
+static int submit_impl(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool packed, const int8_t* sm, int8_t gap,
+                       int32_t* scores, uint64_t n, swb200_ticket* ticket)
 {
     if (!ticket) return ctx ? fail(ctx, SWB200_ERR_ARG, "ticket is NULL") : SWB200_ERR_ARG;
     int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
     if (rc != SWB200_OK) return rc;
-    int8_t sm_copy[16];
-    memcpy(sm_copy, sm, 16);
+    std::array<int8_t, 16> m;
+    memcpy(m.data(), sm, 16);
     int* result = new int(SWB200_OK);
     std::lock_guard<std::mutex> lock(ctx->tickets_mu);
     const uint64_t id = ctx->next_ticket++;
-    std::thread th([=] {
-        int8_t m[16];
-        memcpy(m, sm_copy, 16);
-        *result = score_host(ctx, seq1, seq2, false, m, gap, scores, n);
-    });
+    std::thread th([=] { *result = score_host(ctx, seq1, seq2, packed, m.data(), gap, scores, n); });
     ctx->tickets.emplace(id, std::make_pair(std::move(th), result));
     *ticket = id;
     return SWB200_OK;
+}
+
+int swb200_submit(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap,
+                  int32_t* scores, uint64_t n, swb200_ticket* ticket)
+{
+    return submit_impl(ctx, seq1, seq2, false, sm, gap, scores, n, ticket);
+}
+
+int swb200_submit_packed(swb200_ctx* ctx, const uint8_t* seq1_packed, const uint8_t* seq2_packed, const int8_t* sm, int8_t gap,
+                         int32_t* scores, uint64_t n, swb200_ticket* ticket)
+{
+    return submit_impl(ctx, seq1_packed, seq2_packed, true, sm, gap, scores, n, ticket);
 }
 
 int swb200_wait(swb200_ctx* ctx, swb200_ticket ticket)

@@ -29,7 +29,7 @@ GAP_111 = 1                                                                     
 ABI_SYMBOLS = (
     "swb200_device_count", "swb200_init", "swb200_shutdown", "swb200_n_devices", "swb200_last_error",
     "swb200_strerror", "swb200_alloc_pinned", "swb200_free_pinned", "swb200_score_pair",
-    "swb200_score_batch", "swb200_score_batch_packed", "swb200_submit", "swb200_wait",
+    "swb200_score_batch", "swb200_score_batch_packed", "swb200_submit", "swb200_submit_packed", "swb200_wait",
     "swb200_score_batch_device", "swb200_score_batch_packed_device", "swb200_validate_codes_device",
     "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
@@ -86,8 +86,10 @@ def load_library():
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64]
-    lib.swb200_submit.restype = i32
-    lib.swb200_submit.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64, C.POINTER(u64)]
+    for name in ("swb200_submit", "swb200_submit_packed"):
+        f = getattr(lib, name)
+        f.restype = i32
+        f.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64, C.POINTER(u64)]
     lib.swb200_wait.restype = i32
     lib.swb200_wait.argtypes = [vp, u64]
     for name in ("swb200_score_batch_device", "swb200_score_batch_packed_device"):
@@ -239,13 +241,16 @@ class Context:
         self._check(fn(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n))
         return out[:n]
 
-    def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray) -> int:
+    def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray, packed: bool = False) -> int:
+        """Asynchronous batch: returns a ticket; the arrays must stay alive and untouched until wait(ticket)."""
         assert seq1.flags.c_contiguous and seq2.flags.c_contiguous and out.flags.c_contiguous
         assert seq1.dtype == np.uint8 and seq2.dtype == np.uint8 and out.dtype == np.int32
+        assert seq1.shape == seq2.shape and seq1.shape[1] == (32 if packed else SEQ_LEN) and out.size >= seq1.shape[0]
         m = _matrix(score_matrix)
         t = C.c_uint64()
-        self._check(self._lib.swb200_submit(self._h, seq1.ctypes.data, seq2.ctypes.data, m.ctypes.data, _gap(gap_penalty),
-                                            out.ctypes.data, seq1.shape[0], C.byref(t)))
+        fn = self._lib.swb200_submit_packed if packed else self._lib.swb200_submit
+        self._check(fn(self._h, seq1.ctypes.data, seq2.ctypes.data, m.ctypes.data, _gap(gap_penalty),
+                       out.ctypes.data, seq1.shape[0], C.byref(t)))
         return int(t.value)
 
     def wait(self, ticket: int):
