@@ -289,7 +289,7 @@ def run_b200_arm(args):
     achieved_tinstr = n * CELLS_PER_PAIR * ALGO_INSTR_PER_CELL / (avg_launch_ms * 1e-3) / 1e12
     hbm_achieved = n * ALGO_BYTES_PER_PAIR / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "int_alu", "kernel": "sw128_kernel<FAST=%d>" % info["fast_path"],
+        "bound": "int_alu", "kernel": "swb::sw_kernel<FAST=%d, L=128, NT=128, MINB=3>" % info["fast_path"],
         "achieved": achieved_tinstr, "peak": alu_peak_tinstr, "unit": "Tinstr/s (thread-level packed int16x2 ALU instructions)",
         "frac": achieved_tinstr / alu_peak_tinstr,
         "algorithmic_instr_per_cell": ALGO_INSTR_PER_CELL, "cells_per_launch": n * CELLS_PER_PAIR,
@@ -404,6 +404,50 @@ def run_stream_arm(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- length sweep
+def run_sweep_arm(args):
+    """BASELINE.json configs[3]: `--workload sweep` -- square pairs of 128, 256 and 512 bases on one
+    GPU, device-resident, the same number of cells per launch (2^34) at every length."""
+    import torch
+    import swb200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- no CPU fallback")
+    torch.cuda.set_device(0)
+    matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
+    ctx = swb200.Context(devices=[0])
+    peaks = load_peaks()
+    rows = []
+    for L in swb200.SWEEP_LENGTHS:
+        n = (1 << 34) // (L * L)
+        g = torch.Generator(device="cuda").manual_seed(1234 + L)
+        d_a = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
+        d_b = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
+        d_s = torch.empty(n, dtype=torch.int32, device="cuda")
+        for _ in range(max(3, args.warmup)):
+            ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        info = ctx.kernel_info(matrix, gap, seq_len=L)
+        gcups = n * L * L / (ms * 1e-3) / 1e9
+        peak_t = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        rows.append({"seq_len": L, "pairs": n, "ms_per_launch": ms, "gcups": gcups, "alignments_per_s": n / (ms * 1e-3),
+                     "roofline_frac": gcups * 1e9 * ALGO_INSTR_PER_CELL / 1e12 / peak_t, "mean_score": float(d_s.float().mean().item()), "kernel": info})
+        del d_a, d_b, d_s
+    line = {"metric": "GCUPS", "unit": "GCUPS", "value": rows[0]["gcups"], "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": rows[0]["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), 2^34 cells per launch, iid pairs, matrix +10/-30, gap 15",
+                       "roofline_peak": f"{peaks['alu_src']}, at sm_max clock"},
+            "sweep": rows}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -411,7 +455,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["batch1m", "stream"], default="batch1m",
+    ap.add_argument("--workload", choices=["batch1m", "stream", "sweep"], default="batch1m",
                     help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
@@ -424,6 +468,8 @@ def main():
         run_reference_arm(args)
     elif args.workload == "stream":
         run_stream_arm(args)
+    elif args.workload == "sweep":
+        run_sweep_arm(args)
     else:
         run_b200_arm(args)
 

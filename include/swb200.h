@@ -122,6 +122,17 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index,
                                      const int8_t* score_matrix, int8_t gap_penalty,
                                      int32_t* d_scores, uint64_t n, void* cuda_stream);
 
+/* Length sweep (BASELINE.json configs[3]): the same scoring for square pairs of seq_len bases,
+ * seq_len in {128, 256, 512}; arrays are [n][seq_len].  The oracle is the scalar recurrence of
+ * source.cpp:35-60 restated for any length.  SWB200_ERR_DOMAIN when seq_len * max(score_matrix)
+ * does not fit the packed int16 arithmetic (possible only at 512). */
+int swb200_score_batch_len(swb200_ctx* ctx, int seq_len, const uint8_t* seq1, const uint8_t* seq2,
+                           const int8_t* score_matrix, int8_t gap_penalty, int32_t* scores, uint64_t n);
+int swb200_score_batch_len_device(swb200_ctx* ctx, int device_index, int seq_len,
+                                  const uint8_t* d_seq1, const uint8_t* d_seq2,
+                                  const int8_t* score_matrix, int8_t gap_penalty,
+                                  int32_t* d_scores, uint64_t n, void* cuda_stream);
+
 /* Counts bytes > 3 in a DEVICE buffer (the reference never checks, source.cpp:50). */
 int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_t* d_codes,
                                  uint64_t n_bytes, uint64_t* n_bad, void* cuda_stream);
@@ -140,6 +151,9 @@ typedef struct swb200_kernel_info {
 
 /* Which kernel swb200_score_batch* would launch for this matrix/gap, and its resources. */
 int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* score_matrix,
+                           int8_t gap_penalty, swb200_kernel_info* info);
+
+int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const int8_t* score_matrix,
                            int8_t gap_penalty, swb200_kernel_info* info);
 
 /* Kernel launches issued by this context since creation (all GPUs). */

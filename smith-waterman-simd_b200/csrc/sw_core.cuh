@@ -93,7 +93,7 @@ struct SwParams {
     uint32_t dummy;    // profile word of an inert row (its cells never exceed a real neighbour)
     uint32_t G;        // fast: (g,g)
     uint32_t NG;       // general: (-g,-g)
-    uint32_t C;        // fast: (128g,128g), subtracted from every live value once per strip (frame renormalisation)
+    uint32_t C;        // fast: (L*g,L*g), subtracted from every live value once per strip (frame renormalisation)
     uint32_t one;      // 1          } multipliers the compiler cannot fold: `a*one + b` stays an IMAD, i.e. the
     uint32_t mone;     // 0xffffffff } frame bookkeeping adds run on the FMA pipe while the ALU pipe is saturated
     int32_t  gap;      // g
@@ -105,10 +105,9 @@ struct SwParams {
 SWB_HD uint32_t fadd(uint32_t a, uint32_t b, const SwParams& p) { return a * p.one + b; }
 SWB_HD uint32_t fsub(uint32_t a, uint32_t b, const SwParams& p) { return b * p.mone + a; }
 
-constexpr int SW_L = 128;          // sequence length (source.cpp:36-37)
+constexpr int SW_L = 128;          // the reference's sequence length (source.cpp:36-37); the kernels are templated
+                                   // on L (a multiple of 16) for the length sweep, BASELINE.json configs[3]
 constexpr int SW_R = 16;           // strip height = cells per anti-diagonal step per thread
-constexpr int SW_STRIPS = SW_L / SW_R;
-constexpr int SW_ITERS = SW_STRIPS * (SW_L / 16) + 1;   // 16-step iterations incl. the draining one
 
 // Thread-private state.  Everything is indexed by compile-time constants after unrolling,
 // so it lives in registers.
@@ -161,7 +160,7 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 //         columns col0..col0+15; columns col0+8.. are loaded here at u = 0, the next
 //         iteration's first eight at u = 8 (always 8 steps ahead of their first use).
 //   aw_lo/aw_hi: (WRAP only) the 16 query bases of the strip being entered.
-template <bool FAST, bool WRAP, class Fifo, class Table>
+template <bool FAST, bool WRAP, int L, class Fifo, class Table>
 SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
                       const uint8_t* b_lo, uint32_t dq,
                       const uint32_t (&aw_lo)[4], const uint32_t (&aw_hi)[4], bool next_is_dummy)
@@ -176,7 +175,7 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
         if (u == 8) {
-            const uint8_t* p = b_lo + (((WRAP ? 0 : col0) + 16) & (SW_L - 1));
+            const uint8_t* p = b_lo + (((WRAP ? 0 : col0) + 16) & (L - 1));
             ld8(p, st.bq_lo[0], st.bq_lo[1]);
             ld8(p + dq, st.bq_hi[0], st.bq_hi[1]);
         }
@@ -225,7 +224,7 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         // --- bottom row to the FIFO (column of row 15 at this step), as a true H value.
         //     (a WRAP iteration always starts at column 0; elsewhere col0 >= 16 and nothing wraps,
         //     so every FIFO address is `per-iteration base + compile-time offset`)
-        fifo.push(WRAP ? ((u - (SW_R - 1)) & (SW_L - 1)) : (col0 + u - (SW_R - 1)),
+        fifo.push(WRAP ? ((u - (SW_R - 1)) & (L - 1)) : (col0 + u - (SW_R - 1)),
                   FAST ? fsub(hn[SW_R - 1], st.Z, prm) : hn[SW_R - 1]);   // plain subtract: hn >= Z in both halves
         // --- running best
         if (FAST) st.B = vaddmax2(st.B, prm.G, hn[0]);
@@ -241,11 +240,11 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
 }
 
 // Scores two pairs: (a_lo,b_lo) in the low halves, (a_lo+dq, b_lo+dq) in the high halves
-// (dq = 128 for the neighbouring pair, 0 when the batch's last pair stands alone).
-// Both pointers address 128 byte-coded bases (0..3), 8-byte aligned.
-// The FIFO must hold 128 words for this thread; it is (re)initialised here.
-template <bool FAST, class Fifo, class Table>
-SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
+// (dq = L for the neighbouring pair, 0 when the batch's last pair stands alone).
+// Both pointers address L byte-coded bases (0..3), 8-byte aligned; L is a power of two >= 32.
+// The FIFO must hold L words for this thread; it is (re)initialised here.
+template <bool FAST, int L, class Fifo, class Table>
+SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
                             Fifo& fifo, const Table& t4, const SwParams& prm, int32_t& score_lo, int32_t& score_hi)
 {
     SwState st;
@@ -255,7 +254,8 @@ SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t d
         st.prA[k] = prm.dummy; st.prB[k] = prm.dummy;
     }
     // Top boundary H[0][*] = 0 (source.cpp:44)
-    for (int c = 0; c < SW_L; ++c) fifo.push(c, 0u);
+    constexpr int STRIPS = L / SW_R;
+    for (int c = 0; c < L; ++c) fifo.push(c, 0u);
     st.Z = FAST ? prm.G + prm.G : 0u;         // Z_0 = g*(0+2)
     st.Zp = FAST ? prm.G : 0u;                // Z_{-1}
     st.B = FAST ? prm.G : 0u;                 // best = 0 in the frame of step -1
@@ -267,24 +267,24 @@ SWB_HD void sw128_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t d
     ld8(b_lo + dq, st.bq_hi[0], st.bq_hi[1]);
     ld16(a_lo, an_lo); ld16(a_lo + dq, an_hi);
 
-    for (int strip = 0; strip <= SW_STRIPS; ++strip) {
+    for (int strip = 0; strip <= STRIPS; ++strip) {
         if (FAST && strip > 0) {
-            // Renormalise the frame: T restarts at 0, every live value drops by 128g
-            // (all are >= Z_{T-2} = 128g here, so the plain subtraction cannot borrow).
+            // Renormalise the frame: T restarts at 0, every live value drops by L*g
+            // (all are >= Z_{T-2} = L*g here, so the plain subtraction cannot borrow).
 #pragma unroll
             for (int k = 0; k < SW_R; ++k) { st.h1[k] = fsub(st.h1[k], prm.C, prm); st.h2[k] = fsub(st.h2[k], prm.C, prm); }
             st.Z = fsub(st.Z, prm.C, prm); st.Zp = fsub(st.Zp, prm.C, prm);
             st.B = fsub(st.B, prm.C, prm); st.up0 = fsub(st.up0, prm.C, prm);
         }
-        sw_iter16<FAST, true>(st, fifo, t4, prm, 0, b_lo, dq, an_lo, an_hi, strip >= SW_STRIPS);
-        if (strip == SW_STRIPS) break;
+        sw_iter16<FAST, true, L>(st, fifo, t4, prm, 0, b_lo, dq, an_lo, an_hi, strip >= STRIPS);
+        if (strip == STRIPS) break;
 #pragma unroll 1
-        for (int j = 1; j < SW_L / 16; ++j) {
-            if (j == SW_L / 16 - 1) {   // one iteration ahead of the wrap that consumes them
-                const int ns = (strip + 1 < SW_STRIPS) ? strip + 1 : SW_STRIPS - 1;
+        for (int j = 1; j < L / 16; ++j) {
+            if (j == L / 16 - 1) {   // one iteration ahead of the wrap that consumes them
+                const int ns = (strip + 1 < STRIPS) ? strip + 1 : STRIPS - 1;
                 ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dq, an_hi);
             }
-            sw_iter16<FAST, false>(st, fifo, t4, prm, 16 * j, b_lo, dq, an_lo, an_hi, false);
+            sw_iter16<FAST, false, L>(st, fifo, t4, prm, 16 * j, b_lo, dq, an_lo, an_hi, false);
         }
     }
     if (FAST) {

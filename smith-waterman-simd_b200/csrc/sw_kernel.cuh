@@ -31,16 +31,21 @@ struct SmemTable {
     }
 };
 
-template <int NT>
-constexpr size_t sw128_smem_bytes() { return (size_t)(SW_L * NT + 4) * sizeof(uint32_t); }
+template <int L, int NT>
+constexpr size_t sw_smem_bytes() { return (size_t)(L * NT + 4) * sizeof(uint32_t); }
 
-template <bool FAST, int NT, int MINB>
+template <int NT>
+constexpr size_t sw128_smem_bytes() { return sw_smem_bytes<SW_L, NT>(); }
+
+// Sequence length L is a template parameter (128 = the reference's shape; 256 and 512 for the
+// length sweep).  The per-thread FIFO is L words of shared memory, so NT shrinks as L grows.
+template <bool FAST, int L, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
-sw128_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
+sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
              int32_t* __restrict__ scores, unsigned long long n, const SwParams prm)
 {
     extern __shared__ uint32_t smem[];
-    uint32_t* t4s = smem + SW_L * NT;
+    uint32_t* t4s = smem + L * NT;
     if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
     __syncthreads();
 
@@ -51,7 +56,7 @@ sw128_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
     SmemFifo<NT> fifo{smem + threadIdx.x};
     SmemTable t4{t4s};
     int32_t lo, hi;
-    sw128_two_pairs<FAST>(seq1 + p * SW_L, seq2 + p * SW_L, (q != p) ? (uint32_t)SW_L : 0u, fifo, t4, prm, lo, hi);
+    sw_two_pairs<FAST, L>(seq1 + p * L, seq2 + p * L, (q != p) ? (uint32_t)L : 0u, fifo, t4, prm, lo, hi);
     if (q != p) {
         *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
     } else {

@@ -21,16 +21,26 @@ inline int sw_check_domain(const int8_t sm[16], int gap)
 
 inline uint32_t sw_pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
 
-inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general = 0)
+// Whether sequences of length L can be scored at all in packed int16: the largest H is
+// L * max(S) (source.cpp:47-53), which must fit.  True for every reference-domain matrix at
+// L = 128 (128*127 = 16256) and L = 256; at L = 512 it needs max(S) <= 63.
+inline bool sw_len_supported(const int8_t sm[16], int L)
+{
+    int smax = 0;
+    for (int i = 0; i < 16; ++i) if (sm[i] > smax) smax = sm[i];
+    return (L == 128 || L == 256 || L == 512) && L * smax <= 32767;
+}
+
+inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general = 0, int L = SW_L)
 {
     SwParams p;
     int smax = 0;
     for (int i = 0; i < 16; ++i) if (sm[i] > smax) smax = sm[i];
     // Fast path (anti-diagonal offset DP) is exact iff every shifted score
-    // e = max(S,-2g)+2g fits a non-negative signed byte, i.e. smax + 2g <= 127.  The frame is
-    // renormalised every 128 steps, so the largest packed value is 128*smax + 130g
-    // <= 128*(127-2g) + 130g <= 16256: int16 never overflows on this domain.
-    const bool fast = !force_general && (smax + 2 * gap <= 127);
+    // e = max(S,-2g)+2g fits a non-negative signed byte (smax + 2g <= 127) and the largest
+    // packed value L*smax + (L+2)*g fits int16.  The frame is renormalised every L steps; at
+    // L = 128 the second condition follows from the first (128*(127-2g) + 130g <= 16256).
+    const bool fast = !force_general && (smax + 2 * gap <= 127) && (L * smax + (L + 2) * gap <= 32767);
     p.fast = fast ? 1 : 0;
     p.gap = gap;
     for (int a = 0; a < 4; ++a) {
@@ -45,7 +55,7 @@ inline SwParams sw_make_params(const int8_t sm[16], int gap, int force_general =
     p.dummy = fast ? 0u : 0x81818181u;   // fast: e = 0 (a step worth two gaps); general: S = -127
     p.G = sw_pack2(gap);
     p.NG = sw_pack2(-gap);
-    p.C = sw_pack2(SW_L * gap);
+    p.C = sw_pack2(L * gap);
     p.one = 1u;
     p.mone = 0xffffffffu;
     return p;

@@ -23,10 +23,8 @@ namespace {
 
 using namespace swb;
 
-constexpr int kNT = 128;         // threads per block: 64 KiB of FIFO
-constexpr int kMinBlocks = 3;    // resident blocks per SM the register budget is set for
 constexpr int kSlots = 3;        // chunks in flight per GPU
-constexpr uint64_t kChunkPairs = 1ull << 17;   // 131072 pairs = 16 MiB per sequence array per chunk
+constexpr uint64_t kChunkPairs = 1ull << 17;   // 131072 pairs of 128 bases = 16 MiB per sequence array per chunk (fewer pairs for longer sequences)
 
 thread_local std::string g_init_error;
 
@@ -104,19 +102,54 @@ __global__ void count_bad_codes_kernel(const uint8_t* __restrict__ codes, unsign
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_bad, local);
 }
 
-template <bool FAST>
-cudaError_t launch_sw128(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st)
+// Launch geometry per sequence length: the FIFO is L words of shared memory per thread, so the
+// block shrinks as L grows (64 KiB of FIFO per block, 3 resident blocks per SM in every case).
+template <int L> struct LenCfg;
+template <> struct LenCfg<128> { static constexpr int NT = 128, MINB = 3; };
+template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; };
+template <> struct LenCfg<512> { static constexpr int NT = 32,  MINB = 3; };
+
+template <bool FAST, int L>
+cudaError_t launch_sw(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    constexpr int NT = LenCfg<L>::NT;
     const uint64_t threads = (n + 1) / 2;
-    const unsigned grid = (unsigned)((threads + kNT - 1) / kNT);
-    sw128_kernel<FAST, kNT, kMinBlocks><<<grid, kNT, sw128_smem_bytes<kNT>(), st>>>(d1, d2, dsc, n, prm);
+    const unsigned grid = (unsigned)((threads + NT - 1) / NT);
+    sw_kernel<FAST, L, NT, LenCfg<L>::MINB><<<grid, NT, sw_smem_bytes<L, NT>(), st>>>(d1, d2, dsc, n, prm);
     return cudaGetLastError();
 }
 
-cudaError_t launch_for(const SwParams& prm, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st)
+cudaError_t launch_for(const SwParams& prm, int L, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st)
 {
-    return prm.fast ? launch_sw128<true>(d1, d2, dsc, n, prm, st) : launch_sw128<false>(d1, d2, dsc, n, prm, st);
+    switch (L) {
+    case 128: return prm.fast ? launch_sw<true, 128>(d1, d2, dsc, n, prm, st) : launch_sw<false, 128>(d1, d2, dsc, n, prm, st);
+    case 256: return prm.fast ? launch_sw<true, 256>(d1, d2, dsc, n, prm, st) : launch_sw<false, 256>(d1, d2, dsc, n, prm, st);
+    case 512: return prm.fast ? launch_sw<true, 512>(d1, d2, dsc, n, prm, st) : launch_sw<false, 512>(d1, d2, dsc, n, prm, st);
+    default:  return cudaErrorInvalidValue;
+    }
+}
+
+template <bool FAST, int L>
+cudaError_t prepare_kernel()
+{
+    constexpr int NT = LenCfg<L>::NT;
+    auto kern = sw_kernel<FAST, L, NT, LenCfg<L>::MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes<L, NT>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <bool FAST, int L>
+cudaError_t kernel_resources(cudaFuncAttributes* fa, int* blocks, int* nt, int* smem)
+{
+    constexpr int NT = LenCfg<L>::NT;
+    auto kern = sw_kernel<FAST, L, NT, LenCfg<L>::MINB>;
+    cudaError_t e = cudaFuncGetAttributes(fa, kern);
+    if (e != cudaSuccess) return e;
+    *nt = NT;
+    *smem = (int)sw_smem_bytes<L, NT>();
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, sw_smem_bytes<L, NT>());
 }
 
 cudaError_t launch_unpack(const uint8_t* d_packed, uint8_t* d_codes, uint64_t n_seqs, cudaStream_t st)
@@ -132,10 +165,9 @@ int setup_device(swb200_ctx* ctx, Device* d)
 {
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     SWB_CUDA(ctx, cudaGetDeviceProperties(&d->prop, d->id));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<true, kNT, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw128_smem_bytes<kNT>()));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<false, kNT, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw128_smem_bytes<kNT>()));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<true, kNT, kMinBlocks>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sw128_kernel<false, kNT, kMinBlocks>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SWB_CUDA(ctx, (prepare_kernel<true, 128>()));  SWB_CUDA(ctx, (prepare_kernel<false, 128>()));
+    SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
+    SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
     for (Slot& s : d->slots) {
         SWB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -164,7 +196,7 @@ int ensure_staging(swb200_ctx* ctx, Device* d, bool packed)
 
 // One GPU's share [lo, hi) of a host batch: chunks of kChunkPairs cycle through kSlots
 // streams, so chunk c+1's H2D and chunk c-1's D2H run under chunk c's kernel.
-int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed,
+int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed, int L,
               const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi)
 {
     if (hi <= lo) return SWB200_OK;
@@ -172,11 +204,12 @@ int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* se
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     int rc = ensure_staging(ctx, d, packed);
     if (rc != SWB200_OK) return rc;
-    const size_t in_stride = packed ? 32 : SWB200_SEQ_LEN;
+    const size_t in_stride = packed ? 32 : (size_t)L;
+    const uint64_t chunk = kChunkPairs * SWB200_SEQ_LEN / (uint64_t)L;    // same bytes per chunk at every length
     int si = 0;
-    for (uint64_t c0 = lo; c0 < hi; c0 += kChunkPairs, si = (si + 1) % kSlots) {
+    for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si = (si + 1) % kSlots) {
         Slot& s = d->slots[si];
-        const uint64_t m = (hi - c0 < kChunkPairs) ? hi - c0 : kChunkPairs;
+        const uint64_t m = (hi - c0 < chunk) ? hi - c0 : chunk;
         if (s.busy) SWB_CUDA(ctx, cudaEventSynchronize(s.done));
         uint8_t* in1 = packed ? s.d_pk1 : s.d_seq1;
         uint8_t* in2 = packed ? s.d_pk2 : s.d_seq2;
@@ -187,7 +220,7 @@ int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* se
             SWB_CUDA(ctx, launch_unpack(s.d_pk2, s.d_seq2, m, s.stream));
             ctx->launches += 2;
         }
-        SWB_CUDA(ctx, launch_for(prm, s.d_seq1, s.d_seq2, s.d_scores, m, s.stream));
+        SWB_CUDA(ctx, launch_for(prm, L, s.d_seq1, s.d_seq2, s.d_scores, m, s.stream));
         ctx->launches += 1;
         SWB_CUDA(ctx, cudaMemcpyAsync(scores + c0, s.d_scores, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         SWB_CUDA(ctx, cudaEventRecord(s.done, s.stream));
@@ -209,21 +242,29 @@ int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, 
     return SWB200_OK;
 }
 
+int check_len(swb200_ctx* ctx, const int8_t* sm, int L)
+{
+    if (L != 128 && L != 256 && L != 512) return fail(ctx, SWB200_ERR_ARG, "seq_len must be 128, 256 or 512");
+    if (!sw_len_supported(sm, L)) return fail(ctx, SWB200_ERR_DOMAIN, "seq_len * max(score_matrix) exceeds the packed int16 range");
+    return SWB200_OK;
+}
+
 int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool packed,
-               const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n)
+               const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n, int L = SWB200_SEQ_LEN)
 {
     int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
+    if (rc == SWB200_OK) rc = check_len(ctx, sm, L);
     if (rc != SWB200_OK || n == 0) return rc;
-    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
-    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, prm, scores, 0, n);
+    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, L, prm, scores, 0, n);
     // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
     // every GPU DMA-writes its own slice of `scores`: that is the whole gather.
     std::vector<std::thread> pool;
     std::vector<int> rcs(G, SWB200_OK);
     for (size_t k = 0; k < G; ++k) {
         const uint64_t lo = n * k / G, hi = n * (k + 1) / G;
-        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, prm, scores, lo, hi); });
+        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, L, prm, scores, lo, hi); });
     }
     for (auto& t : pool) t.join();
     for (int r : rcs) if (r != SWB200_OK) return r;
@@ -402,17 +443,30 @@ static int device_args(swb200_ctx* ctx, int device_index, const void* a, const v
     return SWB200_OK;
 }
 
-int swb200_score_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2,
-                              const int8_t* sm, int8_t gap, int32_t* d_scores, uint64_t n, void* cuda_stream)
+int swb200_score_batch_len_device(swb200_ctx* ctx, int device_index, int seq_len, const uint8_t* d_seq1, const uint8_t* d_seq2,
+                                  const int8_t* sm, int8_t gap, int32_t* d_scores, uint64_t n, void* cuda_stream)
 {
     int rc = check_args(ctx, d_seq1, d_seq2, sm, gap, d_scores, n);
+    if (rc == SWB200_OK) rc = check_len(ctx, sm, seq_len);
     if (rc == SWB200_OK) rc = device_args(ctx, device_index, d_seq1, d_seq2, d_scores, n);
     if (rc != SWB200_OK || n == 0) return rc;
     SWB_CUDA(ctx, cudaSetDevice(ctx->devs[device_index]->id));
-    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
-    SWB_CUDA(ctx, launch_for(prm, d_seq1, d_seq2, d_scores, n, (cudaStream_t)cuda_stream));
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general, seq_len);
+    SWB_CUDA(ctx, launch_for(prm, seq_len, d_seq1, d_seq2, d_scores, n, (cudaStream_t)cuda_stream));
     ctx->launches += 1;
     return SWB200_OK;
+}
+
+int swb200_score_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2,
+                              const int8_t* sm, int8_t gap, int32_t* d_scores, uint64_t n, void* cuda_stream)
+{
+    return swb200_score_batch_len_device(ctx, device_index, SWB200_SEQ_LEN, d_seq1, d_seq2, sm, gap, d_scores, n, cuda_stream);
+}
+
+int swb200_score_batch_len(swb200_ctx* ctx, int seq_len, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap,
+                           int32_t* scores, uint64_t n)
+{
+    return score_host(ctx, seq1, seq2, false, sm, gap, scores, n, seq_len);
 }
 
 int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const uint8_t* d_pk1, const uint8_t* d_pk2,
@@ -434,7 +488,7 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const ui
         const uint64_t m = (n - c0 < kChunkPairs) ? n - c0 : kChunkPairs;
         SWB_CUDA(ctx, launch_unpack(d_pk1 + c0 * 32, s.d_seq1, m, st));
         SWB_CUDA(ctx, launch_unpack(d_pk2 + c0 * 32, s.d_seq2, m, st));
-        SWB_CUDA(ctx, launch_for(prm, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
+        SWB_CUDA(ctx, launch_for(prm, SWB200_SEQ_LEN, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
         ctx->launches += 3;
     }
     return SWB200_OK;
@@ -461,33 +515,40 @@ int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_
     return SWB200_OK;
 }
 
-int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, int8_t gap, swb200_kernel_info* info)
+int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const int8_t* sm, int8_t gap, swb200_kernel_info* info)
 {
     if (!ctx || !info || !sm) return SWB200_ERR_ARG;
     if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
     if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return fail(ctx, SWB200_ERR_DOMAIN, "matrix/gap outside the domain");
+    int rc = check_len(ctx, sm, seq_len);
+    if (rc != SWB200_OK) return rc;
     Device* d = ctx->devs[device_index];
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
+    const SwParams prm = sw_make_params(sm, gap, ctx->force_general, seq_len);
     cudaFuncAttributes fa{};
-    int blocks = 0;
-    if (prm.fast) {
-        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sw128_kernel<true, kNT, kMinBlocks>));
-        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sw128_kernel<true, kNT, kMinBlocks>, kNT, sw128_smem_bytes<kNT>()));
-    } else {
-        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sw128_kernel<false, kNT, kMinBlocks>));
-        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sw128_kernel<false, kNT, kMinBlocks>, kNT, sw128_smem_bytes<kNT>()));
+    int blocks = 0, nt = 0, smem = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (seq_len) {
+    case 128: e = prm.fast ? kernel_resources<true, 128>(&fa, &blocks, &nt, &smem) : kernel_resources<false, 128>(&fa, &blocks, &nt, &smem); break;
+    case 256: e = prm.fast ? kernel_resources<true, 256>(&fa, &blocks, &nt, &smem) : kernel_resources<false, 256>(&fa, &blocks, &nt, &smem); break;
+    case 512: e = prm.fast ? kernel_resources<true, 512>(&fa, &blocks, &nt, &smem) : kernel_resources<false, 512>(&fa, &blocks, &nt, &smem); break;
     }
+    SWB_CUDA(ctx, e);
     info->fast_path = prm.fast;
     info->regs_per_thread = fa.numRegs;
-    info->threads_per_block = kNT;
+    info->threads_per_block = nt;
     info->blocks_per_sm = blocks;
-    info->smem_bytes_per_block = (int)sw128_smem_bytes<kNT>();
+    info->smem_bytes_per_block = smem;
     info->sm_count = d->prop.multiProcessorCount;
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->id);
     info->sm_clock_khz = khz;
     return SWB200_OK;
+}
+
+int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, int8_t gap, swb200_kernel_info* info)
+{
+    return swb200_kernel_info_len(ctx, device_index, SWB200_SEQ_LEN, sm, gap, info);
 }
 
 uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }

@@ -27,7 +27,7 @@ class StreamReport:
     pairs: int = 0
     wall_s: float = 0.0
     produce_s: float = 0.0       # summed over batches: time spent generating (all producer threads, wall per batch)
-    wait_s: float = 0.0          # driver thread blocked in swb200_wait
+    wait_s: float = 0.0          # driver thread blocked on the GPU pipeline (a slot it needs is still in flight)
     batches: int = 0
     bytes_h2d: int = 0
     bytes_d2h: int = 0
@@ -67,10 +67,12 @@ class StreamRunner:
             b = swb200.PinnedArray((self.batch, self.width), np.uint8)
             s = swb200.PinnedArray((self.batch,), np.int32)
             self.bufs.append((a, b, s))
-        self.pool = ThreadPoolExecutor(max_workers=1)   # one batch is generated ahead while the driver submits/waits
+        self.pool = ThreadPoolExecutor(max_workers=1)       # generates one batch ahead of the GPU
+        self.finisher = ThreadPoolExecutor(max_workers=1)   # waits for tickets and checksums finished batches, in order
 
     def close(self):
         self.pool.shutdown(wait=True)
+        self.finisher.shutdown(wait=True)
         for a, b, s in self.bufs:
             a.free(); b.free(); s.free()
         self.bufs = []
@@ -84,36 +86,39 @@ class StreamRunner:
     def run(self, first: int, total: int, score_matrix, gap_penalty, seed: int = 10000,
             on_batch: Optional[Callable[[int, np.ndarray], None]] = None) -> StreamReport:
         """Scores pairs [first, first+total).  `on_batch(batch_first_index, scores_view)` is called
-        with each finished batch (the view is only valid during the call)."""
+        (on the finisher thread, in batch order) with each finished batch; the view is only valid
+        during the call.  Three stages overlap: generation of batch i+1, GPU pipeline of batch i,
+        checksum/callback of batch i-1."""
         rep = StreamReport()
         nb = len(self.bufs)
         starts = list(range(first, first + total, self.batch))
         sizes = [min(self.batch, first + total - s0) for s0 in starts]
-        inflight = {}    # slot -> (ticket, start, size)
+        done = {}    # slot -> future of the finisher for the batch that last used it
         t0 = time.perf_counter()
         fut = self.pool.submit(self._produce, 0, starts[0], sizes[0], seed) if starts else None
         for i, (s0, m) in enumerate(zip(starts, sizes)):
             slot = i % nb
             rep.produce_s += fut.result()
-            # generate the next batch while this one is on the GPU; its slot must be free first
-            if i + 1 < len(starts):
+            if i + 1 < len(starts):     # the next batch's slot must have been fully consumed before it is overwritten
                 nslot = (i + 1) % nb
-                if nslot in inflight:
-                    self._finish(inflight.pop(nslot), nslot, rep, on_batch)
+                if nslot in done:
+                    t = time.perf_counter()
+                    done.pop(nslot).result()
+                    rep.wait_s += time.perf_counter() - t
                 fut = self.pool.submit(self._produce, nslot, starts[i + 1], sizes[i + 1], seed)
             a, b, s = self.bufs[slot]
             ticket = self.ctx.submit(a.array[:m], b.array[:m], score_matrix, gap_penalty, s.array[:m], packed=self.packed)
-            inflight[slot] = (ticket, s0, m)
-        for slot in sorted(inflight, key=lambda k: inflight[k][1]):
-            self._finish(inflight[slot], slot, rep, on_batch)
+            done[slot] = self.finisher.submit(self._finish, (ticket, s0, m), slot, rep, on_batch)
+        t = time.perf_counter()
+        for f in done.values():
+            f.result()
+        rep.wait_s += time.perf_counter() - t
         rep.wall_s = time.perf_counter() - t0
         return rep
 
     def _finish(self, job, slot, rep: StreamReport, on_batch):
         ticket, s0, m = job
-        t = time.perf_counter()
         self.ctx.wait(ticket)
-        rep.wait_s += time.perf_counter() - t
         scores = self.bufs[slot][2].array[:m]
         rep.pairs += m
         rep.batches += 1

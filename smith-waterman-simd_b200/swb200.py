@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswb200.so")
 SEQ_LEN = 128
+SWEEP_LENGTHS = (128, 256, 512)   # BASELINE.json configs[3]: 1x, 2x, 4x the built-in shape
 
 # reference harness constants
 MATRIX_SPEEDTEST = (10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10)  # source.cpp:3041-3045
@@ -33,7 +34,7 @@ ABI_SYMBOLS = (
     "swb200_score_batch_device", "swb200_score_batch_packed_device", "swb200_validate_codes_device",
     "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
-    "swb200_fnv1a64_i32",
+    "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -96,6 +97,12 @@ def load_library():
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [vp, i32, vp, vp, vp, C.c_int8, vp, u64, vp]
+    lib.swb200_score_batch_len.restype = i32
+    lib.swb200_score_batch_len.argtypes = [vp, i32, vp, vp, vp, C.c_int8, vp, u64]
+    lib.swb200_score_batch_len_device.restype = i32
+    lib.swb200_score_batch_len_device.argtypes = [vp, i32, i32, vp, vp, vp, C.c_int8, vp, u64, vp]
+    lib.swb200_kernel_info_len.restype = i32
+    lib.swb200_kernel_info_len.argtypes = [vp, i32, i32, vp, C.c_int8, C.POINTER(KernelInfo)]
     lib.swb200_validate_codes_device.restype = i32
     lib.swb200_validate_codes_device.argtypes = [vp, i32, vp, u64, C.POINTER(u64), vp]
     lib.swb200_kernel_info_for.restype = i32
@@ -207,10 +214,10 @@ class Context:
     def set_force_general(self, on: bool):
         self._check(self._lib.swb200_set_force_general(self._h, int(on)))
 
-    def kernel_info(self, score_matrix, gap_penalty, device_index: int = 0) -> dict:
+    def kernel_info(self, score_matrix, gap_penalty, device_index: int = 0, seq_len: int = SEQ_LEN) -> dict:
         m = _matrix(score_matrix)
         info = KernelInfo()
-        self._check(self._lib.swb200_kernel_info_for(self._h, device_index, m.ctypes.data, _gap(gap_penalty), C.byref(info)))
+        self._check(self._lib.swb200_kernel_info_len(self._h, device_index, seq_len, m.ctypes.data, _gap(gap_penalty), C.byref(info)))
         return {k: getattr(info, k) for k, _ in KernelInfo._fields_}
 
     # -- the reference's per-pair call (source.cpp:462-466)
@@ -227,18 +234,22 @@ class Context:
     # -- the batch loop (source.cpp:2947-2970), host arrays
     def score_batch(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty,
                     out: Optional[np.ndarray] = None, packed: bool = False) -> np.ndarray:
-        width = 32 if packed else SEQ_LEN
         a = np.ascontiguousarray(seq1, dtype=np.uint8)
         b = np.ascontiguousarray(seq2, dtype=np.uint8)
-        if a.ndim != 2 or a.shape[1] != width or a.shape != b.shape:
-            raise ValueError(f"seq1 and seq2 must both be uint8 [n][{width}]")
-        n = a.shape[0]
+        if a.ndim != 2 or a.shape != b.shape or (packed and a.shape[1] != 32) or (not packed and a.shape[1] not in SWEEP_LENGTHS):
+            raise ValueError("seq1 and seq2 must both be uint8 [n][128] ([n][256] / [n][512] for the length sweep; [n][32] packed)")
+        n, width = a.shape
         m = _matrix(score_matrix)
         if out is None:
             out = np.empty(n, dtype=np.int32)
         assert out.dtype == np.int32 and out.size >= n and out.flags.c_contiguous
-        fn = self._lib.swb200_score_batch_packed if packed else self._lib.swb200_score_batch
-        self._check(fn(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n))
+        if packed:
+            rc = self._lib.swb200_score_batch_packed(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n)
+        elif width == SEQ_LEN:
+            rc = self._lib.swb200_score_batch(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n)
+        else:
+            rc = self._lib.swb200_score_batch_len(self._h, width, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n)
+        self._check(rc)
         return out[:n]
 
     def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray, packed: bool = False) -> int:
@@ -265,9 +276,13 @@ class Context:
         m = _matrix(score_matrix)
         if stream is None:
             stream = torch.cuda.current_stream(d_seq1.device).cuda_stream
-        fn = self._lib.swb200_score_batch_packed_device if packed else self._lib.swb200_score_batch_device
-        self._check(fn(self._h, device_index, d_seq1.data_ptr(), d_seq2.data_ptr(), m.ctypes.data, _gap(gap_penalty),
-                       d_scores.data_ptr(), n, stream))
+        if packed:
+            rc = self._lib.swb200_score_batch_packed_device(self._h, device_index, d_seq1.data_ptr(), d_seq2.data_ptr(), m.ctypes.data,
+                                                            _gap(gap_penalty), d_scores.data_ptr(), n, stream)
+        else:
+            rc = self._lib.swb200_score_batch_len_device(self._h, device_index, int(d_seq1.shape[1]), d_seq1.data_ptr(), d_seq2.data_ptr(),
+                                                         m.ctypes.data, _gap(gap_penalty), d_scores.data_ptr(), n, stream)
+        self._check(rc)
         return d_scores
 
     def count_bad_codes_device(self, d_codes, device_index: int = 0) -> int:

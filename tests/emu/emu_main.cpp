@@ -11,31 +11,51 @@
 
 using namespace swb;
 
+template <int L>
 struct HostFifo {
-    uint32_t w[SW_L];
-    uint32_t pop(int c) const { return w[c & (SW_L - 1)]; }
-    void push(int c, uint32_t v) { w[c & (SW_L - 1)] = v; }
+    uint32_t w[L];
+    uint32_t pop(int c) const { return w[c & (L - 1)]; }
+    void push(int c, uint32_t v) { w[c & (L - 1)] = v; }
 };
 struct HostTable {
     const uint32_t* t;
     uint32_t operator()(uint32_t byte_off) const { return t[byte_off >> 2]; }
 };
 
-extern "C" int swemu_score_batch(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap,
-                                 int32_t* scores, uint64_t n, int force_general)
+template <int L>
+static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap, int32_t* scores, uint64_t n, int force_general)
 {
-    if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return -1;
-    const SwParams prm = sw_make_params(sm, gap, force_general);
+    if (!sw_len_supported(sm, L)) return -2;
+    const SwParams prm = sw_make_params(sm, gap, force_general, L);
     HostTable t4{prm.t4};
     for (uint64_t p = 0; p < n; p += 2) {
         const uint64_t q = (p + 1 < n) ? p + 1 : p;
-        HostFifo fifo;
+        HostFifo<L> fifo;
         int32_t lo, hi;
-        const uint32_t dq = (q != p) ? 128u : 0u;
-        if (prm.fast) sw128_two_pairs<true>(seq1 + p * 128, seq2 + p * 128, dq, fifo, t4, prm, lo, hi);
-        else          sw128_two_pairs<false>(seq1 + p * 128, seq2 + p * 128, dq, fifo, t4, prm, lo, hi);
+        const uint32_t dq = (q != p) ? (uint32_t)L : 0u;
+        if (prm.fast) sw_two_pairs<true, L>(seq1 + p * L, seq2 + p * L, dq, fifo, t4, prm, lo, hi);
+        else          sw_two_pairs<false, L>(seq1 + p * L, seq2 + p * L, dq, fifo, t4, prm, lo, hi);
         scores[p] = lo;
         if (q != p) scores[q] = hi;
     }
     return prm.fast;
+}
+
+// returns 1 = fast kernel's algorithm ran, 0 = general, -1 = outside the reference domain, -2 = length unsupported
+extern "C" int swemu_score_batch_len(int len, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap,
+                                     int32_t* scores, uint64_t n, int force_general)
+{
+    if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return -1;
+    switch (len) {
+    case 128: return run_len<128>(seq1, seq2, sm, gap, scores, n, force_general);
+    case 256: return run_len<256>(seq1, seq2, sm, gap, scores, n, force_general);
+    case 512: return run_len<512>(seq1, seq2, sm, gap, scores, n, force_general);
+    default: return -2;
+    }
+}
+
+extern "C" int swemu_score_batch(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap,
+                                 int32_t* scores, uint64_t n, int force_general)
+{
+    return swemu_score_batch_len(128, seq1, seq2, sm, gap, scores, n, force_general);
 }

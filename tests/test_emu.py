@@ -19,16 +19,16 @@ CSRC = os.path.join(ROOT, "smith-waterman-simd_b200", "csrc")
 def emu():
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{CSRC}", "-o", EMU_LIB, EMU_SRC], check=True)
     lib = C.CDLL(EMU_LIB)
-    lib.swemu_score_batch.restype = C.c_int
-    lib.swemu_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    lib.swemu_score_batch_len.restype = C.c_int
+    lib.swemu_score_batch_len.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
 
-    def run(a, b, sm, gap, force_general=0):
+    def run(a, b, sm, gap, force_general=0, allow_refusal=False):
         a = np.ascontiguousarray(a, dtype=np.uint8)
         b = np.ascontiguousarray(b, dtype=np.uint8)
         m = np.asarray(sm, dtype=np.int8)
         out = np.empty(a.shape[0], dtype=np.int32)
-        rc = lib.swemu_score_batch(a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], force_general)
-        assert rc >= 0
+        rc = lib.swemu_score_batch_len(a.shape[1], a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], force_general)
+        assert rc >= 0 or allow_refusal
         return rc, out
     return run
 
@@ -69,3 +69,37 @@ def test_emu_fast_path_domain_boundary(emu, oracle):
         path, got = emu(a, b, sm, g)
         assert path == want_fast, (sm[0], g)
         assert np.array_equal(got, oracle.score_batch(a, b, sm, g)), (sm[0], g)
+
+
+def _related_pairs(rng, n, L):
+    """half iid pairs, half pairs sharing long gapped matches (so scores grow with L)"""
+    a = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    for i in range(n // 2):
+        keep = rng.random(L) > 0.08
+        sub = a[i][keep]
+        ins = rng.integers(0, 4, L, dtype=np.uint8)
+        b[i] = np.concatenate([sub, ins])[:L]
+        mut = rng.random(L) < 0.05
+        b[i][mut] = (b[i][mut] + 1) % 4
+    a[0] = b[0]   # identical pair: score = L * match
+    return a, b
+
+
+@pytest.mark.parametrize("L", [256, 512])
+def test_emu_length_sweep(emu, oracle, L):
+    # BASELINE.json configs[3]: 2x and 4x the built-in shape; oracle = source.cpp:35-60 restated for any length
+    rng = np.random.default_rng(L)
+    a, b = _related_pairs(rng, 41, L)
+
+    def mm(m, x):
+        return [m if i == j else x for i in range(4) for j in range(4)]
+    for sm, g in ((mm(10, -30), 15), (mm(1, -1), 1), (mm(5, -4), 0), (mm(40, -50), 30), (mm(60, -127), 3)):
+        exp = oracle.score_batch(a, b, sm, g, threads=os.cpu_count())
+        for force_general in (0, 1):
+            path, got = emu(a, b, sm, g, force_general)
+            assert np.array_equal(got, exp), (L, sm[0], g, path)
+    assert exp.max() >= L * 60 * 0.5          # long alignments really were exercised
+    # 512 * 127 does not fit int16: refused, not wrong
+    rc, _ = emu(a, b, mm(127, -127), 127, allow_refusal=True)
+    assert rc == (-2 if L == 512 else 0)

@@ -203,3 +203,39 @@ def test_all_visible_gpus_shard_by_index_range(swb, oracle):
         got = c.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
     sample = np.r_[0:2000, n - 2000:n, np.arange(0, n, 499)]
     assert np.array_equal(got[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
+@pytest.mark.parametrize("L", [256, 512])
+def test_length_sweep_parity(ctx, swb, oracle, L):
+    # BASELINE.json configs[3]: 2x / 4x the built-in shape, templated kernels, same C ABI family
+    rng = np.random.default_rng(1000 + L)
+    n = 3001
+    a = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, L), dtype=np.uint8)
+    for i in range(n // 2):                       # related pairs: long gapped alignments
+        keep = rng.random(L) > 0.08
+        b[i] = np.concatenate([a[i][keep], rng.integers(0, 4, L, dtype=np.uint8)])[:L]
+    a[0] = b[0]
+    for sm, g in ((swb.MATRIX_SPEEDTEST, 15), (swb.MATRIX_111, 1), (mm(40, -50), 30), (mm(60, -127), 3)):
+        exp = oracle.score_batch(a, b, sm, g, threads=NCPU)
+        for force_general in (False, True):
+            ctx.set_force_general(force_general)
+            try:
+                got = ctx.score_batch(a, b, sm, g)
+            finally:
+                ctx.set_force_general(False)
+            assert np.array_equal(got, exp), (L, sm[0], g, force_general)
+    assert ctx.score_batch(a[:1], b[:1], swb.MATRIX_SPEEDTEST, 15)[0] == 10 * L
+    info = ctx.kernel_info(swb.MATRIX_SPEEDTEST, 15, seq_len=L)
+    assert info["fast_path"] == 1 and info["threads_per_block"] * L == 128 * 128
+    if L == 512:
+        with pytest.raises(swb.SwbError) as e:    # 512 * 127 overflows packed int16: refused, not wrong
+            ctx.score_batch(a[:4], b[:4], mm(127, -127), 127)
+        assert e.value.code == swb.ERR_DOMAIN
+    # device-resident entry at this length
+    import torch
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    ds = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.score_batch_device(da, db, swb.MATRIX_SPEEDTEST, 15, ds)
+    torch.cuda.synchronize()
+    assert np.array_equal(ds.cpu().numpy(), oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU))

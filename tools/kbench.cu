@@ -23,7 +23,7 @@ static bool g_quick = false;   // `kbench ncu`: one warm-up + one timed launch o
 template <bool FAST, int NT, int MINB>
 void run(const char* name, const SwParams& prm, uint64_t want_fnv, long long want_sum)
 {
-    auto kern = sw128_kernel<FAST, NT, MINB>;
+    auto kern = sw_kernel<FAST, 128, NT, MINB>;
     const size_t smem = sw128_smem_bytes<NT>();
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
