@@ -168,10 +168,39 @@ def cpu_model() -> str:
     return "unknown"
 
 
+def run_cpu_table(args):
+    """the reference's scalar, simd4, simd7 and simd9 on the 1M-pair batch
+    (scalar on a 50 000-pair sample), one thread and all host cores, both harness matrices.
+    `python bench.py --impl reference --cpu-table` -> one JSON line per row."""
+    from oracle import oracle as O
+    import swb200
+    if not O.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libswref.so not built (no /root/reference here and no prebuilt file)"}))
+        return
+    cores = os.cpu_count() or 1
+    a, b = swb200.reference_stream(PAIRS_PER_GPU)
+    names = {0: "scalar SmithWaterman (source.cpp:35-60)", 4: "SmithWaterman_simd4 (462-571)", 7: "SmithWaterman_simd7 (758-850)", 9: "SmithWaterman_simd9 (953-1071)"}
+    for label, matrix, gap in (("+10/-30 gap 15 (SpeedTest, source.cpp:3041-3046)", swb200.MATRIX_SPEEDTEST, 15),
+                               ("+1/-1 gap 1 (speedtest111x32, source.cpp:3202-3207)", swb200.MATRIX_111, 1)):
+        for variant in (0, 4, 7, 9):
+            for threads in (1, cores):
+                m = (50_000 if variant == 0 else 250_000) * (1 if threads == 1 else min(4, cores))
+                m = min(m, PAIRS_PER_GPU)
+                O.ref_score_batch(variant, a[:2000], b[:2000], matrix, gap, threads=threads)
+                t = time.perf_counter()
+                O.ref_score_batch(variant, a[:m], b[:m], matrix, gap, threads=threads)
+                dt = time.perf_counter() - t
+                print(json.dumps({"impl": "reference", "kernel": names[variant], "scoring": label, "threads": threads, "host_cores": cores,
+                                  "cpu_model": cpu_model(), "sample_pairs": m, "ms_per_1M_pairs": dt / m * 1e9, "gcups": m * CELLS_PER_PAIR / dt / 1e9,
+                                  "alignments_per_s": m / dt, "build": "g++ -std=c++17 -O3 -mavx2, unmodified source"}), flush=True)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.cpu_table:
+        return run_cpu_table(args)
     import swb200
     # inputs come from the product's generator (a .so load, no GPU needed); scoring is all reference
     a, b = swb200.reference_stream(PAIRS_PER_GPU)
@@ -455,6 +484,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-table", action="store_true", help="with --impl reference: scalar/simd4/simd7/simd9, 1 thread and all cores")
     ap.add_argument("--workload", choices=["batch1m", "stream", "sweep"], default="batch1m",
                     help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")
     ap.add_argument("--pairs", type=int, default=100_000_000)

@@ -92,6 +92,15 @@ int swb200_score_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2
                        const int8_t* score_matrix, int8_t gap_penalty,
                        int32_t* scores, uint64_t n);
 
+/* Many queries against ONE target: replaces
+ *   int SmithWaterman_8b111x32markN(const std::array<uint8_t,128*32>& seq1, const std::array<uint8_t,128>& seq2,
+ *                                   std::array<int,32>& dest)           (source.cpp:1227-1230, 1299, 1383)
+ * for any n (not only 32) and any matrix/gap of the domain (the reference fixes 1/-1/1 there):
+ * seq1s[n][128] row-major, seq2[128], scores[n] = score(seq1s[p], seq2). */
+int swb200_score_one_vs_many(swb200_ctx* ctx, const uint8_t* seq1s, const uint8_t* seq2,
+                             const int8_t* score_matrix, int8_t gap_penalty,
+                             int32_t* scores, uint64_t n);
+
 /* Same, inputs as the reference's 2-bit packing: 32 bytes per sequence,
  * code(i*4+j) = (byte[i] >> 2j) & 3   (source.cpp:1580-1583, `unpack`).
  * seq1_packed[n][32], seq2_packed[n][32].  Unpacking happens on the device. */

@@ -83,6 +83,10 @@ def ref():
         lib.swref_reference_stream.argtypes = [C.c_uint64, C.c_uint64, _u8p, _u8p]
         lib.swref_unpack.restype = None
         lib.swref_unpack.argtypes = [_u8p, _u8p]
+        lib.swref_111.restype = C.c_int
+        lib.swref_111.argtypes = [_u8p, _u8p]
+        lib.swref_x32.restype = C.c_int
+        lib.swref_x32.argtypes = [C.c_int, _u8p, _u8p, _i32p]
         lib.swref_hardware_threads.restype = C.c_int
         _ref = lib
     return _ref
@@ -121,6 +125,34 @@ def ref_score_batch(variant: int, seq1: np.ndarray, seq2: np.ndarray, score_matr
     if rc != 0:
         raise ValueError(f"unknown reference variant {variant}")
     return out
+
+
+def ref_x32(mark: int, seq1_32: np.ndarray, seq2: np.ndarray) -> np.ndarray:
+    """The reference's SmithWaterman_8b111x32mark{1,2,3}: 32 queries [32][128] vs one target [128], fixed 1/1/1."""
+    a = np.ascontiguousarray(seq1_32, dtype=np.uint8).reshape(32 * 128)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(128)
+    out = np.empty(32, dtype=np.int32)
+    rc = ref().swref_x32(mark, _p(a, _u8p), _p(b, _u8p), _p(out, _i32p))
+    assert rc == out[0]          # the reference returns dest[0] (source.cpp:1233, 1296)
+    return out
+
+
+def ref_111(seq1: np.ndarray, seq2: np.ndarray) -> int:
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(128)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(128)
+    return int(ref().swref_111(_p(a, _u8p), _p(b, _u8p)))
+
+
+def x32_stream(iterations: int, seed: int = 10000):
+    """Inputs of TestSimdSmithWaterman111x32 (source.cpp:3004-3013): per iteration 4096 draws for the 32
+    queries, then 128 draws for the target."""
+    n = iterations * (4096 + 128)
+    flat1 = np.empty((n // 2 // 128 + 1, 128), dtype=np.uint8)
+    flat2 = np.empty_like(flat1)
+    port().swo_reference_stream(seed, flat1.shape[0], _p(flat1, _u8p), _p(flat2, _u8p))
+    draws = np.stack([flat1, flat2], axis=2).reshape(-1)[:n]     # undo the a/b interleaving: draw order
+    draws = draws.reshape(iterations, 4096 + 128)
+    return np.ascontiguousarray(draws[:, :4096].reshape(iterations, 32, 128)), np.ascontiguousarray(draws[:, 4096:])
 
 
 def reference_stream(n: int, seed: int = 10000, use_ref: bool = False):

@@ -113,6 +113,34 @@ void swref_unpack(const uint8_t* src32, uint8_t* dest128)
     std::memcpy(dest128, d.data(), 128);
 }
 
+// SmithWaterman_111 (source.cpp:1073-1103): fixed match/mismatch/gap = 1/1/1
+int swref_111(const uint8_t* seq1, const uint8_t* seq2)
+{
+    Seq a, b;
+    std::memcpy(a.data(), seq1, 128);
+    std::memcpy(b.data(), seq2, 128);
+    return SmithWaterman_111(a, b);
+}
+
+// SmithWaterman_8b111x32mark1/2/3 (source.cpp:1227, 1299, 1383): 32 queries x one target, fixed 1/1/1
+int swref_x32(int mark, const uint8_t* seq1_32x128, const uint8_t* seq2, int32_t* dest32)
+{
+    std::array<uint8_t, 128 * 32> a;
+    std::array<uint8_t, 128> b;
+    std::array<int, 32> d;
+    std::memcpy(a.data(), seq1_32x128, 128 * 32);
+    std::memcpy(b.data(), seq2, 128);
+    int rc;
+    switch (mark) {
+    case 1: rc = SmithWaterman_8b111x32mark1(a, b, d); break;
+    case 2: rc = SmithWaterman_8b111x32mark2(a, b, d); break;
+    case 3: rc = SmithWaterman_8b111x32mark3(a, b, d); break;
+    default: return -1;
+    }
+    for (int i = 0; i < 32; ++i) dest32[i] = d[i];
+    return rc;
+}
+
 int swref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 } // extern "C"

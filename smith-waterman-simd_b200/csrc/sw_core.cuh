@@ -239,13 +239,14 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
     }
 }
 
-// Scores two pairs: (a_lo,b_lo) in the low halves, (a_lo+dq, b_lo+dq) in the high halves
-// (dq = L for the neighbouring pair, 0 when the batch's last pair stands alone).
+// Scores two pairs: (a_lo,b_lo) in the low halves, (a_lo+dqa, b_lo+dqb) in the high halves
+// (dqa = dqb = L for the neighbouring pair; 0 when the batch's last pair stands alone;
+// dqb = 0 also when every pair shares one target, the one-vs-many entry).
 // Both pointers address L byte-coded bases (0..3), 8-byte aligned; L is a power of two >= 32.
 // The FIFO must hold L words for this thread; it is (re)initialised here.
 template <bool FAST, int L, class Fifo, class Table>
-SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
-                            Fifo& fifo, const Table& t4, const SwParams& prm, int32_t& score_lo, int32_t& score_hi)
+SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa, uint32_t dqb,
+                         Fifo& fifo, const Table& t4, const SwParams& prm, int32_t& score_lo, int32_t& score_hi)
 {
     SwState st;
 #pragma unroll
@@ -264,8 +265,8 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
 
     uint32_t an_lo[4], an_hi[4];
     ld8(b_lo, st.bq_lo[0], st.bq_lo[1]);
-    ld8(b_lo + dq, st.bq_hi[0], st.bq_hi[1]);
-    ld16(a_lo, an_lo); ld16(a_lo + dq, an_hi);
+    ld8(b_lo + dqb, st.bq_hi[0], st.bq_hi[1]);
+    ld16(a_lo, an_lo); ld16(a_lo + dqa, an_hi);
 
     for (int strip = 0; strip <= STRIPS; ++strip) {
         if (FAST && strip > 0) {
@@ -276,15 +277,15 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dq,
             st.Z = fsub(st.Z, prm.C, prm); st.Zp = fsub(st.Zp, prm.C, prm);
             st.B = fsub(st.B, prm.C, prm); st.up0 = fsub(st.up0, prm.C, prm);
         }
-        sw_iter16<FAST, true, L>(st, fifo, t4, prm, 0, b_lo, dq, an_lo, an_hi, strip >= STRIPS);
+        sw_iter16<FAST, true, L>(st, fifo, t4, prm, 0, b_lo, dqb, an_lo, an_hi, strip >= STRIPS);
         if (strip == STRIPS) break;
 #pragma unroll 1
         for (int j = 1; j < L / 16; ++j) {
             if (j == L / 16 - 1) {   // one iteration ahead of the wrap that consumes them
                 const int ns = (strip + 1 < STRIPS) ? strip + 1 : STRIPS - 1;
-                ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dq, an_hi);
+                ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dqa, an_hi);
             }
-            sw_iter16<FAST, false, L>(st, fifo, t4, prm, 16 * j, b_lo, dq, an_lo, an_hi, false);
+            sw_iter16<FAST, false, L>(st, fifo, t4, prm, 16 * j, b_lo, dqb, an_lo, an_hi, false);
         }
     }
     if (FAST) {

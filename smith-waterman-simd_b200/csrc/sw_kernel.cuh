@@ -42,8 +42,10 @@ constexpr size_t sw128_smem_bytes() { return sw_smem_bytes<SW_L, NT>(); }
 template <bool FAST, int L, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
-             int32_t* __restrict__ scores, unsigned long long n, const SwParams prm)
+             int32_t* __restrict__ scores, unsigned long long n, const SwParams prm, const unsigned seq2_stride)
 {
+    // seq2_stride = L: pair p's target is seq2[p][L];  0: one target shared by all pairs
+    // (the batched shape of SmithWaterman_8b111x32mark1, source.cpp:1227-1234).
     extern __shared__ uint32_t smem[];
     uint32_t* t4s = smem + L * NT;
     if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
@@ -56,7 +58,8 @@ sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
     SmemFifo<NT> fifo{smem + threadIdx.x};
     SmemTable t4{t4s};
     int32_t lo, hi;
-    sw_two_pairs<FAST, L>(seq1 + p * L, seq2 + p * L, (q != p) ? (uint32_t)L : 0u, fifo, t4, prm, lo, hi);
+    sw_two_pairs<FAST, L>(seq1 + p * L, seq2 + p * seq2_stride, (q != p) ? (uint32_t)L : 0u, (q != p) ? seq2_stride : 0u,
+                          fifo, t4, prm, lo, hi);
     if (q != p) {
         *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
     } else {

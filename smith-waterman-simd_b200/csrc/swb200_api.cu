@@ -110,22 +110,24 @@ template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; };
 template <> struct LenCfg<512> { static constexpr int NT = 32,  MINB = 3; };
 
 template <bool FAST, int L>
-cudaError_t launch_sw(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st)
+cudaError_t launch_sw(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st, bool shared_target)
 {
     if (n == 0) return cudaSuccess;
     constexpr int NT = LenCfg<L>::NT;
     const uint64_t threads = (n + 1) / 2;
     const unsigned grid = (unsigned)((threads + NT - 1) / NT);
-    sw_kernel<FAST, L, NT, LenCfg<L>::MINB><<<grid, NT, sw_smem_bytes<L, NT>(), st>>>(d1, d2, dsc, n, prm);
+    sw_kernel<FAST, L, NT, LenCfg<L>::MINB><<<grid, NT, sw_smem_bytes<L, NT>(), st>>>(d1, d2, dsc, n, prm, shared_target ? 0u : (unsigned)L);
     return cudaGetLastError();
 }
 
-cudaError_t launch_for(const SwParams& prm, int L, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st)
+cudaError_t launch_for(const SwParams& prm, int L, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st,
+                       bool shared_target = false)
 {
+    const bool sh = shared_target;
     switch (L) {
-    case 128: return prm.fast ? launch_sw<true, 128>(d1, d2, dsc, n, prm, st) : launch_sw<false, 128>(d1, d2, dsc, n, prm, st);
-    case 256: return prm.fast ? launch_sw<true, 256>(d1, d2, dsc, n, prm, st) : launch_sw<false, 256>(d1, d2, dsc, n, prm, st);
-    case 512: return prm.fast ? launch_sw<true, 512>(d1, d2, dsc, n, prm, st) : launch_sw<false, 512>(d1, d2, dsc, n, prm, st);
+    case 128: return prm.fast ? launch_sw<true, 128>(d1, d2, dsc, n, prm, st, sh) : launch_sw<false, 128>(d1, d2, dsc, n, prm, st, sh);
+    case 256: return prm.fast ? launch_sw<true, 256>(d1, d2, dsc, n, prm, st, sh) : launch_sw<false, 256>(d1, d2, dsc, n, prm, st, sh);
+    case 512: return prm.fast ? launch_sw<true, 512>(d1, d2, dsc, n, prm, st, sh) : launch_sw<false, 512>(d1, d2, dsc, n, prm, st, sh);
     default:  return cudaErrorInvalidValue;
     }
 }
@@ -197,7 +199,7 @@ int ensure_staging(swb200_ctx* ctx, Device* d, bool packed)
 // One GPU's share [lo, hi) of a host batch: chunks of kChunkPairs cycle through kSlots
 // streams, so chunk c+1's H2D and chunk c-1's D2H run under chunk c's kernel.
 int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed, int L,
-              const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi)
+              const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi, bool shared_target = false)
 {
     if (hi <= lo) return SWB200_OK;
     std::lock_guard<std::mutex> lock(d->mu);
@@ -214,13 +216,14 @@ int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* se
         uint8_t* in1 = packed ? s.d_pk1 : s.d_seq1;
         uint8_t* in2 = packed ? s.d_pk2 : s.d_seq2;
         SWB_CUDA(ctx, cudaMemcpyAsync(in1, seq1 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
-        SWB_CUDA(ctx, cudaMemcpyAsync(in2, seq2 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
+        if (shared_target) SWB_CUDA(ctx, cudaMemcpyAsync(in2, seq2, in_stride, cudaMemcpyHostToDevice, s.stream));   // one target for all pairs
+        else               SWB_CUDA(ctx, cudaMemcpyAsync(in2, seq2 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
         if (packed) {
             SWB_CUDA(ctx, launch_unpack(s.d_pk1, s.d_seq1, m, s.stream));
             SWB_CUDA(ctx, launch_unpack(s.d_pk2, s.d_seq2, m, s.stream));
             ctx->launches += 2;
         }
-        SWB_CUDA(ctx, launch_for(prm, L, s.d_seq1, s.d_seq2, s.d_scores, m, s.stream));
+        SWB_CUDA(ctx, launch_for(prm, L, s.d_seq1, s.d_seq2, s.d_scores, m, s.stream, shared_target));
         ctx->launches += 1;
         SWB_CUDA(ctx, cudaMemcpyAsync(scores + c0, s.d_scores, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         SWB_CUDA(ctx, cudaEventRecord(s.done, s.stream));
@@ -250,21 +253,21 @@ int check_len(swb200_ctx* ctx, const int8_t* sm, int L)
 }
 
 int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool packed,
-               const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n, int L = SWB200_SEQ_LEN)
+               const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n, int L = SWB200_SEQ_LEN, bool shared_target = false)
 {
     int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
     if (rc == SWB200_OK) rc = check_len(ctx, sm, L);
     if (rc != SWB200_OK || n == 0) return rc;
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
-    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, L, prm, scores, 0, n);
+    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, L, prm, scores, 0, n, shared_target);
     // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
     // every GPU DMA-writes its own slice of `scores`: that is the whole gather.
     std::vector<std::thread> pool;
     std::vector<int> rcs(G, SWB200_OK);
     for (size_t k = 0; k < G; ++k) {
         const uint64_t lo = n * k / G, hi = n * (k + 1) / G;
-        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, L, prm, scores, lo, hi); });
+        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, L, prm, scores, lo, hi, shared_target); });
     }
     for (auto& t : pool) t.join();
     for (int r : rcs) if (r != SWB200_OK) return r;
@@ -380,6 +383,12 @@ int swb200_score_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2
 int swb200_score_batch_packed(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* scores, uint64_t n)
 {
     return score_host(ctx, seq1, seq2, true, sm, gap, scores, n);
+}
+
+int swb200_score_one_vs_many(swb200_ctx* ctx, const uint8_t* seq1s, const uint8_t* seq2, const int8_t* sm, int8_t gap,
+                             int32_t* scores, uint64_t n)
+{
+    return score_host(ctx, seq1s, seq2, false, sm, gap, scores, n, SWB200_SEQ_LEN, true);
 }
 
 int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* score)

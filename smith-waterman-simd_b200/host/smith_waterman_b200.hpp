@@ -87,3 +87,20 @@ inline void SmithWaterman_b200_batch(
     c.check(swb200_score_batch(c.get(), seq1s.empty() ? nullptr : seq1s[0].data(), seq2s.empty() ? nullptr : seq2s[0].data(),
                                score_matrix.data(), gap_penalty, reinterpret_cast<int32_t*>(dest.data()), seq1s.size()));
 }
+
+// Drop-in for SmithWaterman_8b111x32mark1/2/3 (source.cpp:1227-1230, 1299, 1383): 32 row-major
+// 128-mers against one target, results in dest, return value dest[0] (as the reference does,
+// "for no deep reason", source.cpp:1233).  The reference fixes match/mismatch/gap = 1/1/1
+// there (source.cpp:1238); this form takes them as defaulted arguments.
+inline int SmithWaterman_b200_x32(
+    const std::array<uint8_t, 128 * 32>& seq1,
+    const std::array<uint8_t, 128>& seq2,
+    std::array<int, 32>& dest,
+    const std::array<int8_t, 16>& score_matrix = {1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1},
+    const int8_t gap_penalty = 1)
+{
+    swb200::Context& c = swb200::default_context();
+    c.check(swb200_score_one_vs_many(c.get(), seq1.data(), seq2.data(), score_matrix.data(), gap_penalty,
+                                     reinterpret_cast<int32_t*>(dest.data()), 32));
+    return dest[0];
+}

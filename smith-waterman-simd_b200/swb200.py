@@ -34,7 +34,7 @@ ABI_SYMBOLS = (
     "swb200_score_batch_device", "swb200_score_batch_packed_device", "swb200_validate_codes_device",
     "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
-    "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len",
+    "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -103,6 +103,8 @@ def load_library():
     lib.swb200_score_batch_len_device.argtypes = [vp, i32, i32, vp, vp, vp, C.c_int8, vp, u64, vp]
     lib.swb200_kernel_info_len.restype = i32
     lib.swb200_kernel_info_len.argtypes = [vp, i32, i32, vp, C.c_int8, C.POINTER(KernelInfo)]
+    lib.swb200_score_one_vs_many.restype = i32
+    lib.swb200_score_one_vs_many.argtypes = [vp, vp, vp, vp, C.c_int8, vp, u64]
     lib.swb200_validate_codes_device.restype = i32
     lib.swb200_validate_codes_device.argtypes = [vp, i32, vp, u64, C.POINTER(u64), vp]
     lib.swb200_kernel_info_for.restype = i32
@@ -250,6 +252,20 @@ class Context:
         else:
             rc = self._lib.swb200_score_batch_len(self._h, width, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n)
         self._check(rc)
+        return out[:n]
+
+    # -- many queries vs one target (SmithWaterman_8b111x32mark1, source.cpp:1227-1234)
+    def score_one_vs_many(self, seq1s: np.ndarray, seq2: np.ndarray, score_matrix=MATRIX_111, gap_penalty=GAP_111,
+                          out: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(seq1s, dtype=np.uint8).reshape(-1, SEQ_LEN)
+        b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(-1)
+        if b.size != SEQ_LEN:
+            raise ValueError("seq2 must hold exactly 128 codes")
+        n = a.shape[0]
+        m = _matrix(score_matrix)
+        if out is None:
+            out = np.empty(n, dtype=np.int32)
+        self._check(self._lib.swb200_score_one_vs_many(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n))
         return out[:n]
 
     def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray, packed: bool = False) -> int:

@@ -23,7 +23,8 @@ struct HostTable {
 };
 
 template <int L>
-static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap, int32_t* scores, uint64_t n, int force_general)
+static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap, int32_t* scores, uint64_t n, int force_general,
+                   uint32_t stride2 = (uint32_t)L)
 {
     if (!sw_len_supported(sm, L)) return -2;
     const SwParams prm = sw_make_params(sm, gap, force_general, L);
@@ -33,8 +34,9 @@ static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, i
         HostFifo<L> fifo;
         int32_t lo, hi;
         const uint32_t dq = (q != p) ? (uint32_t)L : 0u;
-        if (prm.fast) sw_two_pairs<true, L>(seq1 + p * L, seq2 + p * L, dq, fifo, t4, prm, lo, hi);
-        else          sw_two_pairs<false, L>(seq1 + p * L, seq2 + p * L, dq, fifo, t4, prm, lo, hi);
+        const uint32_t dqb = (q != p) ? stride2 : 0u;
+        if (prm.fast) sw_two_pairs<true, L>(seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi);
+        else          sw_two_pairs<false, L>(seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi);
         scores[p] = lo;
         if (q != p) scores[q] = hi;
     }
@@ -58,4 +60,12 @@ extern "C" int swemu_score_batch(const uint8_t* seq1, const uint8_t* seq2, const
                                  int32_t* scores, uint64_t n, int force_general)
 {
     return swemu_score_batch_len(128, seq1, seq2, sm, gap, scores, n, force_general);
+}
+
+// many queries against one target (stride 0 on the target side), as the kernel does for swb200_score_one_vs_many
+extern "C" int swemu_one_vs_many(const uint8_t* seq1s, const uint8_t* seq2, const int8_t* sm, int gap,
+                                 int32_t* scores, uint64_t n, int force_general)
+{
+    if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return -1;
+    return run_len<128>(seq1s, seq2, sm, gap, scores, n, force_general, 0u);
 }

@@ -26,6 +26,14 @@ int main()
             const int one = SmithWaterman_b200(as[it], bs[it], score_matrix, gap_penalty);
             bad += (one != expect[it]) + (dest[it] != expect[it]);
         }
+        // the x32 shape (source.cpp:1227-1234): 32 queries vs one target, fixed +1/-1/1
+        std::array<uint8_t, 128 * 32> q32;
+        for (int p = 0; p < 32; ++p) for (int i = 0; i < 128; ++i) q32[p * 128 + i] = as[p % 16][i];
+        std::array<int, 32> dest32;
+        const std::array<int8_t, 16> m111 = {1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1};
+        const int first = SmithWaterman_b200_x32(q32, bs[0], dest32);
+        for (int p = 0; p < 32; ++p) bad += (dest32[p] != SmithWaterman_b200(as[p % 16], bs[0], m111, 1));
+        bad += (first != dest32[0]);
         std::printf("host mirror: %s\n", bad ? "MISMATCH" : "16/16 scores equal the reference's known answers");
         return bad ? 1 : 0;
     } catch (const std::exception& e) {

@@ -111,6 +111,17 @@ def main():
     np.savez_compressed(os.path.join(HERE, "structured.npz"), seq1=sa, seq2=sb, **exp)
     meta["structured"] = {"n": int(sa.shape[0]), "param_sets": [{"name": n_, "matrix": m_, "gap": g_} for n_, m_, g_ in PARAM_SETS]}
 
+    # 3. one-vs-many: the reference's batched functions on their own test inputs
+    #    (TestSimdSmithWaterman111x32, source.cpp:3003-3030; fixed +1/-1/1 scoring)
+    qs, ts = O.x32_stream(40)
+    x32 = np.stack([O.ref_x32(1, qs[i], ts[i]) for i in range(40)])
+    for i in range(40):
+        for mark in (2, 3):
+            assert np.array_equal(O.ref_x32(mark, qs[i], ts[i]), x32[i])
+        assert O.ref_111(qs[i][0], ts[i]) == x32[i][0]
+    np.savez_compressed(os.path.join(HERE, "x32_first40.npz"), queries=qs, targets=ts, scores=x32.astype(np.int16))
+    meta["x32"] = {"iterations": 40, "source": "SmithWaterman_8b111x32mark1 == mark2 == mark3 (source.cpp:1227,1299,1383)", "sum": int(x32.sum())}
+
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print(json.dumps(meta["reference_stream"]["sets"], indent=1))

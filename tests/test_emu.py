@@ -103,3 +103,20 @@ def test_emu_length_sweep(emu, oracle, L):
     # 512 * 127 does not fit int16: refused, not wrong
     rc, _ = emu(a, b, mm(127, -127), 127, allow_refusal=True)
     assert rc == (-2 if L == 512 else 0)
+
+
+def test_emu_one_vs_many_matches_x32_golden():
+    # the kernel's algorithm with a shared target (stride 0) vs the fixture made by the reference's
+    # SmithWaterman_8b111x32mark1 (tests/golden/x32_first40.npz, written by tests/test_oracle.py)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "x32_first40.npz"))
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{CSRC}", "-o", EMU_LIB, EMU_SRC], check=True)
+    lib = C.CDLL(EMU_LIB)
+    lib.swemu_one_vs_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    m = np.asarray([1 if i == j else -1 for i in range(4) for j in range(4)], dtype=np.int8)
+    for it in range(40):
+        q = np.ascontiguousarray(z["queries"][it]); t = np.ascontiguousarray(z["targets"][it])
+        for n in (32, 31):
+            out = np.empty(n, np.int32)
+            for fg in (0, 1):
+                assert lib.swemu_one_vs_many(q.ctypes.data, t.ctypes.data, m.ctypes.data, 1, out.ctypes.data, n, fg) >= 0
+                assert np.array_equal(out, z["scores"][it][:n].astype(np.int32)), (it, n, fg)

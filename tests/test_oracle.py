@@ -91,3 +91,20 @@ def test_rectangular_and_long(oracle):
     # the templated-length restatement used by the length sweep (config 4): L=256 identical pair
     a = np.tile(np.arange(4, dtype=np.uint8), 64)[None, :]
     assert oracle.score_batch(a, a, oracle.MATRIX_SPEEDTEST, 15)[0] == 2560
+
+
+def test_one_vs_many_row_is_pinned_by_the_reference_x32_functions(oracle):
+    """the reference's batched functions SmithWaterman_8b111x32mark1/2/3
+    (source.cpp:1227, 1299, 1383) and SmithWaterman_111 (source.cpp:1073) equal the oracle with a
+    +1/-1 matrix and gap 1, on the inputs of TestSimdSmithWaterman111x32 (source.cpp:3004-3013)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    qs, ts = oracle.x32_stream(40)
+    for it in range(40):
+        exp = oracle.score_batch(qs[it], np.repeat(ts[it][None, :], 32, axis=0), oracle.MATRIX_111, oracle.GAP_111)
+        for mark in (1, 2, 3):
+            assert np.array_equal(oracle.ref_x32(mark, qs[it], ts[it]), exp), (it, mark)
+        assert oracle.ref_111(qs[it][5], ts[it]) == exp[5]
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "x32_first40.npz"))   # committed fixture = the same run
+    assert np.array_equal(z["queries"], qs) and np.array_equal(z["targets"], ts)
+    assert np.array_equal(z["scores"][7].astype(np.int32), oracle.ref_x32(3, qs[7], ts[7]))

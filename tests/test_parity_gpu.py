@@ -239,3 +239,22 @@ def test_length_sweep_parity(ctx, swb, oracle, L):
     ctx.score_batch_device(da, db, swb.MATRIX_SPEEDTEST, 15, ds)
     torch.cuda.synchronize()
     assert np.array_equal(ds.cpu().numpy(), oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
+def test_one_vs_many_equals_reference_x32(ctx, swb, oracle):
+    # many queries vs one target, the shape of SmithWaterman_8b111x32mark1
+    # (source.cpp:1227-1234), on the inputs of TestSimdSmithWaterman111x32 (source.cpp:3004-3013)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "x32_first40.npz"))
+    for it in range(40):
+        got = ctx.score_one_vs_many(z["queries"][it], z["targets"][it])          # defaults: +1/-1, gap 1
+        assert np.array_equal(got, z["scores"][it].astype(np.int32)), it
+        if oracle.have_ref():
+            for mark in (1, 2, 3):
+                assert np.array_equal(got, oracle.ref_x32(mark, z["queries"][it], z["targets"][it]))
+    # any n, any matrix of the domain; equals the pairwise entry with the target repeated
+    n = 200_001
+    q, _ = swb.counter_pairs(7, n)
+    t = z["targets"][3]
+    got = ctx.score_one_vs_many(q, t, swb.MATRIX_SPEEDTEST, 15)
+    assert np.array_equal(got, ctx.score_batch(q, np.repeat(t[None, :], n, axis=0), swb.MATRIX_SPEEDTEST, 15))
+    assert np.array_equal(got[:3000], oracle.score_batch(q[:3000], np.repeat(t[None, :], 3000, axis=0), swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
