@@ -134,15 +134,25 @@ def cpu_reference_run(a, b, matrix, gap, steps, warmup, budget_s=150.0):
     from oracle import oracle as O   # allowed here: cpu_baseline / --impl reference legs only
     cores = os.cpu_count() or 1
     n = a.shape[0]
+    probe = min(n, 20_000)
     if O.have_ref():
-        kind, variant = "reference", "SmithWaterman_simd4 (source.cpp:462-571), unmodified, g++ -O3 -mavx2"
-        run = lambda m: O.ref_score_batch(4, a[:m], b[:m], matrix, gap, threads=cores)
+        # the reference's AVX2 path: simd4 is the README's reference point, simd9 its fastest variant on
+        # most CPUs (README.md:12); time both on a probe and run the faster one, so the baseline is the
+        # reference at its best on THIS box
+        best = None
+        for v, nm in ((4, "SmithWaterman_simd4 (source.cpp:462-571)"), (9, "SmithWaterman_simd9 (source.cpp:953-1071)")):
+            O.ref_score_batch(v, a[:2000], b[:2000], matrix, gap, threads=cores)
+            t = time.perf_counter(); O.ref_score_batch(v, a[:probe], b[:probe], matrix, gap, threads=cores); dtv = time.perf_counter() - t
+            if best is None or dtv < best[0]:
+                best = (dtv, v, nm)
+        dt, vbest, nm = best
+        kind, variant = "reference", nm + ", unmodified, g++ -O3 -mavx2 (faster of simd4/simd9 on this host)"
+        run = lambda m: O.ref_score_batch(vbest, a[:m], b[:m], matrix, gap, threads=cores)
     else:
         O.build()
         kind, variant = "port", "oracle/sw_oracle.c scalar restatement of source.cpp:35-60, gcc -O2"
         run = lambda m: O.score_batch(a[:m], b[:m], matrix, gap, threads=cores)
-    probe = min(n, 20_000)
-    t = time.perf_counter(); run(probe); dt = time.perf_counter() - t
+        t = time.perf_counter(); run(probe); dt = time.perf_counter() - t
     per_pair = dt / probe
     # a step is the whole batch unless the whole run would blow the budget
     sample = n
