@@ -250,6 +250,8 @@ def run_b200_arm(args):
     ddist = dist if world > 1 else None
 
     matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
+    # multi-rank: run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off
+    numa = swb200.bind_to_gpu_numa_node(local_rank) if world > 1 else None
     ctx = swb200.Context(devices=[local_rank])
     info = ctx.kernel_info(matrix, gap)
     n = PAIRS_PER_GPU
@@ -361,7 +363,7 @@ def run_b200_arm(args):
             "alignments_per_s": total_pairs / (ms_step * 1e-3),
             "config": {"workload": "configs[1]: 1M seeded random 128-mer pairs per GPU (rank 0 = reference stream source.cpp:2944-2953; rank r = counter stream pairs [r*1M,(r+1)*1M)), matrix +10/-30, gap 15",
                        "pairs_per_gpu": n, "cells_per_pair": CELLS_PER_PAIR, "sharding": "contiguous index ranges, no collective",
-                       "l2": "inputs 256 MB per launch > 126 MB L2, no flush needed",
+                       "l2": "inputs 256 MB per launch > 126 MB L2, no flush needed", "numa": numa,
                        "kernel": info},
             "clocks": clocks,
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "ms_per_step": e2e_ms, "alignments_per_s": total_pairs / (e2e_ms * 1e-3),
@@ -404,6 +406,7 @@ def run_stream_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ddist = dist if world > 1 else None
     matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
+    numa = swb200.bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before any pinned allocation
     ctx = swb200.Context(devices=[local_rank])
     lo, hi = shard_range(args.pairs, rank, world)
     threads = max(1, (os.cpu_count() or 8) // world - 1)
@@ -415,12 +418,15 @@ def run_stream_arm(args):
     launches0 = ctx.launch_count
     rep = runner.run(lo, hi - lo, matrix, gap)
     torch.cuda.synchronize()
+    # every collective is executed by EVERY rank, before any rank-0-only code
     wall = max_over_ranks(rep.wall_s, ddist)
     total = sum_over_ranks(rep.pairs, ddist)
     score_sum = sum_over_ranks(rep.score_sum, ddist)
     gen_s = max_over_ranks(rep.produce_s, ddist)
     wait_s = max_over_ranks(rep.wait_s, ddist)
     launches = sum_over_ranks(ctx.launch_count - launches0, ddist)
+    h2d = sum_over_ranks(rep.bytes_h2d, ddist)
+    d2h = sum_over_ranks(rep.bytes_d2h, ddist)
     if rank == 0:
         line = {
             "metric": "alignments_per_s_streaming_e2e", "value": total / wall, "unit": "alignments/s", "gcups": total * CELLS_PER_PAIR / wall / 1e9,
@@ -428,9 +434,8 @@ def run_stream_arm(args):
             "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
             "config": {"workload": f"streaming: {args.pairs} counter-stream pairs sharded by contiguous index range over {world} rank(s); host threads -> pinned ring buffers -> swb200_submit{'_packed' if args.packed else ''}",
                        "pairs": args.pairs, "batch_pairs": args.batch_pairs, "wire_format": "2-bit packed (source.cpp:1580-1583), 64 B/pair" if args.packed else "byte codes, 256 B/pair",
-                       "gen_threads_per_rank": threads, "host_cores": os.cpu_count()},
-            "e2e": {"value": total / wall, "unit": "alignments/s", "h2d_bytes_per_step": int(sum_over_ranks(rep.bytes_h2d, ddist)) if world > 1 else rep.bytes_h2d,
-                    "d2h_bytes_per_step": int(sum_over_ranks(rep.bytes_d2h, ddist)) if world > 1 else rep.bytes_d2h},
+                       "gen_threads_per_rank": threads, "host_cores": os.cpu_count(), "numa": numa},
+            "e2e": {"value": total / wall, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "breakdown": {"wall_s": wall, "host_generation_s_max_rank": gen_s, "blocked_on_gpu_pipeline_s_max_rank": wait_s,
                           "bottleneck": "host generation" if gen_s > 0.8 * wall else "PCIe/kernel pipeline"},
             "gpu_launches": int(launches), "score_sum": int(score_sum), "mean_score": score_sum / total,

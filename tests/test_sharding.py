@@ -67,3 +67,31 @@ def test_two_rank_gloo_shards_equal_single_rank(tmp_path):
     got = np.array(np.memmap(out_path, dtype=np.int32, mode="r", shape=(n,)))
     a, b = swb200.counter_pairs(0, n)
     assert np.array_equal(got, O.score_batch(a, b, O.MATRIX_SPEEDTEST, 15))
+
+
+def test_bench_has_no_collective_inside_rank0_only_code():
+    """A collective that only rank 0 executes hangs every multi-GPU run.  Static check of bench.py."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    collectives = {"max_over_ranks", "sum_over_ranks", "barrier", "all_reduce", "all_gather", "broadcast"}
+    bad = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and "rank == 0" in ast.unparse(node.test):
+            for sub in ast.walk(ast.Module(body=node.body, type_ignores=[])):
+                if isinstance(sub, ast.Call):
+                    name = sub.func.attr if isinstance(sub.func, ast.Attribute) else getattr(sub.func, "id", "")
+                    if name in collectives:
+                        bad.append((node.lineno, name))
+    assert not bad, bad
+
+
+def test_cpulist_parser_and_numa_binding_is_best_effort(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "smith-waterman-simd_b200"))
+    import swb200
+    assert swb200._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert swb200._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    r = swb200.bind_to_gpu_numa_node(0, sysfs=str(tmp_path))    # no GPU / no sysfs entry: reports, never raises
+    assert r is not None and r["bound"] is False
+    assert os.sched_getaffinity(0) == before
