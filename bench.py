@@ -330,7 +330,7 @@ def run_b200_arm(args):
     achieved_tinstr = n * CELLS_PER_PAIR * ALGO_INSTR_PER_CELL / (avg_launch_ms * 1e-3) / 1e12
     hbm_achieved = n * ALGO_BYTES_PER_PAIR / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "int_alu", "kernel": "swb::sw_kernel<FAST=%d, L=128, NT=128, MINB=3>" % info["fast_path"],
+        "bound": "int_alu", "kernel": "swb::sw_kernel<FAST=%d, L=128, NT=%d, MINB=%d>" % (info["fast_path"], info["threads_per_block"], info["blocks_per_sm"]),
         "achieved": achieved_tinstr, "peak": alu_peak_tinstr, "unit": "Tinstr/s (thread-level packed int16x2 ALU instructions)",
         "frac": achieved_tinstr / alu_peak_tinstr,
         "algorithmic_instr_per_cell": ALGO_INSTR_PER_CELL, "cells_per_launch": n * CELLS_PER_PAIR,

@@ -160,7 +160,19 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 //         columns col0..col0+15; columns col0+8.. are loaded here at u = 0, the next
 //         iteration's first eight at u = 8 (always 8 steps ahead of their first use).
 //   aw_lo/aw_hi: (WRAP only) the 16 query bases of the strip being entered.
-template <bool FAST, bool WRAP, int L, class Fifo, class Table>
+// V = variant bits (tuning knobs, all bit-exact):
+//   bit 0 (SW_V_BEST_FMA): running best -- the +g frame shift is a plain add on the FMA pipe, then
+//          8 VIMNMX3 (instead of VIADDMNMX + 7 VIMNMX3 + VIMNMX).  Measured -2.2 % time.
+// Measured and REJECTED (profiles/r01/kbench_v3_variants.jsonl, kbench_v4_lds_hybrid.jsonl,
+// kbench_v5_dual_best.jsonl):
+//   * two independent best accumulators (half the dependency chain, same count): 0.7 % slower;
+//   * IMAD/IMAD.HI byte extraction for the column selector instead of one PRMT: 4.6 % slower;
+//   * substitution words of 4-10 rows of the strip from a lane-replicated shared-memory table
+//     (IMAD address add + LDS on the FMA/LSU pipes instead of PRMT on the ALU pipe): bit-exact,
+//     0.8-3.5 % slower than the all-PRMT kernel in the same block shape.
+constexpr int SW_V_BEST_FMA = 1;
+
+template <bool FAST, bool WRAP, int L, int V, class Fifo, class Table>
 SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
                       const uint8_t* b_lo, uint32_t dq,
                       const uint32_t (&aw_lo)[4], const uint32_t (&aw_hi)[4], bool next_is_dummy)
@@ -183,8 +195,9 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         //     (b_lo, 8|b_lo, 4|b_hi, 12|b_hi): low half <- byte b_lo of prA sign-extended,
         //     high half <- byte b_hi of prB sign-extended.
         {
-            const uint32_t pick = 0x4440u | (uint32_t)(u & 3) | ((uint32_t)(u & 3) << 4);
-            const uint32_t w = prmt(bw_lo[u >> 2], bw_hi[u >> 2], pick);   // bytes 2,3 are don't-care: PRMT reads selector bits 0..15 only
+            // pick bytes (b_lo, b_hi, 0, 0): nibbles 8|j replicate the sign of a code byte, i.e. 0
+            const uint32_t pick = 0x8800u | (uint32_t)(u & 3) | ((uint32_t)((u & 3) + 4) << 4);
+            const uint32_t w = prmt(bw_lo[u >> 2], bw_hi[u >> 2], pick);   // = b_lo + 256*b_hi
             st.sel[u] = w * 17u + 0xC480u;                                  // IMAD: the FMA pipe, not the ALU pipe
         }
         if (WRAP) {   // row u enters the next strip: new query profile
@@ -227,11 +240,17 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         fifo.push(WRAP ? ((u - (SW_R - 1)) & (L - 1)) : (col0 + u - (SW_R - 1)),
                   FAST ? fsub(hn[SW_R - 1], st.Z, prm) : hn[SW_R - 1]);   // plain subtract: hn >= Z in both halves
         // --- running best
-        if (FAST) st.B = vaddmax2(st.B, prm.G, hn[0]);
-        else      st.B = vmax2(st.B, hn[0]);
+        if (FAST && (V & SW_V_BEST_FMA)) {
+            st.B = fadd(st.B, prm.G, prm);      // best >= 0 in both halves: no carry across
 #pragma unroll
-        for (int k = 1; k + 1 < SW_R; k += 2) st.B = vmax3(st.B, hn[k], hn[k + 1]);
-        st.B = vmax2(st.B, hn[SW_R - 1]);
+            for (int k = 0; k + 1 < SW_R; k += 2) st.B = vmax3(st.B, hn[k], hn[k + 1]);
+        } else {
+            if (FAST) st.B = vaddmax2(st.B, prm.G, hn[0]);
+            else      st.B = vmax2(st.B, hn[0]);
+#pragma unroll
+            for (int k = 1; k + 1 < SW_R; k += 2) st.B = vmax3(st.B, hn[k], hn[k + 1]);
+            st.B = vmax2(st.B, hn[SW_R - 1]);
+        }
         // --- advance
 #pragma unroll
         for (int k = 0; k < SW_R; ++k) { st.h2[k] = st.h1[k]; st.h1[k] = hn[k]; }
@@ -244,7 +263,7 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
 // dqb = 0 also when every pair shares one target, the one-vs-many entry).
 // Both pointers address L byte-coded bases (0..3), 8-byte aligned; L is a power of two >= 32.
 // The FIFO must hold L words for this thread; it is (re)initialised here.
-template <bool FAST, int L, class Fifo, class Table>
+template <bool FAST, int L, int V, class Fifo, class Table>
 SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa, uint32_t dqb,
                          Fifo& fifo, const Table& t4, const SwParams& prm, int32_t& score_lo, int32_t& score_hi)
 {
@@ -277,7 +296,7 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
             st.Z = fsub(st.Z, prm.C, prm); st.Zp = fsub(st.Zp, prm.C, prm);
             st.B = fsub(st.B, prm.C, prm); st.up0 = fsub(st.up0, prm.C, prm);
         }
-        sw_iter16<FAST, true, L>(st, fifo, t4, prm, 0, b_lo, dqb, an_lo, an_hi, strip >= STRIPS);
+        sw_iter16<FAST, true, L, V>(st, fifo, t4, prm, 0, b_lo, dqb, an_lo, an_hi, strip >= STRIPS);
         if (strip == STRIPS) break;
 #pragma unroll 1
         for (int j = 1; j < L / 16; ++j) {
@@ -285,7 +304,7 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
                 const int ns = (strip + 1 < STRIPS) ? strip + 1 : STRIPS - 1;
                 ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dqa, an_hi);
             }
-            sw_iter16<FAST, false, L>(st, fifo, t4, prm, 16 * j, b_lo, dqb, an_lo, an_hi, false);
+            sw_iter16<FAST, false, L, V>(st, fifo, t4, prm, 16 * j, b_lo, dqb, an_lo, an_hi, false);
         }
     }
     if (FAST) {

@@ -16,6 +16,8 @@
 
 namespace swb {
 
+constexpr int SW_DEFAULT_VARIANT = SW_V_BEST_FMA;   // the variant bits (sw_core.cuh) the shipped kernels use
+
 template <int NT>
 struct SmemFifo {
     uint32_t* f;   // &fifo[0*NT + threadIdx.x]
@@ -39,7 +41,7 @@ constexpr size_t sw128_smem_bytes() { return sw_smem_bytes<SW_L, NT>(); }
 
 // Sequence length L is a template parameter (128 = the reference's shape; 256 and 512 for the
 // length sweep).  The per-thread FIFO is L words of shared memory, so NT shrinks as L grows.
-template <bool FAST, int L, int NT, int MINB>
+template <bool FAST, int L, int NT, int MINB, int V = SW_DEFAULT_VARIANT>
 __global__ void __launch_bounds__(NT, MINB)
 sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
              int32_t* __restrict__ scores, unsigned long long n, const SwParams prm, const unsigned seq2_stride)
@@ -58,8 +60,8 @@ sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
     SmemFifo<NT> fifo{smem + threadIdx.x};
     SmemTable t4{t4s};
     int32_t lo, hi;
-    sw_two_pairs<FAST, L>(seq1 + p * L, seq2 + p * seq2_stride, (q != p) ? (uint32_t)L : 0u, (q != p) ? seq2_stride : 0u,
-                          fifo, t4, prm, lo, hi);
+    sw_two_pairs<FAST, L, V>(seq1 + p * L, seq2 + p * seq2_stride, (q != p) ? (uint32_t)L : 0u, (q != p) ? seq2_stride : 0u,
+                             fifo, t4, prm, lo, hi);
     if (q != p) {
         *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
     } else {

@@ -102,10 +102,11 @@ __global__ void count_bad_codes_kernel(const uint8_t* __restrict__ codes, unsign
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_bad, local);
 }
 
-// Launch geometry per sequence length: the FIFO is L words of shared memory per thread, so the
-// block shrinks as L grows (64 KiB of FIFO per block, 3 resident blocks per SM in every case).
+// Launch geometry per sequence length: the FIFO is L words of shared memory per thread (192 KiB
+// of FIFO per SM in every case), so the resident thread count shrinks as L grows.  L = 128:
+// 6 blocks x 64 threads measured best of the shapes in profiles/r01/kbench_*.jsonl.
 template <int L> struct LenCfg;
-template <> struct LenCfg<128> { static constexpr int NT = 128, MINB = 3; };
+template <> struct LenCfg<128> { static constexpr int NT = 64,  MINB = 6; };
 template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; };
 template <> struct LenCfg<512> { static constexpr int NT = 32,  MINB = 3; };
 

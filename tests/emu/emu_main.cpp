@@ -22,6 +22,16 @@ struct HostTable {
     uint32_t operator()(uint32_t byte_off) const { return t[byte_off >> 2]; }
 };
 
+static int g_variant = 0;   // variant bits of sw_core.cuh under test (SW_V_BEST_FMA)
+
+template <int L, int V>
+static void two_pairs(bool fast, const uint8_t* a, const uint8_t* b, uint32_t dqa, uint32_t dqb, HostFifo<L>& fifo, HostTable& t4,
+                      const SwParams& prm, int32_t& lo, int32_t& hi)
+{
+    if (fast) sw_two_pairs<true, L, V>(a, b, dqa, dqb, fifo, t4, prm, lo, hi);
+    else      sw_two_pairs<false, L, V>(a, b, dqa, dqb, fifo, t4, prm, lo, hi);
+}
+
 template <int L>
 static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int gap, int32_t* scores, uint64_t n, int force_general,
                    uint32_t stride2 = (uint32_t)L)
@@ -35,8 +45,11 @@ static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, i
         int32_t lo, hi;
         const uint32_t dq = (q != p) ? (uint32_t)L : 0u;
         const uint32_t dqb = (q != p) ? stride2 : 0u;
-        if (prm.fast) sw_two_pairs<true, L>(seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi);
-        else          sw_two_pairs<false, L>(seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi);
+        switch (g_variant) {
+        case 0: two_pairs<L, 0>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
+        case 1: two_pairs<L, 1>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
+        default: two_pairs<L, 1>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
+        }
         scores[p] = lo;
         if (q != p) scores[q] = hi;
     }
@@ -69,3 +82,5 @@ extern "C" int swemu_one_vs_many(const uint8_t* seq1s, const uint8_t* seq2, cons
     if (sw_check_domain(sm, gap) != SW_DOMAIN_OK) return -1;
     return run_len<128>(seq1s, seq2, sm, gap, scores, n, force_general, 0u);
 }
+
+extern "C" void swemu_set_variant(int v) { g_variant = v; }

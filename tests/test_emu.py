@@ -33,9 +33,11 @@ def emu():
     return run
 
 
-def test_emu_structured_all_param_sets(emu, golden):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emu_structured_all_param_sets(emu, golden, variant):
     z = golden["structured_npz"]
     fast_seen = general_seen = 0
+    C.CDLL(EMU_LIB).swemu_set_variant(variant)     # tuning variants of sw_core.cuh must all be bit-exact
     for ps in golden["structured"]["param_sets"]:
         exp = z[ps["name"]].astype(np.int32)
         for force_general in (0, 1):
@@ -43,6 +45,7 @@ def test_emu_structured_all_param_sets(emu, golden):
             assert np.array_equal(got, exp), (ps["name"], "fast" if path else "general")
             fast_seen += path
             general_seen += 1 - path
+    C.CDLL(EMU_LIB).swemu_set_variant(0)
     assert fast_seen >= 5 and general_seen >= 5   # both kernels' algorithms were exercised
 
 

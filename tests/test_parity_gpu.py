@@ -227,7 +227,7 @@ def test_length_sweep_parity(ctx, swb, oracle, L):
             assert np.array_equal(got, exp), (L, sm[0], g, force_general)
     assert ctx.score_batch(a[:1], b[:1], swb.MATRIX_SPEEDTEST, 15)[0] == 10 * L
     info = ctx.kernel_info(swb.MATRIX_SPEEDTEST, 15, seq_len=L)
-    assert info["fast_path"] == 1 and info["threads_per_block"] * L == 128 * 128
+    assert info["fast_path"] == 1 and info["threads_per_block"] * info["blocks_per_sm"] * L * 4 <= 227 * 1024
     if L == 512:
         with pytest.raises(swb.SwbError) as e:    # 512 * 127 overflows packed int16: refused, not wrong
             ctx.score_batch(a[:4], b[:4], mm(127, -127), 127)

@@ -20,31 +20,31 @@ static uint8_t *d1, *d2; static int32_t* dsc; static std::vector<int32_t> hsc;
 static uint64_t N = 1000000;
 static bool g_quick = false;   // `kbench ncu`: one warm-up + one timed launch of the two shipped kernels
 
-template <bool FAST, int NT, int MINB>
+template <bool FAST, int NT, int MINB, int V = SW_DEFAULT_VARIANT>
 void run(const char* name, const SwParams& prm, uint64_t want_fnv, long long want_sum)
 {
-    auto kern = sw_kernel<FAST, 128, NT, MINB>;
-    const size_t smem = sw128_smem_bytes<NT>();
+    auto kern = sw_kernel<FAST, 128, NT, MINB, V>;
+    const size_t smem = sw_smem_bytes<128, NT>();
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     const unsigned grid = (unsigned)(((N + 1) / 2 + NT - 1) / NT);
     CK(cudaMemset(dsc, 0xff, N * 4));
-    for (int i = 0; i < (g_quick ? 1 : 3); ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm);
+    for (int i = 0; i < (g_quick ? 1 : 3); ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm, 128u);
     CK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int reps = g_quick ? 1 : 10;
     cudaEventRecord(e0);
-    for (int i = 0; i < reps; ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm);
+    for (int i = 0; i < reps; ++i) kern<<<grid, NT, smem>>>(d1, d2, dsc, N, prm, 128u);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
     CK(cudaMemcpy(hsc.data(), dsc, N * 4, cudaMemcpyDeviceToHost));
     long long sum = 0; for (uint64_t i = 0; i < N; ++i) sum += hsc[i];
     const uint64_t fnv = swb200_fnv1a64_i32(hsc.data(), N);
-    printf("{\"variant\": \"%s\", \"fast\": %d, \"nt\": %d, \"minb\": %d, \"regs\": %d, \"occ_blocks\": %d, \"smem\": %zu, \"ms\": %.4f, \"gcups\": %.1f, \"ok\": %s}\n",
-           name, (int)FAST, NT, MINB, fa.numRegs, occ, smem, ms, N * 16384.0 / (ms * 1e-3) / 1e9,
+    printf("{\"variant\": \"%s\", \"fast\": %d, \"nt\": %d, \"minb\": %d, \"regs\": %d, \"v\": %d, \"occ_blocks\": %d, \"smem\": %zu, \"ms\": %.4f, \"gcups\": %.1f, \"ok\": %s}\n",
+           name, (int)FAST, NT, MINB, fa.numRegs, V, occ, smem, ms, N * 16384.0 / (ms * 1e-3) / 1e9,
            (fnv == want_fnv && sum == want_sum) ? "true" : "false");
     fflush(stdout);
 }
@@ -63,6 +63,9 @@ int main(int argc, char** argv)
     g_quick = argc > 1;
     run<true, 128, 3>("fast nt128 x3", fast, F, S);
     if (g_quick) { run<false, 128, 3>("general nt128 x3", gen, F, S); return 0; }
+    run<true, 128, 3, 0>("fast nt128 x3 V=0", fast, F, S);
+    run<true, 64, 6, 1>("fast nt64 x6 V=1", fast, F, S);
+    run<true, 64, 5, 1>("fast nt64 x5 V=1 (204 regs)", fast, F, S);
     run<true, 96, 4>("fast nt96 x4", fast, F, S);
     run<true, 64, 6>("fast nt64 x6", fast, F, S);
     run<true, 192, 2>("fast nt192 x2", fast, F, S);
