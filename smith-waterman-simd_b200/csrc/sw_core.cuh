@@ -127,6 +127,7 @@ struct SwState {
     uint32_t Z, Zp;       // fast: Z_T and Z_{T-1}
     uint32_t B;           // running best (fast: in the frame of the current step)
     uint32_t bq_lo[2], bq_hi[2];   // target bases of the next iteration's columns 0..7 (loaded 8 steps ahead)
+    uint32_t pq[8];                // Fifo::kPrefetch only: the next iteration's first 8 FIFO words (loaded 8 steps ahead)
 };
 
 // byte `idx` (0..3) of word w, times 4 (a word offset into t4[]), masked to a valid code
@@ -184,12 +185,28 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         ld8(p, bw_lo[2], bw_lo[3]);
         ld8(p + dq, bw_hi[2], bw_hi[3]);
     }
+    // A FIFO with long latency (global memory) is read 8 steps ahead of use, like the bases:
+    // words 8..15 of this iteration here, words 0..7 of the next iteration at u = 8.  Every word
+    // read was pushed at least L-15-16 steps earlier by this same thread, and the columns pushed
+    // in between (col0-15 .. col0) never coincide with the ones prefetched (L >= 64).
+    uint32_t pv[16];
+    if (Fifo::kPrefetch) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pv[q] = st.pq[q];
+#pragma unroll
+        for (int q = 8; q < 16; ++q) pv[q] = fifo.pop((WRAP ? 0 : col0) + q);
+    }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
         if (u == 8) {
-            const uint8_t* p = b_lo + (((WRAP ? 0 : col0) + 16) & (L - 1));
+            const int nc = ((WRAP ? 0 : col0) + 16) & (L - 1);
+            const uint8_t* p = b_lo + nc;
             ld8(p, st.bq_lo[0], st.bq_lo[1]);
             ld8(p + dq, st.bq_hi[0], st.bq_hi[1]);
+            if (Fifo::kPrefetch) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) st.pq[q] = fifo.pop(nc + q);
+            }
         }
         // --- selector of the column entering the window: bytes (b_lo, b_hi) -> nibbles
         //     (b_lo, 8|b_lo, 4|b_hi, 12|b_hi): low half <- byte b_lo of prA sign-extended,
@@ -210,7 +227,7 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
             }
         }
         // --- row 0's upper neighbours come from the previous strip's bottom row (frame-free in the FIFO)
-        const uint32_t popped = fifo.pop(WRAP ? u : col0 + u);
+        const uint32_t popped = Fifo::kPrefetch ? pv[u] : fifo.pop(WRAP ? u : col0 + u);
         st.dg0 = st.up0;
         st.up0 = FAST ? fadd(popped, st.Zp, prm) : popped;   // plain add: both halves >= 0, no carry across
         const uint32_t Zm2 = (FAST && WRAP) ? fsub(st.Zp, prm.G, prm) : 0u;   // true zero two steps ago
@@ -275,7 +292,12 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
     }
     // Top boundary H[0][*] = 0 (source.cpp:44)
     constexpr int STRIPS = L / SW_R;
+    static_assert(L >= 64 && (L & (L - 1)) == 0, "L must be a power of two >= 64");
     for (int c = 0; c < L; ++c) fifo.push(c, 0u);
+    if (Fifo::kPrefetch) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st.pq[q] = fifo.pop(q);
+    }
     st.Z = FAST ? prm.G + prm.G : 0u;         // Z_0 = g*(0+2)
     st.Zp = FAST ? prm.G : 0u;                // Z_{-1}
     st.B = FAST ? prm.G : 0u;                 // best = 0 in the frame of step -1

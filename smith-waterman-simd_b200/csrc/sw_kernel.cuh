@@ -20,9 +20,24 @@ constexpr int SW_DEFAULT_VARIANT = SW_V_BEST_FMA;   // the variant bits (sw_core
 
 template <int NT>
 struct SmemFifo {
+    static constexpr bool kPrefetch = false;   // 29-cycle LDS: read at the step of use
     uint32_t* f;   // &fifo[0*NT + threadIdx.x]
     __device__ __forceinline__ uint32_t pop(int c) const { return f[c * NT]; }
     __device__ __forceinline__ void push(int c, uint32_t v) { f[c * NT] = v; }
+};
+
+// The same FIFO in GLOBAL memory, for sequence lengths whose L-word FIFO would leave too few
+// resident threads if it lived in shared memory (L = 512: 3 warps per SM).  One slot of L*NT
+// words per resident block of a persistent grid, thread-interleaved (a warp's access is one
+// 128-byte line); the working set (resident threads x L x 4 B, 58 MB at L = 256, 116 MB at
+// L = 512) lives in the 126 MB L2.  A thread only ever reads what it wrote itself, so plain
+// (coherent) loads and stores are ordered correctly without fences; .cg keeps them out of L1.
+template <int NT>
+struct GlobalFifo {
+    static constexpr bool kPrefetch = true;    // L2 latency: read 8 steps ahead (sw_core.cuh)
+    uint32_t* f;   // &slot[0*NT + threadIdx.x]
+    __device__ __forceinline__ uint32_t pop(int c) const { return __ldcg(f + c * NT); }
+    __device__ __forceinline__ void push(int c, uint32_t v) { __stcg(f + c * NT, v); }
 };
 
 struct SmemTable {
@@ -66,6 +81,32 @@ sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
         *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);   // p is even: 8-byte aligned
     } else {
         scores[p] = lo;
+    }
+}
+
+// Persistent-grid variant with the FIFO in global memory: grid = resident blocks; block b owns
+// slot b of `fifo_scratch` (L*NT words) and walks the work items b, b+gridDim.x, ...
+template <bool FAST, int L, int NT, int MINB, int V = SW_DEFAULT_VARIANT>
+__global__ void __launch_bounds__(NT, MINB)
+sw_kernel_gfifo(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
+                int32_t* __restrict__ scores, unsigned long long n, const SwParams prm, const unsigned seq2_stride,
+                uint32_t* __restrict__ fifo_scratch)
+{
+    __shared__ uint32_t t4s[4];
+    if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
+    __syncthreads();
+    GlobalFifo<NT> fifo{fifo_scratch + (size_t)blockIdx.x * L * NT + threadIdx.x};
+    SmemTable t4{t4s};
+    const unsigned long long n_items = (n + 1) / 2;
+    for (unsigned long long item = (unsigned long long)blockIdx.x * NT + threadIdx.x; item < n_items;
+         item += (unsigned long long)gridDim.x * NT) {
+        const unsigned long long p = 2ull * item;
+        const unsigned long long q = (p + 1 < n) ? p + 1 : p;
+        int32_t lo, hi;
+        sw_two_pairs<FAST, L, V>(seq1 + p * L, seq2 + p * seq2_stride, (q != p) ? (uint32_t)L : 0u, (q != p) ? seq2_stride : 0u,
+                                 fifo, t4, prm, lo, hi);
+        if (q != p) *reinterpret_cast<int2*>(scores + p) = make_int2(lo, hi);
+        else scores[p] = lo;
     }
 }
 

@@ -11,8 +11,18 @@
 
 using namespace swb;
 
+static int g_prefetch = 0;  // 1: exercise the read-ahead path used by the global-memory FIFO
+
 template <int L>
 struct HostFifo {
+    static constexpr bool kPrefetch = false;
+    uint32_t w[L];
+    uint32_t pop(int c) const { return w[c & (L - 1)]; }
+    void push(int c, uint32_t v) { w[c & (L - 1)] = v; }
+};
+template <int L>
+struct HostFifoAhead {          // same storage, but sw_core.cuh reads it 8 steps ahead (Fifo::kPrefetch)
+    static constexpr bool kPrefetch = true;
     uint32_t w[L];
     uint32_t pop(int c) const { return w[c & (L - 1)]; }
     void push(int c, uint32_t v) { w[c & (L - 1)] = v; }
@@ -28,6 +38,13 @@ template <int L, int V>
 static void two_pairs(bool fast, const uint8_t* a, const uint8_t* b, uint32_t dqa, uint32_t dqb, HostFifo<L>& fifo, HostTable& t4,
                       const SwParams& prm, int32_t& lo, int32_t& hi)
 {
+    if (g_prefetch) {
+        HostFifoAhead<L> ahead;
+        for (int i = 0; i < L; ++i) ahead.w[i] = 0xdeadbeefu;   // anything read before it was written shows up as a wrong score
+        if (fast) sw_two_pairs<true, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
+        else      sw_two_pairs<false, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
+        return;
+    }
     if (fast) sw_two_pairs<true, L, V>(a, b, dqa, dqb, fifo, t4, prm, lo, hi);
     else      sw_two_pairs<false, L, V>(a, b, dqa, dqb, fifo, t4, prm, lo, hi);
 }
@@ -84,3 +101,4 @@ extern "C" int swemu_one_vs_many(const uint8_t* seq1s, const uint8_t* seq2, cons
 }
 
 extern "C" void swemu_set_variant(int v) { g_variant = v; }
+extern "C" void swemu_set_prefetch(int on) { g_prefetch = on; }

@@ -89,11 +89,13 @@ def _related_pairs(rng, n, L):
     return a, b
 
 
+@pytest.mark.parametrize("prefetch", [0, 1])
 @pytest.mark.parametrize("L", [256, 512])
-def test_emu_length_sweep(emu, oracle, L):
+def test_emu_length_sweep(emu, oracle, L, prefetch):
     # BASELINE.json configs[3]: 2x and 4x the built-in shape; oracle = source.cpp:35-60 restated for any length
     rng = np.random.default_rng(L)
     a, b = _related_pairs(rng, 41, L)
+    C.CDLL(EMU_LIB).swemu_set_prefetch(prefetch)   # 1 = the read-ahead FIFO path of the global-memory FIFO kernels
 
     def mm(m, x):
         return [m if i == j else x for i in range(4) for j in range(4)]
@@ -106,6 +108,20 @@ def test_emu_length_sweep(emu, oracle, L):
     # 512 * 127 does not fit int16: refused, not wrong
     rc, _ = emu(a, b, mm(127, -127), 127, allow_refusal=True)
     assert rc == (-2 if L == 512 else 0)
+    C.CDLL(EMU_LIB).swemu_set_prefetch(0)
+
+
+def test_emu_prefetching_fifo_at_128(emu, golden):
+    z = golden["structured_npz"]
+    lib = C.CDLL(EMU_LIB)
+    lib.swemu_set_prefetch(1)
+    try:
+        for ps in golden["structured"]["param_sets"][:6]:
+            for force_general in (0, 1):
+                _, got = emu(z["seq1"], z["seq2"], ps["matrix"], ps["gap"], force_general)
+                assert np.array_equal(got, z[ps["name"]].astype(np.int32)), ps["name"]
+    finally:
+        lib.swemu_set_prefetch(0)
 
 
 def test_emu_one_vs_many_matches_x32_golden():
