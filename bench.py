@@ -303,9 +303,29 @@ def run_b200_arm(args):
         verified = (f"{swb200.fnv1a64(scores):016x}" == "ae56a1e6a1d57492") and int(scores.sum()) == 75_478_815
 
     # ================= leg 2: end to end through the C-ABI host call (pinned host in/out)
-    for _ in range(min(args.warmup, 3)):
+    # Host cores per GPU that compress sub-chunks to 2 bits before PCIe (include/swb200.h, "host-side
+    # 2-bit packing lanes").  One rank: the library's own default.  Several ranks share the box's cores.
+    if args.pack_threads is not None:
+        ctx.set_host_pack_threads(args.pack_threads)
+    elif world > 1:
+        ctx.set_host_pack_threads(max(0, (os.cpu_count() or 1) // world - 2))
+    plain_ms = None
+    if world == 1 and not args.no_plain_e2e:
+        # the same call with the packing lanes off (every byte crosses PCIe), for the record
+        keep = ctx.host_pack_stats()["pack_threads_per_gpu"]
+        ctx.set_host_pack_threads(0)
+        for _ in range(2):
+            ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
+        tp0 = time.perf_counter()
+        for _ in range(5):
+            ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
+        plain_ms = 1e3 * (time.perf_counter() - tp0) / 5
+        ctx.set_host_pack_threads(args.pack_threads if args.pack_threads is not None else -1)
+        assert ctx.host_pack_stats()["pack_threads_per_gpu"] == keep
+    for _ in range(max(min(args.warmup, 3), 3)):
         ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
     barrier()
+    pack0 = ctx.host_pack_stats()
     launches1 = ctx.launch_count
     e2e_steps = args.steps
     t0 = time.perf_counter()
@@ -315,6 +335,8 @@ def run_b200_arm(args):
     t1 = time.perf_counter()
     sampler.stop()
     launches_e2e = ctx.launch_count - launches1
+    pack1 = ctx.host_pack_stats()
+    packed_frac = (pack1["packed_pairs"] - pack0["packed_pairs"]) / float(n * e2e_steps)
     e2e_ms = max_over_ranks(1e3 * (t1 - t0) / e2e_steps, ddist)
     e2e_gcups = total_pairs * CELLS_PER_PAIR / (e2e_ms * 1e-3) / 1e9
     e2e_ok = bool(np.array_equal(ps.array, scores))
@@ -367,8 +389,13 @@ def run_b200_arm(args):
                        "kernel": info},
             "clocks": clocks,
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "ms_per_step": e2e_ms, "alignments_per_s": total_pairs / (e2e_ms * 1e-3),
-                    "h2d_bytes_per_step": 2 * n * 128, "d2h_bytes_per_step": 4 * n,
-                    "api": "swb200_score_batch (C ABI, pinned host arrays, chunked H2D/kernel/D2H overlap)", "scores_equal_device_leg": all_ok},
+                    "h2d_bytes_per_step": int(round(2 * n * (128 * (1.0 - packed_frac) + 32 * packed_frac))), "d2h_bytes_per_step": 4 * n,
+                    "host_input_bytes_per_step": 2 * n * 128,
+                    "api": "swb200_score_batch (C ABI, pinned host byte arrays [n][128] in, int32 scores out; RAW lane + host 2-bit packing lanes, H2D/kernel/D2H overlapped)",
+                    "host_pack": {"threads_per_gpu": pack1["pack_threads_per_gpu"], "fraction_of_pairs_sent_packed": packed_frac,
+                                  "plain_pipeline_ms_per_step": plain_ms,
+                                  "note": "rank 0's split; wire compression only, no scoring on the host"},
+                    "scores_equal_device_leg": all_ok},
             "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,
             "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok},
@@ -499,6 +526,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pack-threads", type=int, default=None, help="host 2-bit packing lanes per GPU in the e2e leg (default: library auto; 0 = off)")
+    ap.add_argument("--no-plain-e2e", action="store_true", help="skip the lanes-off comparison run of the e2e leg")
     ap.add_argument("--cpu-table", action="store_true", help="with --impl reference: scalar/simd4/simd7/simd9, 1 thread and all cores")
     ap.add_argument("--workload", choices=["batch1m", "stream", "sweep"], default="batch1m",
                     help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")

@@ -101,7 +101,16 @@ int swb200_score_one_vs_many(swb200_ctx* ctx, const uint8_t* seq1s, const uint8_
                              const int8_t* score_matrix, int8_t gap_penalty,
                              int32_t* scores, uint64_t n);
 
-/* Same, inputs as the reference's 2-bit packing: 32 bytes per sequence,
+/* Fixed match/mismatch/gap = 1/1/1 scoring, replacing
+ *   int SmithWaterman_111(const std::array<uint8_t,128>& seq1, const std::array<uint8_t,128>& seq2)      (source.cpp:1073-1103)
+ *   int SmithWaterman_8bit111simd(same arguments)                                                        (source.cpp:1105-1225)
+ * for n pairs.  The reference needs a separate 8-bit kernel for this scoring because AVX2 doubles
+ * its lane count at 8 bits; sm_100a has no native u8x4 min/max, and the packed int16x2 kernel
+ * already spends no instruction on the generality (the score comes from one PRMT either way), so
+ * this entry runs the same kernel with the matrix fixed at +1/-1 and gap 1. */
+int swb200_score_batch_111(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t* scores, uint64_t n);
+
+/* Batch scoring with inputs as the reference's 2-bit packing: 32 bytes per sequence,
  * code(i*4+j) = (byte[i] >> 2j) & 3   (source.cpp:1580-1583, `unpack`).
  * seq1_packed[n][32], seq2_packed[n][32].  Unpacking happens on the device. */
 int swb200_score_batch_packed(swb200_ctx* ctx, const uint8_t* seq1_packed, const uint8_t* seq2_packed,
@@ -164,6 +173,22 @@ int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* scor
 
 int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const int8_t* score_matrix,
                            int8_t gap_penalty, swb200_kernel_info* info);
+
+/* ---- host-side 2-bit packing lanes of swb200_score_batch ------------------------------
+ * The caller's byte codes carry 2 bits each but cross PCIe as 8.  For large batches
+ * swb200_score_batch therefore runs, per GPU, one RAW lane (the caller's bytes, 256 B per pair)
+ * and `threads_per_gpu` PACK lanes (a host core compresses a sub-chunk to the reference's
+ * 2-bit layout, source.cpp:1580-1583, into pinned staging; 64 B per pair cross the link and
+ * the device expands them).  All lanes draw sub-chunks of 16384 pairs from one counter, so
+ * the split adapts to the machine.  This is wire compression only: no score is ever computed
+ * on the host.  threads_per_gpu: -1 = auto (CPUs this process may run on, minus two, per GPU;
+ * env SWB200_PACK_THREADS overrides), 0 = off (every pair travels as bytes). */
+int swb200_set_host_pack_threads(swb200_ctx* ctx, int threads_per_gpu);
+/* Pairs sent packed / as bytes by host batches so far, and the lane count in effect. */
+int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64_t* raw_pairs, int* threads_per_gpu);
+/* The packer itself (inverse of the reference's `unpack`, source.cpp:1580-1583), for callers
+ * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
+int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);
 
 /* Kernel launches issued by this context since creation (all GPUs). */
 uint64_t swb200_launch_count(const swb200_ctx* ctx);

@@ -85,6 +85,8 @@ def ref():
         lib.swref_unpack.argtypes = [_u8p, _u8p]
         lib.swref_111.restype = C.c_int
         lib.swref_111.argtypes = [_u8p, _u8p]
+        lib.swref_8bit111.restype = C.c_int
+        lib.swref_8bit111.argtypes = [_u8p, _u8p]
         lib.swref_x32.restype = C.c_int
         lib.swref_x32.argtypes = [C.c_int, _u8p, _u8p, _i32p]
         lib.swref_hardware_threads.restype = C.c_int
@@ -141,6 +143,13 @@ def ref_111(seq1: np.ndarray, seq2: np.ndarray) -> int:
     a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(128)
     b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(128)
     return int(ref().swref_111(_p(a, _u8p), _p(b, _u8p)))
+
+
+def ref_8bit111(seq1: np.ndarray, seq2: np.ndarray) -> int:
+    """The reference's SmithWaterman_8bit111simd (source.cpp:1105-1225)."""
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(128)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(128)
+    return int(ref().swref_8bit111(_p(a, _u8p), _p(b, _u8p)))
 
 
 def x32_stream(iterations: int, seed: int = 10000):

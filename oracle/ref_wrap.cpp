@@ -122,6 +122,15 @@ int swref_111(const uint8_t* seq1, const uint8_t* seq2)
     return SmithWaterman_111(a, b);
 }
 
+// SmithWaterman_8bit111simd (source.cpp:1105-1225): the 8-bit AVX2 kernel for the same fixed scoring
+int swref_8bit111(const uint8_t* seq1, const uint8_t* seq2)
+{
+    Seq a, b;
+    std::memcpy(a.data(), seq1, 128);
+    std::memcpy(b.data(), seq2, 128);
+    return SmithWaterman_8bit111simd(a, b);
+}
+
 // SmithWaterman_8b111x32mark1/2/3 (source.cpp:1227, 1299, 1383): 32 queries x one target, fixed 1/1/1
 int swref_x32(int mark, const uint8_t* seq1_32x128, const uint8_t* seq2, int32_t* dest32)
 {

@@ -6,9 +6,13 @@
 
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <array>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -19,12 +23,22 @@
 #include "sw_kernel.cuh"
 #include "sw_params.h"
 
+namespace swb { void pack2bit_host(const uint8_t* codes, uint8_t* packed, size_t n_codes); }   // hostpack.cpp
+
 namespace {
 
 using namespace swb;
 
 constexpr int kSlots = 3;        // chunks in flight per GPU
 constexpr uint64_t kChunkPairs = 1ull << 17;   // 131072 pairs of 128 bases = 16 MiB per sequence array per chunk (fewer pairs for longer sequences)
+
+// Host-packing lanes (see run_range_lanes): sub-chunks of kSubPairs pairs, kLaneDepth in flight per lane.
+constexpr uint64_t kSubPairs = 1ull << 14;     // 16384 pairs: 2 MiB per byte-coded array, 0.5 MiB packed
+constexpr int kLaneDepth = 8;                  // buffer sets per lane (array size)
+constexpr int kPackDepth = 3;                  // in flight per PACK lane: the host core is the slow stage
+constexpr int kRawDepth = 8;                   // in flight on the RAW lane: enough 4 MiB copies queued to keep the link busy
+                                               // while earlier sub-chunks wait for their kernel (measured: depth 3 left it at 14 GB/s)
+constexpr uint64_t kLanesMinPairs = 16 * kSubPairs;   // below this the plain chunk pipeline is used
 
 thread_local std::string g_init_error;
 
@@ -39,12 +53,49 @@ struct Slot {
     bool busy = false;
 };
 
+// One lane = one host thread + one stream + kLaneDepth sets of buffers.  A PACK lane compresses a
+// sub-chunk of the caller's byte codes to 2 bits per base on its host core (hostpack.cpp), sends
+// 64 B per pair over PCIe and expands them on the device; the RAW lane sends the caller's bytes
+// as they are (256 B per pair).  Both kinds pull sub-chunks from one counter, so the PCIe link
+// and the host cores are both kept busy and the split adapts to whatever machine this is.
+struct Lane {
+    bool pack = false;
+    int depth = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done[kLaneDepth] = {};
+    bool busy[kLaneDepth] = {};
+    uint8_t* h_pk[kLaneDepth] = {};      // pinned [2][kSubPairs][32]   (pack lanes)
+    uint8_t* d_pk[kLaneDepth] = {};      // device [2][kSubPairs][32]   (pack lanes)
+    uint8_t* d_seq[kLaneDepth] = {};     // device [2][kSubPairs][128]: seq1 rows then seq2 rows
+    int32_t* d_scores[kLaneDepth] = {};
+    std::thread th;
+};
+
+struct LaneJob {
+    const uint8_t* seq1 = nullptr;
+    const uint8_t* seq2 = nullptr;
+    int32_t* scores = nullptr;
+    uint64_t lo = 0, hi = 0;
+    SwParams prm{};
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> rc{0};
+    std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};
+};
+
 struct Device {
     int id = -1;
     cudaDeviceProp prop{};
     Slot slots[kSlots];
     std::mutex mu;                   // one host batch at a time per GPU
     unsigned long long* d_bad = nullptr;
+    // lane pool (created on first use)
+    std::vector<Lane*> lanes;
+    std::mutex pool_mu;
+    std::condition_variable pool_cv, pool_done_cv;
+    uint64_t pool_gen = 0;
+    int pool_pending = 0;
+    bool pool_stop = false;
+    LaneJob* job = nullptr;
 };
 
 } // namespace
@@ -53,7 +104,9 @@ struct swb200_ctx {
     std::vector<Device*> devs;
     std::string err;
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};   // host batches: pairs sent 2-bit packed / as bytes
     int force_general = 0;
+    int pack_threads = -1;           // per GPU; -1 = auto (host cores available to this process), 0 = off
     std::mutex tickets_mu;
     std::map<uint64_t, std::pair<std::thread, int*>> tickets;
     uint64_t next_ticket = 1;
@@ -102,13 +155,27 @@ __global__ void count_bad_codes_kernel(const uint8_t* __restrict__ codes, unsign
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_bad, local);
 }
 
-// Launch geometry per sequence length: the FIFO is L words of shared memory per thread (192 KiB
-// of FIFO per SM in every case), so the resident thread count shrinks as L grows.  L = 128:
-// 6 blocks x 64 threads measured best of the shapes in profiles/r01/kbench_*.jsonl.
+// Launch geometry per sequence length.  With the FIFO in shared memory (L words per thread,
+// 192 KiB of FIFO per SM in every case) the resident thread count shrinks as L grows: 12 warps
+// per SM at L = 128, 6 at 256, 3 at 512 -- and 3 warps leave one of the four schedulers idle.
+// L = 512 therefore keeps its FIFO in global memory (GlobalFifo, sw_kernel.cuh): a persistent
+// grid of SMs x MINB blocks, one L*NT-word slot per block, resident in L2.
+// L = 128: 6 blocks x 64 threads measured best of the shapes in profiles/r01/kbench_*.jsonl;
+// the long shapes: profiles/r01/kbench_len.jsonl.
 template <int L> struct LenCfg;
-template <> struct LenCfg<128> { static constexpr int NT = 64,  MINB = 6; };
-template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; };
-template <> struct LenCfg<512> { static constexpr int NT = 32,  MINB = 3; };
+template <> struct LenCfg<128> { static constexpr int NT = 64,  MINB = 6; static constexpr bool GFIFO = false; };
+template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; static constexpr bool GFIFO = false; };
+template <> struct LenCfg<512> { static constexpr int NT = 64,  MINB = 4; static constexpr bool GFIFO = true; };
+
+template <bool FAST, int L>
+constexpr auto kernel_ptr()
+{
+    if constexpr (LenCfg<L>::GFIFO) return sw_kernel_gfifo<FAST, L, LenCfg<L>::NT, LenCfg<L>::MINB>;
+    else return sw_kernel<FAST, L, LenCfg<L>::NT, LenCfg<L>::MINB>;
+}
+
+template <int L>
+constexpr size_t kernel_smem() { return LenCfg<L>::GFIFO ? 0 : sw_smem_bytes<L, LenCfg<L>::NT>(); }
 
 template <bool FAST, int L>
 cudaError_t launch_sw(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, const SwParams& prm, cudaStream_t st, bool shared_target)
@@ -116,9 +183,28 @@ cudaError_t launch_sw(const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64
     if (n == 0) return cudaSuccess;
     constexpr int NT = LenCfg<L>::NT;
     const uint64_t threads = (n + 1) / 2;
-    const unsigned grid = (unsigned)((threads + NT - 1) / NT);
-    sw_kernel<FAST, L, NT, LenCfg<L>::MINB><<<grid, NT, sw_smem_bytes<L, NT>(), st>>>(d1, d2, dsc, n, prm, shared_target ? 0u : (unsigned)L);
-    return cudaGetLastError();
+    const uint64_t blocks = (threads + NT - 1) / NT;
+    const unsigned stride = shared_target ? 0u : (unsigned)L;
+    if constexpr (LenCfg<L>::GFIFO) {
+        // persistent grid; the FIFO slots come from the stream-ordered pool (kept warm by
+        // setup_device's release threshold), so concurrent streams never share a slot
+        int dev = 0, n_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        const uint64_t resident = (uint64_t)n_sm * LenCfg<L>::MINB;
+        const unsigned grid = (unsigned)(blocks < resident ? blocks : resident);
+        uint32_t* fifo = nullptr;
+        e = cudaMallocAsync(&fifo, (size_t)grid * L * NT * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        sw_kernel_gfifo<FAST, L, NT, LenCfg<L>::MINB><<<grid, NT, 0, st>>>(d1, d2, dsc, n, prm, stride, fifo);
+        e = cudaGetLastError();
+        const cudaError_t e2 = cudaFreeAsync(fifo, st);
+        return e != cudaSuccess ? e : e2;
+    } else {
+        sw_kernel<FAST, L, NT, LenCfg<L>::MINB><<<(unsigned)blocks, NT, sw_smem_bytes<L, NT>(), st>>>(d1, d2, dsc, n, prm, stride);
+        return cudaGetLastError();
+    }
 }
 
 cudaError_t launch_for(const SwParams& prm, int L, const uint8_t* d1, const uint8_t* d2, int32_t* dsc, uint64_t n, cudaStream_t st,
@@ -136,23 +222,27 @@ cudaError_t launch_for(const SwParams& prm, int L, const uint8_t* d1, const uint
 template <bool FAST, int L>
 cudaError_t prepare_kernel()
 {
-    constexpr int NT = LenCfg<L>::NT;
-    auto kern = sw_kernel<FAST, L, NT, LenCfg<L>::MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes<L, NT>());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if constexpr (LenCfg<L>::GFIFO) return cudaSuccess;
+    else {
+        auto kern = kernel_ptr<FAST, L>();
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kernel_smem<L>());
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
 }
 
 template <bool FAST, int L>
 cudaError_t kernel_resources(cudaFuncAttributes* fa, int* blocks, int* nt, int* smem)
 {
     constexpr int NT = LenCfg<L>::NT;
-    auto kern = sw_kernel<FAST, L, NT, LenCfg<L>::MINB>;
+    auto kern = kernel_ptr<FAST, L>();
     cudaError_t e = cudaFuncGetAttributes(fa, kern);
     if (e != cudaSuccess) return e;
     *nt = NT;
-    *smem = (int)sw_smem_bytes<L, NT>();
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, sw_smem_bytes<L, NT>());
+    *smem = (int)kernel_smem<L>();
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, kernel_smem<L>());
+    if (LenCfg<L>::GFIFO && *blocks > LenCfg<L>::MINB) *blocks = LenCfg<L>::MINB;   // the persistent grid launches MINB per SM
+    return e;
 }
 
 cudaError_t launch_unpack(const uint8_t* d_packed, uint8_t* d_codes, uint64_t n_seqs, cudaStream_t st)
@@ -172,6 +262,13 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
+    {
+        // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
+        cudaMemPool_t pool;
+        SWB_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, d->id));
+        uint64_t keep = ~0ull;
+        SWB_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (Slot& s : d->slots) {
         SWB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         SWB_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -235,6 +332,183 @@ int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* se
     return SWB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Host-packing lanes.  PCIe moves the caller's byte-coded arrays at ~52 GB/s, i.e. 5 ms per
+// million pairs against 1.8 ms of kernel time.  The bytes carry 2 bits of information each, so
+// spare host cores compress sub-chunks to the reference's 2-bit wire format (hostpack.cpp) into
+// pinned staging while the RAW lane keeps the link busy with uncompressed sub-chunks.
+int available_cpus()
+{
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return n;
+    }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
+int pack_threads_per_gpu(const swb200_ctx* ctx)
+{
+    if (ctx->pack_threads >= 0) return ctx->pack_threads;
+    if (const char* e = getenv("SWB200_PACK_THREADS")) return atoi(e) < 0 ? 0 : atoi(e);
+    const int G = (int)ctx->devs.size();
+    int t = (available_cpus() - 1) / G - 1;      // one core per GPU stays with the RAW lane, one with the caller
+    if (t > 30) t = 30;
+    return t >= 3 ? t : 0;                       // a couple of cores cannot beat the link: plain pipeline
+}
+
+int lane_alloc(swb200_ctx* ctx, Lane* ln)
+{
+    SWB_CUDA(ctx, cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+    ln->depth = ln->pack ? kPackDepth : kRawDepth;
+    for (int b = 0; b < ln->depth; ++b) {
+        SWB_CUDA(ctx, cudaEventCreateWithFlags(&ln->done[b], cudaEventDisableTiming));
+        SWB_CUDA(ctx, cudaMalloc(&ln->d_seq[b], 2 * kSubPairs * SWB200_SEQ_LEN));
+        SWB_CUDA(ctx, cudaMalloc(&ln->d_scores[b], kSubPairs * sizeof(int32_t)));
+        if (ln->pack) {
+            SWB_CUDA(ctx, cudaHostAlloc(&ln->h_pk[b], 2 * kSubPairs * 32, cudaHostAllocPortable));
+            SWB_CUDA(ctx, cudaMalloc(&ln->d_pk[b], 2 * kSubPairs * 32));
+        }
+    }
+    return SWB200_OK;
+}
+
+void lane_free(Lane* ln)
+{
+    for (int b = 0; b < kLaneDepth; ++b) {
+        if (ln->done[b]) cudaEventDestroy(ln->done[b]);
+        cudaFree(ln->d_seq[b]); cudaFree(ln->d_scores[b]); cudaFree(ln->d_pk[b]);
+        if (ln->h_pk[b]) cudaFreeHost(ln->h_pk[b]);
+    }
+    if (ln->stream) cudaStreamDestroy(ln->stream);
+}
+
+// One lane's share of a job: sub-chunks taken from the job's counter until none are left.
+int lane_run(swb200_ctx* ctx, Lane* ln, LaneJob* job)
+{
+    const uint64_t n_sub = (job->hi - job->lo + kSubPairs - 1) / kSubPairs;
+    int b = 0;
+    for (;;) {
+        if (job->rc.load() != SWB200_OK) break;
+        const uint64_t idx = job->next.fetch_add(1);
+        if (idx >= n_sub) break;
+        const uint64_t c0 = job->lo + idx * kSubPairs;
+        const uint64_t m = (job->hi - c0 < kSubPairs) ? job->hi - c0 : kSubPairs;
+        if (ln->busy[b]) { SWB_CUDA(ctx, cudaEventSynchronize(ln->done[b])); ln->busy[b] = false; }
+        uint8_t* d1 = ln->d_seq[b];
+        uint8_t* d2 = ln->d_seq[b] + m * SWB200_SEQ_LEN;
+        if (ln->pack) {
+            pack2bit_host(job->seq1 + c0 * SWB200_SEQ_LEN, ln->h_pk[b], m * SWB200_SEQ_LEN);
+            pack2bit_host(job->seq2 + c0 * SWB200_SEQ_LEN, ln->h_pk[b] + m * 32, m * SWB200_SEQ_LEN);
+            SWB_CUDA(ctx, cudaMemcpyAsync(ln->d_pk[b], ln->h_pk[b], 2 * m * 32, cudaMemcpyHostToDevice, ln->stream));
+            SWB_CUDA(ctx, launch_unpack(ln->d_pk[b], ln->d_seq[b], 2 * m, ln->stream));   // seq1 rows then seq2 rows
+            ctx->launches += 1;
+            job->packed_pairs += m;
+        } else {
+            SWB_CUDA(ctx, cudaMemcpyAsync(d1, job->seq1 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, ln->stream));
+            SWB_CUDA(ctx, cudaMemcpyAsync(d2, job->seq2 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, ln->stream));
+            job->raw_pairs += m;
+        }
+        SWB_CUDA(ctx, launch_for(job->prm, SWB200_SEQ_LEN, d1, d2, ln->d_scores[b], m, ln->stream, false));
+        ctx->launches += 1;
+        SWB_CUDA(ctx, cudaMemcpyAsync(job->scores + c0, ln->d_scores[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, ln->stream));
+        SWB_CUDA(ctx, cudaEventRecord(ln->done[b], ln->stream));
+        ln->busy[b] = true;
+        b = (b + 1) % ln->depth;
+    }
+    for (int k = 0; k < ln->depth; ++k)
+        if (ln->busy[k]) { ln->busy[k] = false; SWB_CUDA(ctx, cudaEventSynchronize(ln->done[k])); }
+    return SWB200_OK;
+}
+
+// `seen` = the pool generation at the time the lane was created (a pool can be rebuilt after
+// earlier jobs, see swb200_set_host_pack_threads): the lane answers only to jobs posted later.
+void lane_main(swb200_ctx* ctx, Device* d, Lane* ln, uint64_t seen)
+{
+    cudaSetDevice(d->id);
+    for (;;) {
+        LaneJob* job;
+        {
+            std::unique_lock<std::mutex> lk(d->pool_mu);
+            d->pool_cv.wait(lk, [&] { return d->pool_stop || d->pool_gen != seen; });
+            if (d->pool_stop) return;
+            seen = d->pool_gen;
+            job = d->job;
+        }
+        const int rc = lane_run(ctx, ln, job);
+        if (rc != SWB200_OK) job->rc.store(rc);
+        {
+            std::lock_guard<std::mutex> lk(d->pool_mu);
+            if (--d->pool_pending == 0) d->pool_done_cv.notify_all();
+        }
+    }
+}
+
+void stop_lanes(Device* d)
+{
+    {
+        std::lock_guard<std::mutex> lk(d->pool_mu);
+        d->pool_stop = true;
+    }
+    d->pool_cv.notify_all();
+    for (Lane* ln : d->lanes) {
+        if (ln->th.joinable()) ln->th.join();
+        lane_free(ln);
+        delete ln;
+    }
+    d->lanes.clear();
+}
+
+// Creates the pool on first use: one RAW lane + `n_pack` PACK lanes.  Called under d->mu.
+int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
+{
+    if (!d->lanes.empty()) return SWB200_OK;
+    for (int k = 0; k <= n_pack; ++k) {
+        Lane* ln = new Lane;
+        ln->pack = (k > 0);
+        d->lanes.push_back(ln);
+        const int rc = lane_alloc(ctx, ln);
+        if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
+            stop_lanes(d);
+            d->pool_stop = false;
+            return rc;
+        }
+    }
+    uint64_t gen;
+    {
+        std::lock_guard<std::mutex> lk(d->pool_mu);
+        gen = d->pool_gen;
+    }
+    for (Lane* ln : d->lanes) ln->th = std::thread(lane_main, ctx, d, ln, gen);
+    return SWB200_OK;
+}
+
+// One GPU's share [lo, hi) of a byte-coded host batch through the lane pool.
+int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, const SwParams& prm,
+                    int32_t* scores, uint64_t lo, uint64_t hi, int n_pack)
+{
+    std::lock_guard<std::mutex> lock(d->mu);
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    int rc = ensure_lanes(ctx, d, n_pack);
+    if (rc != SWB200_OK) return rc;
+    LaneJob job;
+    job.seq1 = seq1; job.seq2 = seq2; job.scores = scores; job.lo = lo; job.hi = hi; job.prm = prm;
+    {
+        std::unique_lock<std::mutex> lk(d->pool_mu);
+        d->job = &job;
+        d->pool_pending = (int)d->lanes.size();
+        ++d->pool_gen;
+        d->pool_cv.notify_all();
+        d->pool_done_cv.wait(lk, [&] { return d->pool_pending == 0; });
+        d->job = nullptr;
+    }
+    ctx->packed_pairs += job.packed_pairs.load();
+    ctx->raw_pairs += job.raw_pairs.load();
+    return job.rc.load();
+}
+
 int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, int gap, const void* out, uint64_t n)
 {
     if (!ctx) return SWB200_ERR_ARG;
@@ -261,14 +535,20 @@ int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool p
     if (rc != SWB200_OK || n == 0) return rc;
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
-    if (G == 1 || n < 2 * G) return run_range(ctx, ctx->devs[0], seq1, seq2, packed, L, prm, scores, 0, n, shared_target);
+    // Large byte-coded batches of the reference shape go through the host-packing lanes.
+    const int n_pack = (!packed && !shared_target && L == SWB200_SEQ_LEN && n / G >= kLanesMinPairs) ? pack_threads_per_gpu(ctx) : 0;
+    auto range = [=](Device* d, uint64_t lo, uint64_t hi) {
+        return n_pack > 0 ? run_range_lanes(ctx, d, seq1, seq2, prm, scores, lo, hi, n_pack)
+                          : run_range(ctx, d, seq1, seq2, packed, L, prm, scores, lo, hi, shared_target);
+    };
+    if (G == 1 || n < 2 * G) return range(ctx->devs[0], 0, n);
     // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
     // every GPU DMA-writes its own slice of `scores`: that is the whole gather.
     std::vector<std::thread> pool;
     std::vector<int> rcs(G, SWB200_OK);
     for (size_t k = 0; k < G; ++k) {
         const uint64_t lo = n * k / G, hi = n * (k + 1) / G;
-        pool.emplace_back([=, &rcs] { rcs[k] = run_range(ctx, ctx->devs[k], seq1, seq2, packed, L, prm, scores, lo, hi, shared_target); });
+        pool.emplace_back([=, &rcs] { rcs[k] = range(ctx->devs[k], lo, hi); });
     }
     for (auto& t : pool) t.join();
     for (int r : rcs) if (r != SWB200_OK) return r;
@@ -331,6 +611,7 @@ void swb200_shutdown(swb200_ctx* ctx)
     }
     for (Device* d : ctx->devs) {
         cudaSetDevice(d->id);
+        stop_lanes(d);
         for (Slot& s : d->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             cudaFree(s.d_seq1); cudaFree(s.d_seq2); cudaFree(s.d_pk1); cudaFree(s.d_pk2); cudaFree(s.d_scores);
@@ -390,6 +671,12 @@ int swb200_score_one_vs_many(swb200_ctx* ctx, const uint8_t* seq1s, const uint8_
                              int32_t* scores, uint64_t n)
 {
     return score_host(ctx, seq1s, seq2, false, sm, gap, scores, n, SWB200_SEQ_LEN, true);
+}
+
+int swb200_score_batch_111(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t* scores, uint64_t n)
+{
+    static const int8_t m111[16] = {1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1};   // source.cpp:1079
+    return score_host(ctx, seq1, seq2, false, m111, 1, scores, n);
 }
 
 int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, int8_t gap, int32_t* score)
@@ -562,6 +849,36 @@ int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, 
 }
 
 uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int swb200_set_host_pack_threads(swb200_ctx* ctx, int threads_per_gpu)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    for (Device* d : ctx->devs) {
+        std::lock_guard<std::mutex> lock(d->mu);
+        cudaSetDevice(d->id);
+        stop_lanes(d);                 // the pool is rebuilt with the new size on the next batch
+        d->pool_stop = false;
+    }
+    ctx->pack_threads = threads_per_gpu < 0 ? -1 : threads_per_gpu;
+    return SWB200_OK;
+}
+
+int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64_t* raw_pairs, int* threads_per_gpu)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    if (packed_pairs) *packed_pairs = ctx->packed_pairs.load();
+    if (raw_pairs) *raw_pairs = ctx->raw_pairs.load();
+    if (threads_per_gpu) *threads_per_gpu = pack_threads_per_gpu(ctx);
+    return SWB200_OK;
+}
+
+int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes)
+{
+    if ((!codes || !packed) && n_codes) return SWB200_ERR_ARG;
+    if (n_codes % 8) return SWB200_ERR_ARG;
+    pack2bit_host(codes, packed, (size_t)n_codes);
+    return SWB200_OK;
+}
 
 int swb200_set_force_general(swb200_ctx* ctx, int on)
 {

@@ -69,6 +69,18 @@ inline int SmithWaterman_b200(
     return score;
 }
 
+// Drop-in for SmithWaterman_111 (source.cpp:1073-1076) and SmithWaterman_8bit111simd
+// (source.cpp:1105-1107): fixed match/mismatch/gap = 1/1/1, same two arguments.
+inline int SmithWaterman_111_b200(
+    const std::array<uint8_t, 128>& seq1,
+    const std::array<uint8_t, 128>& seq2)
+{
+    swb200::Context& c = swb200::default_context();
+    int32_t score = 0;
+    c.check(swb200_score_batch_111(c.get(), seq1.data(), seq2.data(), &score, 1));
+    return score;
+}
+
 // n pairs at once: seq1s[p], seq2s[p] are the reference's std::array<uint8_t,128>, which are
 // contiguous 128-byte objects, so a vector of them is exactly the [n][128] layout of the ABI.
 inline void SmithWaterman_b200_batch(

@@ -35,6 +35,7 @@ ABI_SYMBOLS = (
     "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
+    "swb200_score_batch_111", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -121,6 +122,14 @@ def load_library():
         f.argtypes = [u64, u64, u64, vp, vp, i32]
     lib.swb200_fnv1a64_i32.restype = u64
     lib.swb200_fnv1a64_i32.argtypes = [vp, u64]
+    lib.swb200_score_batch_111.restype = i32
+    lib.swb200_score_batch_111.argtypes = [vp, vp, vp, vp, u64]
+    lib.swb200_set_host_pack_threads.restype = i32
+    lib.swb200_set_host_pack_threads.argtypes = [vp, i32]
+    lib.swb200_host_pack_stats.restype = i32
+    lib.swb200_host_pack_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
+    lib.swb200_pack2bit_host.restype = i32
+    lib.swb200_pack2bit_host.argtypes = [vp, vp, u64]
     _lib = lib
     return lib
 
@@ -213,6 +222,15 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.swb200_launch_count(self._h))
 
+    def set_host_pack_threads(self, threads_per_gpu: int):
+        """Host cores per GPU that compress byte-coded batches to 2 bits before PCIe (-1 auto, 0 off)."""
+        self._check(self._lib.swb200_set_host_pack_threads(self._h, int(threads_per_gpu)))
+
+    def host_pack_stats(self) -> dict:
+        p, r, t = C.c_uint64(), C.c_uint64(), C.c_int()
+        self._check(self._lib.swb200_host_pack_stats(self._h, C.byref(p), C.byref(r), C.byref(t)))
+        return {"packed_pairs": int(p.value), "raw_pairs": int(r.value), "pack_threads_per_gpu": int(t.value)}
+
     def set_force_general(self, on: bool):
         self._check(self._lib.swb200_set_force_general(self._h, int(on)))
 
@@ -252,6 +270,18 @@ class Context:
         else:
             rc = self._lib.swb200_score_batch_len(self._h, width, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n)
         self._check(rc)
+        return out[:n]
+
+    # -- fixed 1/1/1 scoring (SmithWaterman_111 source.cpp:1073-1103, SmithWaterman_8bit111simd 1105-1225)
+    def score_batch_111(self, seq1: np.ndarray, seq2: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(-1, SEQ_LEN)
+        b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(-1, SEQ_LEN)
+        if a.shape != b.shape:
+            raise ValueError("seq1 and seq2 must both be uint8 [n][128]")
+        n = a.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.int32)
+        self._check(self._lib.swb200_score_batch_111(self._h, a.ctypes.data, b.ctypes.data, out.ctypes.data, n))
         return out[:n]
 
     # -- many queries vs one target (SmithWaterman_8b111x32mark1, source.cpp:1227-1234)
@@ -362,6 +392,11 @@ def SmithWaterman_b200(seq1, seq2, score_matrix, gap_penalty) -> int:
     return default_context().smith_waterman(seq1, seq2, score_matrix, gap_penalty)
 
 
+def SmithWaterman_111_b200(seq1, seq2) -> int:
+    """Drop-in for SmithWaterman_111 / SmithWaterman_8bit111simd (source.cpp:1073-1076, 1105-1107)."""
+    return int(default_context().score_batch_111(np.asarray(seq1, np.uint8)[None, :], np.asarray(seq2, np.uint8)[None, :])[0])
+
+
 # ------------------------------------------------------------------ synthetic pairs
 def reference_stream(n: int, seed: int = 10000, out=None):
     """Pairs [0,n) of the reference's own test stream (source.cpp:2944-2953)."""
@@ -385,6 +420,18 @@ def counter_pairs(first: int, n: int, seed: int = 10000, packed: bool = False, o
     if rc != 0:
         raise SwbError(rc, "swb200_gen_counter_pairs")
     return a, b
+
+
+def pack2bit(codes: np.ndarray) -> np.ndarray:
+    """Byte codes [..., 4k] -> the reference's 2-bit packing [..., k] (inverse of `unpack`, source.cpp:1580-1583)."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    if c.shape[-1] % 8:
+        raise ValueError("the last dimension must be a multiple of 8 codes")
+    out = np.empty(c.shape[:-1] + (c.shape[-1] // 4,), np.uint8)
+    rc = load_library().swb200_pack2bit_host(c.ctypes.data, out.ctypes.data, c.size)
+    if rc != 0:
+        raise SwbError(rc, "swb200_pack2bit_host")
+    return out
 
 
 def fnv1a64(scores: np.ndarray) -> int:

@@ -34,6 +34,10 @@ int main()
         const int first = SmithWaterman_b200_x32(q32, bs[0], dest32);
         for (int p = 0; p < 32; ++p) bad += (dest32[p] != SmithWaterman_b200(as[p % 16], bs[0], m111, 1));
         bad += (first != dest32[0]);
+        // the fixed 1/1/1 call (source.cpp:1073-1076) against the general one with the same scoring
+        for (int it = 0; it < 16; ++it) bad += (SmithWaterman_111_b200(as[it], bs[it]) != SmithWaterman_b200(as[it], bs[it], m111, 1));
+        const int expect111[4] = {18, 20, 14, 24};   // tests/golden/golden.json, x32_1_-1_1 first16
+        for (int it = 0; it < 4; ++it) bad += (SmithWaterman_111_b200(as[it], bs[it]) != expect111[it]);
         std::printf("host mirror: %s\n", bad ? "MISMATCH" : "16/16 scores equal the reference's known answers");
         return bad ? 1 : 0;
     } catch (const std::exception& e) {

@@ -119,3 +119,21 @@ def test_params_derivation_matches_documented_domain():
     assert path(mm(127, -127), 127) == 0
     assert path(mm(10, -128), 15) == -1      # -128 is outside the reference's domain (source.cpp:492)
     assert path(mm(10, -30), -1) == -1
+
+
+def test_host_packer_is_the_inverse_of_the_reference_unpack(swb, oracle):
+    # hostpack.cpp (AVX2 and the SWAR tail) against the oracle's restatement of source.cpp:1580-1583
+    rng = np.random.default_rng(11)
+    for n_codes in (8, 24, 64, 128, 136, 128 * 257):
+        codes = rng.integers(0, 4, n_codes, dtype=np.uint8)
+        packed = swb.pack2bit(codes)
+        assert packed.shape == (n_codes // 4,)
+        # source.cpp:1580-1583: dest[i*4+j] = (src[i] >> 2j) & 3
+        assert np.array_equal(((packed[:, None] >> (2 * np.arange(4, dtype=np.uint8))[None, :]) & 3).reshape(-1), codes)
+    codes = rng.integers(0, 4, (300, 128), dtype=np.uint8)
+    assert np.array_equal(swb.pack2bit(codes), oracle.pack2bit(codes))
+    # codes above 3 are masked to two bits, never smeared into a neighbour
+    dirty = codes | rng.integers(0, 64, codes.shape, dtype=np.uint8) << 2
+    assert np.array_equal(swb.pack2bit(dirty.astype(np.uint8)), oracle.pack2bit(codes))
+    with pytest.raises(ValueError):
+        swb.pack2bit(np.zeros(12, np.uint8))

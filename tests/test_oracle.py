@@ -108,3 +108,15 @@ def test_one_vs_many_row_is_pinned_by_the_reference_x32_functions(oracle):
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "x32_first40.npz"))   # committed fixture = the same run
     assert np.array_equal(z["queries"], qs) and np.array_equal(z["targets"], ts)
     assert np.array_equal(z["scores"][7].astype(np.int32), oracle.ref_x32(3, qs[7], ts[7]))
+
+
+def test_fixed_111_functions_of_the_reference_equal_the_general_scalar(oracle, stream):
+    # SmithWaterman_111 (source.cpp:1073-1103) and SmithWaterman_8bit111simd (1105-1225)
+    # are the general recurrence with +1/-1, gap 1 -- that equality is what lets one kernel serve both.
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    a, b = stream
+    exp = oracle.score_batch(a[:300], b[:300], oracle.MATRIX_111, 1)
+    for i in range(300):
+        assert oracle.ref_111(a[i], b[i]) == exp[i]
+        assert oracle.ref_8bit111(a[i], b[i]) == exp[i]

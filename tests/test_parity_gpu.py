@@ -115,6 +115,32 @@ def test_multi_chunk_batch_with_pinned_buffers(ctx, swb, oracle):
         p.free()
 
 
+def test_host_pack_lanes_equal_plain_pipeline(ctx, swb, oracle):
+    # swb200_score_batch on a large byte-coded batch: RAW + PACK lanes (2-bit wire compression on host
+    # cores) must give the very scores of the plain chunk pipeline, with any lane count.
+    n = 20 * 16384 + 4321
+    a, b = swb.counter_pairs(9_000_000, n)
+    try:
+        ctx.set_host_pack_threads(0)
+        s0 = ctx.host_pack_stats()
+        plain = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+        s1 = ctx.host_pack_stats()
+        assert s1["packed_pairs"] == s0["packed_pairs"] and s1["raw_pairs"] == s0["raw_pairs"]   # lanes unused
+        sample = np.r_[0:2048, n - 2048:n, np.arange(0, n, 1009)]
+        assert np.array_equal(plain[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+        for t in (1, 5):
+            ctx.set_host_pack_threads(t)
+            s1 = ctx.host_pack_stats()
+            assert np.array_equal(ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15), plain), t
+            assert np.array_equal(ctx.score_batch(a, b, mm(127, -127), 127), ctx.score_batch(a[::-1].copy(), b[::-1].copy(), mm(127, -127), 127)[::-1])
+            s2 = ctx.host_pack_stats()
+            assert s2["packed_pairs"] + s2["raw_pairs"] - s1["packed_pairs"] - s1["raw_pairs"] == 3 * n
+            assert s2["packed_pairs"] > s1["packed_pairs"]          # the pack lanes did take work
+            assert s2["pack_threads_per_gpu"] == t
+    finally:
+        ctx.set_host_pack_threads(-1)
+
+
 def test_domain_properties_at_scale(ctx, swb):
     # size-independent properties on 300 000 pairs (no oracle needed)
     n = 300_000
@@ -227,7 +253,20 @@ def test_length_sweep_parity(ctx, swb, oracle, L):
             assert np.array_equal(got, exp), (L, sm[0], g, force_general)
     assert ctx.score_batch(a[:1], b[:1], swb.MATRIX_SPEEDTEST, 15)[0] == 10 * L
     info = ctx.kernel_info(swb.MATRIX_SPEEDTEST, 15, seq_len=L)
-    assert info["fast_path"] == 1 and info["threads_per_block"] * info["blocks_per_sm"] * L * 4 <= 227 * 1024
+    assert info["fast_path"] == 1
+    if info["smem_bytes_per_block"] > 4096:       # FIFO in shared memory: L words per thread must fit the SM
+        assert info["threads_per_block"] * info["blocks_per_sm"] * L * 4 <= 227 * 1024
+    else:
+        # FIFO in global memory / L2 (L = 512): a persistent grid.  Enough pairs that every resident thread
+        # walks more than one work item, checked against the oracle on both sides of the first pass.
+        resident_pairs = 2 * info["threads_per_block"] * info["blocks_per_sm"] * info["sm_count"]
+        n2 = resident_pairs + 9001
+        a2 = rng.integers(0, 4, (n2, L), dtype=np.uint8)
+        b2 = np.where(rng.random((n2, L)) < 0.9, a2, rng.integers(0, 4, (n2, L), dtype=np.uint8)).astype(np.uint8)
+        got2 = ctx.score_batch(a2, b2, swb.MATRIX_SPEEDTEST, 15)
+        sample = np.r_[0:1500, resident_pairs - 1500:resident_pairs + 1500, n2 - 1500:n2]
+        assert np.array_equal(got2[sample], oracle.score_batch(a2[sample], b2[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+        assert np.array_equal(ctx.score_batch(b2, a2, swb.MATRIX_SPEEDTEST, 15), got2)      # symmetric matrix: transpose invariance, all pairs
     if L == 512:
         with pytest.raises(swb.SwbError) as e:    # 512 * 127 overflows packed int16: refused, not wrong
             ctx.score_batch(a[:4], b[:4], mm(127, -127), 127)
@@ -239,6 +278,24 @@ def test_length_sweep_parity(ctx, swb, oracle, L):
     ctx.score_batch_device(da, db, swb.MATRIX_SPEEDTEST, 15, ds)
     torch.cuda.synchronize()
     assert np.array_equal(ds.cpu().numpy(), oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
+def test_fixed_111_entry(ctx, swb, oracle, golden):
+    # swb200_score_batch_111 stands in for SmithWaterman_111 / SmithWaterman_8bit111simd
+    n = 100_000
+    a, b = oracle.reference_stream(n)
+    s = ctx.score_batch_111(a, b)
+    gold = golden["reference_stream"]["sets"]["x32_1_-1_1"]
+    assert list(s[:16]) == gold["first16"]
+    assert int(s.sum()) == gold["100000"]["sum"] and f"{oracle.fnv1a64(s):016x}" == gold["100000"]["fnv1a64"]
+    assert np.array_equal(s, ctx.score_batch(a, b, swb.MATRIX_111, 1))
+    z = golden["structured_npz"]                       # identical / mutated / indel / homopolymer pairs
+    got = ctx.score_batch_111(z["seq1"], z["seq2"])
+    assert np.array_equal(got, oracle.score_batch(z["seq1"], z["seq2"], oracle.MATRIX_111, 1))
+    if oracle.have_ref():
+        for i in range(0, z["seq1"].shape[0], 7):
+            assert got[i] == oracle.ref_111(z["seq1"][i], z["seq2"][i]) == oracle.ref_8bit111(z["seq1"][i], z["seq2"][i])
+    assert swb.SmithWaterman_111_b200(a[0], b[0]) == gold["first16"][0]
 
 
 def test_one_vs_many_equals_reference_x32(ctx, swb, oracle):
