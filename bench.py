@@ -478,7 +478,8 @@ def run_stream_arm(args):
 # --------------------------------------------------------------------------- length sweep
 def run_sweep_arm(args):
     """BASELINE.json configs[3]: `--workload sweep` -- square pairs of 128, 256 and 512 bases on one
-    GPU, device-resident, the same number of cells per launch (2^34) at every length."""
+    GPU, device-resident, 2^34 cells per launch and never fewer than 262144 pairs (the L = 512 kernel keeps
+    75 776 pairs resident at once; a batch below a few such waves would time latency, not throughput)."""
     import torch
     import swb200
     if not torch.cuda.is_available():
@@ -489,7 +490,7 @@ def run_sweep_arm(args):
     peaks = load_peaks()
     rows = []
     for L in swb200.SWEEP_LENGTHS:
-        n = (1 << 34) // (L * L)
+        n = max((1 << 34) // (L * L), 262144)
         g = torch.Generator(device="cuda").manual_seed(1234 + L)
         d_a = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
         d_b = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
@@ -512,7 +513,7 @@ def run_sweep_arm(args):
         del d_a, d_b, d_s
     line = {"metric": "GCUPS", "unit": "GCUPS", "value": rows[0]["gcups"], "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": rows[0]["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
-            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), 2^34 cells per launch, iid pairs, matrix +10/-30, gap 15",
+            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), max(2^34 cells, 262144 pairs) per launch, iid pairs, matrix +10/-30, gap 15",
                        "roofline_peak": f"{peaks['alu_src']}, at sm_max clock"},
             "sweep": rows}
     print(json.dumps(line), flush=True)

@@ -127,7 +127,8 @@ struct SwState {
     uint32_t Z, Zp;       // fast: Z_T and Z_{T-1}
     uint32_t B;           // running best (fast: in the frame of the current step)
     uint32_t bq_lo[2], bq_hi[2];   // target bases of the next iteration's columns 0..7 (loaded 8 steps ahead)
-    uint32_t pq[8];                // Fifo::kPrefetch only: the next iteration's first 8 FIFO words (loaded 8 steps ahead)
+    uint32_t pq[16];               // Fifo::kPrefetch only: FIFO words of the next iteration, loaded ahead of use
+                                   // (kPrefetch 1: its first 8 words; kPrefetch 2: all 16)
 };
 
 // byte `idx` (0..3) of word w, times 4 (a word offset into t4[]), masked to a valid code
@@ -185,16 +186,22 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         ld8(p, bw_lo[2], bw_lo[3]);
         ld8(p + dq, bw_hi[2], bw_hi[3]);
     }
-    // A FIFO with long latency (global memory) is read 8 steps ahead of use, like the bases:
-    // words 8..15 of this iteration here, words 0..7 of the next iteration at u = 8.  Every word
-    // read was pushed at least L-15-16 steps earlier by this same thread, and the columns pushed
-    // in between (col0-15 .. col0) never coincide with the ones prefetched (L >= 64).
+    // A FIFO with long latency (global memory) is read ahead of use, like the bases.
+    //   kPrefetch 1: 8..15 steps ahead -- words 8..15 of this iteration here, words 0..7 of the next at u = 8;
+    //   kPrefetch 2: 16..31 steps ahead -- all 16 words of the next iteration here.
+    // Every word read was pushed at least L-16 steps before its use by this same thread, and the
+    // columns pushed meanwhile (col0-15 .. col0+15) never coincide with the ones prefetched (L >= 64).
     uint32_t pv[16];
-    if (Fifo::kPrefetch) {
+    if (Fifo::kPrefetch == 1) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) pv[q] = st.pq[q];
 #pragma unroll
         for (int q = 8; q < 16; ++q) pv[q] = fifo.pop((WRAP ? 0 : col0) + q);
+    }
+    if (Fifo::kPrefetch == 2) {
+        const int nc = ((WRAP ? 0 : col0) + 16) & (L - 1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { pv[q] = st.pq[q]; st.pq[q] = fifo.pop(nc + q); }
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
@@ -203,7 +210,7 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
             const uint8_t* p = b_lo + nc;
             ld8(p, st.bq_lo[0], st.bq_lo[1]);
             ld8(p + dq, st.bq_hi[0], st.bq_hi[1]);
-            if (Fifo::kPrefetch) {
+            if (Fifo::kPrefetch == 1) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) st.pq[q] = fifo.pop(nc + q);
             }
@@ -296,7 +303,7 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
     for (int c = 0; c < L; ++c) fifo.push(c, 0u);
     if (Fifo::kPrefetch) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) st.pq[q] = fifo.pop(q);
+        for (int q = 0; q < (Fifo::kPrefetch == 2 ? 16 : 8); ++q) st.pq[q] = fifo.pop(q);
     }
     st.Z = FAST ? prm.G + prm.G : 0u;         // Z_0 = g*(0+2)
     st.Zp = FAST ? prm.G : 0u;                // Z_{-1}

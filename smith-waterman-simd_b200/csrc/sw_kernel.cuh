@@ -20,7 +20,7 @@ constexpr int SW_DEFAULT_VARIANT = SW_V_BEST_FMA;   // the variant bits (sw_core
 
 template <int NT>
 struct SmemFifo {
-    static constexpr bool kPrefetch = false;   // 29-cycle LDS: read at the step of use
+    static constexpr int kPrefetch = 0;        // 29-cycle LDS: read at the step of use
     uint32_t* f;   // &fifo[0*NT + threadIdx.x]
     __device__ __forceinline__ uint32_t pop(int c) const { return f[c * NT]; }
     __device__ __forceinline__ void push(int c, uint32_t v) { f[c * NT] = v; }
@@ -32,9 +32,9 @@ struct SmemFifo {
 // 128-byte line); the working set (resident threads x L x 4 B, 58 MB at L = 256, 116 MB at
 // L = 512) lives in the 126 MB L2.  A thread only ever reads what it wrote itself, so plain
 // (coherent) loads and stores are ordered correctly without fences; .cg keeps them out of L1.
-template <int NT>
+template <int NT, int AHEAD = 1>
 struct GlobalFifo {
-    static constexpr bool kPrefetch = true;    // L2 latency: read 8 steps ahead (sw_core.cuh)
+    static constexpr int kPrefetch = AHEAD;    // L2 latency: read 8..15 (1) or 16..31 (2) steps ahead (sw_core.cuh)
     uint32_t* f;   // &slot[0*NT + threadIdx.x]
     __device__ __forceinline__ uint32_t pop(int c) const { return __ldcg(f + c * NT); }
     __device__ __forceinline__ void push(int c, uint32_t v) { __stcg(f + c * NT, v); }
@@ -86,7 +86,7 @@ sw_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
 
 // Persistent-grid variant with the FIFO in global memory: grid = resident blocks; block b owns
 // slot b of `fifo_scratch` (L*NT words) and walks the work items b, b+gridDim.x, ...
-template <bool FAST, int L, int NT, int MINB, int V = SW_DEFAULT_VARIANT>
+template <bool FAST, int L, int NT, int MINB, int V = SW_DEFAULT_VARIANT, int AHEAD = 1>
 __global__ void __launch_bounds__(NT, MINB)
 sw_kernel_gfifo(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2,
                 int32_t* __restrict__ scores, unsigned long long n, const SwParams prm, const unsigned seq2_stride,
@@ -95,7 +95,7 @@ sw_kernel_gfifo(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ se
     __shared__ uint32_t t4s[4];
     if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
     __syncthreads();
-    GlobalFifo<NT> fifo{fifo_scratch + (size_t)blockIdx.x * L * NT + threadIdx.x};
+    GlobalFifo<NT, AHEAD> fifo{fifo_scratch + (size_t)blockIdx.x * L * NT + threadIdx.x};
     SmemTable t4{t4s};
     const unsigned long long n_items = (n + 1) / 2;
     for (unsigned long long item = (unsigned long long)blockIdx.x * NT + threadIdx.x; item < n_items;

@@ -61,7 +61,7 @@ struct Slot {
 struct Lane {
     bool pack = false;
     int depth = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream[kLaneDepth] = {};   // one per buffer set: sub-chunk k+1's copy must not queue behind sub-chunk k's kernel
     cudaEvent_t done[kLaneDepth] = {};
     bool busy[kLaneDepth] = {};
     uint8_t* h_pk[kLaneDepth] = {};      // pinned [2][kSubPairs][32]   (pack lanes)
@@ -165,7 +165,7 @@ __global__ void count_bad_codes_kernel(const uint8_t* __restrict__ codes, unsign
 template <int L> struct LenCfg;
 template <> struct LenCfg<128> { static constexpr int NT = 64,  MINB = 6; static constexpr bool GFIFO = false; };
 template <> struct LenCfg<256> { static constexpr int NT = 64,  MINB = 3; static constexpr bool GFIFO = false; };
-template <> struct LenCfg<512> { static constexpr int NT = 64,  MINB = 4; static constexpr bool GFIFO = true; };
+template <> struct LenCfg<512> { static constexpr int NT = 64,  MINB = 6; static constexpr bool GFIFO = true; };   // 8080 vs 6439 GCUPS in shared memory
 
 template <bool FAST, int L>
 constexpr auto kernel_ptr()
@@ -361,9 +361,9 @@ int pack_threads_per_gpu(const swb200_ctx* ctx)
 
 int lane_alloc(swb200_ctx* ctx, Lane* ln)
 {
-    SWB_CUDA(ctx, cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
     ln->depth = ln->pack ? kPackDepth : kRawDepth;
     for (int b = 0; b < ln->depth; ++b) {
+        SWB_CUDA(ctx, cudaStreamCreateWithFlags(&ln->stream[b], cudaStreamNonBlocking));
         SWB_CUDA(ctx, cudaEventCreateWithFlags(&ln->done[b], cudaEventDisableTiming));
         SWB_CUDA(ctx, cudaMalloc(&ln->d_seq[b], 2 * kSubPairs * SWB200_SEQ_LEN));
         SWB_CUDA(ctx, cudaMalloc(&ln->d_scores[b], kSubPairs * sizeof(int32_t)));
@@ -381,8 +381,8 @@ void lane_free(Lane* ln)
         if (ln->done[b]) cudaEventDestroy(ln->done[b]);
         cudaFree(ln->d_seq[b]); cudaFree(ln->d_scores[b]); cudaFree(ln->d_pk[b]);
         if (ln->h_pk[b]) cudaFreeHost(ln->h_pk[b]);
+        if (ln->stream[b]) cudaStreamDestroy(ln->stream[b]);
     }
-    if (ln->stream) cudaStreamDestroy(ln->stream);
 }
 
 // One lane's share of a job: sub-chunks taken from the job's counter until none are left.
@@ -397,24 +397,25 @@ int lane_run(swb200_ctx* ctx, Lane* ln, LaneJob* job)
         const uint64_t c0 = job->lo + idx * kSubPairs;
         const uint64_t m = (job->hi - c0 < kSubPairs) ? job->hi - c0 : kSubPairs;
         if (ln->busy[b]) { SWB_CUDA(ctx, cudaEventSynchronize(ln->done[b])); ln->busy[b] = false; }
+        cudaStream_t st = ln->stream[b];
         uint8_t* d1 = ln->d_seq[b];
         uint8_t* d2 = ln->d_seq[b] + m * SWB200_SEQ_LEN;
         if (ln->pack) {
             pack2bit_host(job->seq1 + c0 * SWB200_SEQ_LEN, ln->h_pk[b], m * SWB200_SEQ_LEN);
             pack2bit_host(job->seq2 + c0 * SWB200_SEQ_LEN, ln->h_pk[b] + m * 32, m * SWB200_SEQ_LEN);
-            SWB_CUDA(ctx, cudaMemcpyAsync(ln->d_pk[b], ln->h_pk[b], 2 * m * 32, cudaMemcpyHostToDevice, ln->stream));
-            SWB_CUDA(ctx, launch_unpack(ln->d_pk[b], ln->d_seq[b], 2 * m, ln->stream));   // seq1 rows then seq2 rows
+            SWB_CUDA(ctx, cudaMemcpyAsync(ln->d_pk[b], ln->h_pk[b], 2 * m * 32, cudaMemcpyHostToDevice, st));
+            SWB_CUDA(ctx, launch_unpack(ln->d_pk[b], ln->d_seq[b], 2 * m, st));   // seq1 rows then seq2 rows
             ctx->launches += 1;
             job->packed_pairs += m;
         } else {
-            SWB_CUDA(ctx, cudaMemcpyAsync(d1, job->seq1 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, ln->stream));
-            SWB_CUDA(ctx, cudaMemcpyAsync(d2, job->seq2 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, ln->stream));
+            SWB_CUDA(ctx, cudaMemcpyAsync(d1, job->seq1 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, st));
+            SWB_CUDA(ctx, cudaMemcpyAsync(d2, job->seq2 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, st));
             job->raw_pairs += m;
         }
-        SWB_CUDA(ctx, launch_for(job->prm, SWB200_SEQ_LEN, d1, d2, ln->d_scores[b], m, ln->stream, false));
+        SWB_CUDA(ctx, launch_for(job->prm, SWB200_SEQ_LEN, d1, d2, ln->d_scores[b], m, st, false));
         ctx->launches += 1;
-        SWB_CUDA(ctx, cudaMemcpyAsync(job->scores + c0, ln->d_scores[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, ln->stream));
-        SWB_CUDA(ctx, cudaEventRecord(ln->done[b], ln->stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(job->scores + c0, ln->d_scores[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SWB_CUDA(ctx, cudaEventRecord(ln->done[b], st));
         ln->busy[b] = true;
         b = (b + 1) % ln->depth;
     }

@@ -15,14 +15,14 @@ static int g_prefetch = 0;  // 1: exercise the read-ahead path used by the globa
 
 template <int L>
 struct HostFifo {
-    static constexpr bool kPrefetch = false;
+    static constexpr int kPrefetch = 0;
     uint32_t w[L];
     uint32_t pop(int c) const { return w[c & (L - 1)]; }
     void push(int c, uint32_t v) { w[c & (L - 1)] = v; }
 };
-template <int L>
-struct HostFifoAhead {          // same storage, but sw_core.cuh reads it 8 steps ahead (Fifo::kPrefetch)
-    static constexpr bool kPrefetch = true;
+template <int L, int AHEAD>
+struct HostFifoAhead {          // same storage, but sw_core.cuh reads it ahead of use (Fifo::kPrefetch = 1 or 2)
+    static constexpr int kPrefetch = AHEAD;
     uint32_t w[L];
     uint32_t pop(int c) const { return w[c & (L - 1)]; }
     void push(int c, uint32_t v) { w[c & (L - 1)] = v; }
@@ -38,9 +38,16 @@ template <int L, int V>
 static void two_pairs(bool fast, const uint8_t* a, const uint8_t* b, uint32_t dqa, uint32_t dqb, HostFifo<L>& fifo, HostTable& t4,
                       const SwParams& prm, int32_t& lo, int32_t& hi)
 {
-    if (g_prefetch) {
-        HostFifoAhead<L> ahead;
+    if (g_prefetch == 1) {
+        HostFifoAhead<L, 1> ahead;
         for (int i = 0; i < L; ++i) ahead.w[i] = 0xdeadbeefu;   // anything read before it was written shows up as a wrong score
+        if (fast) sw_two_pairs<true, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
+        else      sw_two_pairs<false, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
+        return;
+    }
+    if (g_prefetch == 2) {
+        HostFifoAhead<L, 2> ahead;
+        for (int i = 0; i < L; ++i) ahead.w[i] = 0xdeadbeefu;
         if (fast) sw_two_pairs<true, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
         else      sw_two_pairs<false, L, V>(a, b, dqa, dqb, ahead, t4, prm, lo, hi);
         return;

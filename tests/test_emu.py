@@ -89,7 +89,7 @@ def _related_pairs(rng, n, L):
     return a, b
 
 
-@pytest.mark.parametrize("prefetch", [0, 1])
+@pytest.mark.parametrize("prefetch", [0, 1, 2])
 @pytest.mark.parametrize("L", [256, 512])
 def test_emu_length_sweep(emu, oracle, L, prefetch):
     # BASELINE.json configs[3]: 2x and 4x the built-in shape; oracle = source.cpp:35-60 restated for any length
@@ -114,12 +114,13 @@ def test_emu_length_sweep(emu, oracle, L, prefetch):
 def test_emu_prefetching_fifo_at_128(emu, golden):
     z = golden["structured_npz"]
     lib = C.CDLL(EMU_LIB)
-    lib.swemu_set_prefetch(1)
     try:
-        for ps in golden["structured"]["param_sets"][:6]:
-            for force_general in (0, 1):
-                _, got = emu(z["seq1"], z["seq2"], ps["matrix"], ps["gap"], force_general)
-                assert np.array_equal(got, z[ps["name"]].astype(np.int32)), ps["name"]
+        for ahead in (1, 2):
+            lib.swemu_set_prefetch(ahead)
+            for ps in golden["structured"]["param_sets"][:6]:
+                for force_general in (0, 1):
+                    _, got = emu(z["seq1"], z["seq2"], ps["matrix"], ps["gap"], force_general)
+                    assert np.array_equal(got, z[ps["name"]].astype(np.int32)), (ahead, ps["name"])
     finally:
         lib.swemu_set_prefetch(0)
 

@@ -25,7 +25,7 @@ static int n_sm;
 static uint64_t splitmix(uint64_t& s) { uint64_t z = (s += 0x9e3779b97f4a7c15ull); z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); }
 
 template <int L>
-static uint64_t n_pairs() { return (1ull << 34) / ((uint64_t)L * L); }
+static uint64_t n_pairs() { return 262144; }   // 3.5 resident waves of the 8-warp persistent grid at L = 512 (a batch below one wave measures latency, not throughput)
 
 static bool same(uint64_t n)
 {
@@ -69,11 +69,11 @@ static void run_smem(const SwParams& prm, bool is_ref)
     fflush(stdout);
 }
 
-template <bool FAST, int L, int NT, int MINB>
+template <bool FAST, int L, int NT, int MINB, int AHEAD = 1>
 static void run_gfifo(const SwParams& prm)
 {
     const uint64_t N = n_pairs<L>();
-    auto kern = sw_kernel_gfifo<FAST, L, NT, MINB>;
+    auto kern = sw_kernel_gfifo<FAST, L, NT, MINB, SW_DEFAULT_VARIANT, AHEAD>;
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, 0));
     if (occ > MINB) occ = MINB;
@@ -82,8 +82,8 @@ static void run_gfifo(const SwParams& prm)
     if (need > scratch_bytes) { printf("{\"fifo\": \"global\", \"L\": %d, \"nt\": %d, \"minb\": %d, \"skipped\": \"scratch\"}\n", L, NT, MINB); return; }
     CK(cudaMemset(dsc, 0xff, N * 4));
     const float ms = time_launches([&] { kern<<<grid, NT>>>(d1, d2, dsc, N, prm, (unsigned)L, dscratch); });
-    printf("{\"fifo\": \"global\", \"fast\": %d, \"L\": %d, \"nt\": %d, \"minb\": %d, \"regs\": %d, \"occ_blocks\": %d, \"warps_per_sm\": %d, \"scratch_mb\": %.1f, \"ms\": %.4f, \"gcups\": %.1f, \"ok\": %s}\n",
-           (int)FAST, L, NT, MINB, fa.numRegs, occ, occ * NT / 32, need / 1048576.0, ms, N * (double)L * L / (ms * 1e-3) / 1e9, same(N) ? "true" : "false");
+    printf("{\"fifo\": \"global\", \"ahead\": %d, \"fast\": %d, \"L\": %d, \"nt\": %d, \"minb\": %d, \"regs\": %d, \"occ_blocks\": %d, \"warps_per_sm\": %d, \"scratch_mb\": %.1f, \"ms\": %.4f, \"gcups\": %.1f, \"ok\": %s}\n",
+           AHEAD, (int)FAST, L, NT, MINB, fa.numRegs, occ, occ * NT / 32, need / 1048576.0, ms, N * (double)L * L / (ms * 1e-3) / 1e9, same(N) ? "true" : "false");
     fflush(stdout);
 }
 
@@ -106,12 +106,15 @@ static void fill_inputs()
     CK(cudaMemcpy(d2, b.data(), N * L, cudaMemcpyHostToDevice));
 }
 
-int main()
+static bool g_quick = false;   // `kbench_len ncu`: the L = 512 pair of kernels only, for a profiler capture
+
+int main(int argc, char** argv)
 {
+    g_quick = argc > 1;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     n_sm = prop.multiProcessorCount;
-    const uint64_t maxN = n_pairs<256>();
-    CK(cudaMalloc(&d1, maxN * 256)); CK(cudaMalloc(&d2, maxN * 256));
+    const uint64_t maxN = n_pairs<512>();
+    CK(cudaMalloc(&d1, maxN * 512)); CK(cudaMalloc(&d2, maxN * 512));
     CK(cudaMalloc(&dsc, maxN * 4)); CK(cudaMalloc(&dref, maxN * 4));
     scratch_bytes = (size_t)n_sm * 12 * 512 * 32 * 4 * 2;   // up to 24 warps/SM at L = 512
     CK(cudaMalloc(&dscratch, scratch_bytes));
@@ -121,26 +124,28 @@ int main()
         const SwParams fast = sw_make_params(sm, 15, 0, 512), gen = sw_make_params(sm, 15, 1, 512);
         fill_inputs<512>();
         run_smem<true, 512, 32, 3>(fast, true);
+        if (g_quick) { run_gfifo<true, 512, 64, 4>(fast); return 0; }
         run_gfifo<true, 512, 32, 4>(fast);
-        run_gfifo<true, 512, 32, 6>(fast);
         run_gfifo<true, 512, 64, 4>(fast);
-        run_gfifo<true, 512, 96, 3>(fast);
-        run_gfifo<true, 512, 32, 10>(fast);
+        run_gfifo<true, 512, 64, 4, 2>(fast);
+        run_gfifo<true, 512, 128, 2, 2>(fast);
         run_gfifo<true, 512, 64, 5>(fast);
-        run_gfifo<true, 512, 32, 12>(fast);
-        run_gfifo<true, 512, 128, 2>(fast);
+        run_gfifo<true, 512, 64, 5, 2>(fast);
+        run_gfifo<true, 512, 64, 6>(fast);
+        run_gfifo<true, 512, 64, 6, 2>(fast);
         run_smem<false, 512, 32, 3>(gen, false);
         run_gfifo<false, 512, 64, 4>(gen);
-        run_gfifo<false, 512, 96, 3>(gen);
+        run_gfifo<false, 512, 64, 4, 2>(gen);
+        run_gfifo<false, 512, 64, 6>(gen);
     }
     {
         const SwParams fast = sw_make_params(sm, 15, 0, 256), gen = sw_make_params(sm, 15, 1, 256);
         fill_inputs<256>();
         run_smem<true, 256, 64, 3>(fast, true);
         run_gfifo<true, 256, 64, 4>(fast);
+        run_gfifo<true, 256, 64, 4, 2>(fast);
         run_gfifo<true, 256, 64, 6>(fast);
-        run_gfifo<true, 256, 128, 3>(fast);
-        run_gfifo<false, 256, 64, 6>(gen);
+        run_gfifo<true, 256, 64, 6, 2>(fast);
     }
     return 0;
 }
