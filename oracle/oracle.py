@@ -57,6 +57,8 @@ def port():
         lib.swo_unpack2bit.argtypes = [_u8p, _u8p, C.c_uint64]
         lib.swo_pack2bit.restype = None
         lib.swo_pack2bit.argtypes = [_u8p, _u8p, C.c_uint64]
+        lib.swo_semiglobal_xdrop.restype = C.c_int
+        lib.swo_semiglobal_xdrop.argtypes = [_u8p, _u8p, C.c_int, _i32p, _i32p, _i32p, _u8p, _i32p]
         _port = lib
     return _port
 
@@ -87,6 +89,14 @@ def ref():
         lib.swref_111.argtypes = [_u8p, _u8p]
         lib.swref_8bit111.restype = C.c_int
         lib.swref_8bit111.argtypes = [_u8p, _u8p]
+        lib.swref_semiglobal.restype = C.c_int
+        lib.swref_semiglobal.argtypes = [C.c_int, _u8p, _u8p, _i32p, _i32p, C.c_int64, _i32p]
+        lib.swref_semiglobal_batch.restype = C.c_int
+        lib.swref_semiglobal_batch.argtypes = [C.c_int, _u8p, _u8p, C.c_uint64, _i32p, C.c_int]
+        lib.swref_semiglobal_test_inputs.restype = None
+        lib.swref_semiglobal_test_inputs.argtypes = [C.c_uint64, C.c_uint64, _u8p, _u8p]
+        lib.swref_semiglobal_speedtest_input.restype = None
+        lib.swref_semiglobal_speedtest_input.argtypes = [C.c_uint64, _u8p, _u8p]
         lib.swref_x32.restype = C.c_int
         lib.swref_x32.argtypes = [C.c_int, _u8p, _u8p, _i32p]
         lib.swref_hardware_threads.restype = C.c_int
@@ -202,3 +212,70 @@ MATRIX_SPEEDTEST = [10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30
 GAP_SPEEDTEST = 15                                                                           # source.cpp:3046
 MATRIX_111 = [1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1]                    # source.cpp:3202-3206
 GAP_111 = 1                                                                                  # source.cpp:3207
+
+
+# ------------------------------------------------------------------ semi-global X-drop aligner
+SG_LEN = 16384          # source.cpp:1837-1838
+SG_OPS = ("diagonal", "down", "right")
+
+
+def semiglobal_xdrop(seq1: np.ndarray, seq2: np.ndarray):
+    """oracle/sg_oracle.c on one pair of equal length.  Returns (score, end_y, end_x, ops uint8[n]) with
+    ops in forward order from (0,0): 0 = diagonal, 1 = down (y+1), 2 = right (x+1)."""
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(-1)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(-1)
+    assert a.size == b.size and a.size >= 1
+    ops = np.empty(2 * a.size, np.uint8)
+    score, ey, ex, n = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    rc = port().swo_semiglobal_xdrop(_p(a, _u8p), _p(b, _u8p), a.size, C.byref(score), C.byref(ey), C.byref(ex), _p(ops, _u8p), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"swo_semiglobal_xdrop rc={rc}")
+    return int(score.value), int(ey.value), int(ex.value), ops[:n.value].copy()
+
+
+def ops_to_traceback(ops: np.ndarray) -> np.ndarray:
+    """The reference's traceback vector ((0,0) ... best cell) as int32 [n+1][2] from the op string."""
+    ops = np.asarray(ops)
+    dy = np.cumsum((ops != 2).astype(np.int32))
+    dx = np.cumsum((ops != 1).astype(np.int32))
+    tb = np.zeros((ops.size + 1, 2), np.int32)
+    tb[1:, 0] = dy
+    tb[1:, 1] = dx
+    return tb
+
+
+def ref_semiglobal(variant: int, seq1: np.ndarray, seq2: np.ndarray):
+    """The reference's SemiGlobal_AdaptiveBanded_XDrop_111_32_70 (variant 0, source.cpp:1836-1976) or its AVX2
+    forms _simd / _simd_mark2 / _mark3 / _mark4 (variants 1-4).  Returns (score, traceback int32 [n][2])."""
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(SG_LEN)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(SG_LEN)
+    cap = 2 * SG_LEN + 2
+    tb = np.empty((cap, 2), np.int32)
+    score, n = C.c_int32(), C.c_int32()
+    rc = ref().swref_semiglobal(variant, _p(a, _u8p), _p(b, _u8p), C.byref(score), _p(tb, _i32p), cap, C.byref(n))
+    assert rc == 0
+    return int(score.value), tb[:n.value].copy()
+
+
+def ref_semiglobal_batch(variant: int, seq1: np.ndarray, seq2: np.ndarray, threads: int = 1) -> np.ndarray:
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(-1, SG_LEN)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(-1, SG_LEN)
+    out = np.empty(a.shape[0], np.int32)
+    rc = ref().swref_semiglobal_batch(variant, _p(a, _u8p), _p(b, _u8p), a.shape[0], _p(out, _i32p), threads)
+    assert rc == 0
+    return out
+
+
+def ref_semiglobal_test_inputs(n: int, seed: int = 10000):
+    """Inputs of the reference's TestSemiGlobal (source.cpp:2734-2771), generated by the reference's own code path."""
+    a = np.empty((n, SG_LEN), np.uint8)
+    b = np.empty((n, SG_LEN), np.uint8)
+    ref().swref_semiglobal_test_inputs(seed, n, _p(a, _u8p), _p(b, _u8p))
+    return a, b
+
+
+def ref_semiglobal_speedtest_input(seed: int = 10000):
+    a = np.empty(SG_LEN, np.uint8)
+    b = np.empty(SG_LEN, np.uint8)
+    ref().swref_semiglobal_speedtest_input(seed, _p(a, _u8p), _p(b, _u8p))
+    return a, b

@@ -18,6 +18,7 @@
 #include "source.cpp"
 #undef main
 
+#include <pthread.h>
 #include <thread>
 
 namespace {
@@ -148,6 +149,128 @@ int swref_x32(int mark, const uint8_t* seq1_32x128, const uint8_t* seq2, int32_t
     }
     for (int i = 0; i < 32; ++i) dest32[i] = d[i];
     return rc;
+}
+
+// ---- the adaptive-banded X-drop semi-global aligner ------------------------
+// SemiGlobal_AdaptiveBanded_XDrop_111_32_70 (source.cpp:1836-1976, scalar) and its AVX2 forms
+// _simd (1978-2165), _simd_mark2 (2167-2353), _simd_mark3 (2355-2541), _simd_mark4 (2543-2725).
+// They keep several MB of tables on the stack, so every call runs on a thread with a 64 MiB stack.
+namespace {
+using LongSeq = std::array<uint8_t, 16384>;
+using SgResult = std::pair<int, std::vector<std::pair<int, int>>>;
+typedef SgResult (*SgFn)(const LongSeq&, const LongSeq&);
+
+SgFn pick_sg(int variant)
+{
+    switch (variant) {
+    case 0: return SemiGlobal_AdaptiveBanded_XDrop_111_32_70;
+    case 1: return SemiGlobal_AdaptiveBanded_XDrop_111_32_70_simd;
+    case 2: return SemiGlobal_AdaptiveBanded_XDrop_111_32_70_simd_mark2;
+    case 3: return SemiGlobal_AdaptiveBanded_XDrop_111_32_70_simd_mark3;
+    case 4: return SemiGlobal_AdaptiveBanded_XDrop_111_32_70_simd_mark4;
+    default: return nullptr;
+    }
+}
+
+struct SgJob {
+    SgFn fn; const uint8_t* s1; const uint8_t* s2; uint64_t lo, hi;
+    int32_t* scores; int32_t* tb; int64_t tb_cap; int32_t* tb_len;   // tb: (y,x) pairs of pair `lo` only (may be null)
+};
+
+void* sg_thread(void* arg)
+{
+    SgJob* j = (SgJob*)arg;
+    LongSeq* a = new LongSeq;
+    LongSeq* b = new LongSeq;
+    for (uint64_t p = j->lo; p < j->hi; ++p) {
+        std::memcpy(a->data(), j->s1 + p * 16384, 16384);
+        std::memcpy(b->data(), j->s2 + p * 16384, 16384);
+        const SgResult r = j->fn(*a, *b);
+        j->scores[p] = r.first;
+        if (j->tb && p == j->lo) {
+            *j->tb_len = (int32_t)r.second.size();
+            for (int64_t k = 0; k < (int64_t)r.second.size() && k < j->tb_cap; ++k) {
+                j->tb[2 * k] = r.second[k].first;
+                j->tb[2 * k + 1] = r.second[k].second;
+            }
+        }
+    }
+    delete a;
+    delete b;
+    return nullptr;
+}
+
+int sg_run(std::vector<SgJob>& jobs)
+{
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 64u << 20);
+    std::vector<pthread_t> th(jobs.size());
+    int rc = 0;
+    for (size_t k = 0; k < jobs.size(); ++k) rc |= pthread_create(&th[k], &attr, sg_thread, &jobs[k]);
+    for (size_t k = 0; k < jobs.size(); ++k) pthread_join(th[k], nullptr);
+    pthread_attr_destroy(&attr);
+    return rc;
+}
+} // namespace
+
+// One pair: score and the traceback as (y,x) int pairs from (0,0) to the best cell.
+int swref_semiglobal(int variant, const uint8_t* seq1, const uint8_t* seq2, int32_t* score,
+                     int32_t* tb_yx, int64_t tb_cap, int32_t* tb_len)
+{
+    SgFn fn = pick_sg(variant);
+    if (!fn) return -1;
+    std::vector<SgJob> jobs(1);
+    jobs[0] = SgJob{fn, seq1, seq2, 0, 1, score, tb_yx, tb_cap, tb_len};
+    return sg_run(jobs);
+}
+
+// n pairs over `threads` threads (contiguous ranges), scores only: the CPU baseline of the aligner.
+int swref_semiglobal_batch(int variant, const uint8_t* seq1, const uint8_t* seq2, uint64_t n, int32_t* scores, int threads)
+{
+    SgFn fn = pick_sg(variant);
+    if (!fn || threads < 1) return -1;
+    std::vector<SgJob> jobs((size_t)threads);
+    for (int k = 0; k < threads; ++k)
+        jobs[k] = SgJob{fn, seq1, seq2, n * k / threads, n * (k + 1) / threads, scores, nullptr, 0, nullptr};
+    return sg_run(jobs);
+}
+
+// The inputs of TestSemiGlobal (source.cpp:2734-2771): iteration `it` of mt19937_64(seed) with
+// dna(0,3) / dice(0,99): a = iid, b = a with 10 % mismatch, 10 % insert, 10 % delete.  a, b: [n][16384].
+void swref_semiglobal_test_inputs(uint64_t seed, uint64_t n, uint8_t* a_out, uint8_t* b_out)
+{
+    std::mt19937_64 rnd(seed);
+    std::uniform_int_distribution<int> dna(0, 3);
+    std::uniform_int_distribution<int> dice(0, 99);
+    for (uint64_t it = 0; it < n; ++it) {
+        uint8_t* a = a_out + it * 16384;
+        uint8_t* b = b_out + it * 16384;
+        for (int i = 0; i < 16384; ++i) a[i] = (uint8_t)dna(rnd);
+        for (int i = 0, j = 0; i < 16384;) {
+            if (j == 16384) b[i++] = (uint8_t)dna(rnd);
+            else {
+                const int p = dice(rnd);
+                if (p < 10) { b[i++] = (uint8_t)dna(rnd); ++j; }
+                else if (p < 20) { b[i++] = (uint8_t)dna(rnd); }
+                else if (p < 30) { ++j; }
+                else { b[i++] = a[j++]; }
+            }
+        }
+    }
+}
+
+// The single pair of SpeedtestSemiGlobal (source.cpp:2804-2813): dice(0,19), 5 % substitutions.
+void swref_semiglobal_speedtest_input(uint64_t seed, uint8_t* a, uint8_t* b)
+{
+    std::mt19937_64 rnd(seed);
+    std::uniform_int_distribution<int> dna(0, 3);
+    std::uniform_int_distribution<int> dice(0, 19);
+    for (int i = 0; i < 16384; ++i) {
+        a[i] = (uint8_t)dna(rnd);
+        if (dice(rnd)) b[i] = a[i];
+        else b[i] = (uint8_t)dna(rnd);
+    }
 }
 
 int swref_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
