@@ -155,6 +155,28 @@ int swb200_score_batch_len_device(swb200_ctx* ctx, int device_index, int seq_len
 int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_t* d_codes,
                                  uint64_t n_bytes, uint64_t* n_bad, void* cuda_stream);
 
+/* ---- adaptive-banded X-drop semi-global aligner --------------------
+ * Replaces, for n pairs,
+ *   std::pair<int, std::vector<std::pair<int,int>>>
+ *   SemiGlobal_AdaptiveBanded_XDrop_111_32_70(const std::array<uint8_t,16384>& seq1,
+ *                                             const std::array<uint8_t,16384>& seq2)     (source.cpp:1836-1976)
+ * and its AVX2 forms _simd, _simd_mark2, _simd_mark3, _simd_mark4 (source.cpp:1978-2725), which the
+ * reference asserts equal to it (source.cpp:2774-2784).  Fixed by the reference's name: match /
+ * mismatch / gap = 1/1/1, band 32, X-drop 70; the alignment starts at (0,0) and ends at the best cell.
+ * seq1, seq2: [n][seq_len] codes 0..3 (the reference's shape is seq_len = 16384; 1..32768 accepted).
+ * Per pair: scores = the pair's .first; (end_y, end_x) = the last element of its traceback vector;
+ * ops[p][0..n_ops[p]) = the traceback as moves in forward order from (0,0): 0 = diagonal (y+1,x+1),
+ * 1 = down (y+1), 2 = right (x+1) -- the vector itself is the running sum of the moves, (0,0) first
+ * (host/smith_waterman_b200.hpp rebuilds it).  ops is [n][2*seq_len]; ops and n_ops may both be NULL
+ * (score and end cell only; the traceback is then skipped on the device as well). */
+int swb200_semiglobal_xdrop_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t seq_len, uint64_t n,
+                                  int32_t* scores, int32_t* end_y, int32_t* end_x, int32_t* n_ops, uint8_t* ops);
+/* The kernel launch alone on DEVICE arrays (same meaning), stream-ordered on `cuda_stream`.  Launches
+ * of one device share its trace scratch: issue them on one stream, or order them yourself. */
+int swb200_semiglobal_xdrop_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2,
+                                         int32_t seq_len, uint64_t n, int32_t* d_scores, int32_t* d_end_y, int32_t* d_end_x,
+                                         int32_t* d_n_ops, uint8_t* d_ops, void* cuda_stream);
+
 /* ---- introspection for the benchmark harness --------------------------------------- */
 
 typedef struct swb200_kernel_info {
@@ -189,6 +211,9 @@ int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64
 /* The packer itself (inverse of the reference's `unpack`, source.cpp:1580-1583), for callers
  * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);
+
+/* Resources of the semi-global aligner's kernel (fast_path is 0 there). */
+int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kernel_info* info);
 
 /* Kernel launches issued by this context since creation (all GPUs). */
 uint64_t swb200_launch_count(const swb200_ctx* ctx);

@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include "sg_kernel.cuh"
 #include "sw_kernel.cuh"
 #include "sw_params.h"
 
@@ -88,6 +89,15 @@ struct Device {
     Slot slots[kSlots];
     std::mutex mu;                   // one host batch at a time per GPU
     unsigned long long* d_bad = nullptr;
+    // semi-global aligner: per-resident-warp trace slots, and two staging slots for host batches
+    uint8_t* d_sg_scratch = nullptr;
+    size_t sg_scratch_bytes = 0;
+    struct SgSlot {
+        cudaStream_t stream = nullptr;
+        uint8_t *d_seq1 = nullptr, *d_seq2 = nullptr, *d_ops = nullptr;
+        int32_t* d_meta = nullptr;       // [4][cap]: score, end_y, end_x, n_ops
+        size_t cap_pairs = 0; int len = 0; bool with_ops = false;
+    } sg_slots[2];
     // lane pool (created on first use)
     std::vector<Lane*> lanes;
     std::mutex pool_mu;
@@ -473,6 +483,11 @@ int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
         const int rc = lane_alloc(ctx, ln);
         if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
             stop_lanes(d);
+        cudaFree(d->d_sg_scratch);
+        for (auto& g : d->sg_slots) {
+            if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
+            cudaFree(g.d_seq1); cudaFree(g.d_seq2); cudaFree(g.d_ops); cudaFree(g.d_meta);
+        }
             d->pool_stop = false;
             return rc;
         }
@@ -508,6 +523,114 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
     ctx->packed_pairs += job.packed_pairs.load();
     ctx->raw_pairs += job.raw_pairs.load();
     return job.rc.load();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Semi-global X-drop aligner (sg_kernel.cuh)
+constexpr int kSgBlocksPerSm = 8;                 // 32 warps = 32 pairs in flight per SM
+constexpr int kSgMaxLen = 1 << 15;                // scores stay far inside int32; scratch = 16.3 bytes per base per resident warp
+
+int sg_grid(const Device* d, uint64_t n)
+{
+    const uint64_t resident = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
+    const uint64_t need = (n + SG_WARPS_PER_BLOCK - 1) / SG_WARPS_PER_BLOCK;
+    return (int)(need < resident ? need : resident);
+}
+
+int sg_ensure_scratch(swb200_ctx* ctx, Device* d, int len)
+{
+    const size_t need = (size_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK * sg_slot_bytes(len);
+    if (need <= d->sg_scratch_bytes) return SWB200_OK;
+    SWB_CUDA(ctx, cudaDeviceSynchronize());
+    cudaFree(d->d_sg_scratch);
+    d->d_sg_scratch = nullptr; d->sg_scratch_bytes = 0;
+    SWB_CUDA(ctx, cudaMalloc(&d->d_sg_scratch, need));
+    d->sg_scratch_bytes = need;
+    return SWB200_OK;
+}
+
+// The launch alone, on device arrays.  Launches on `st` share the device's scratch, so they must be
+// stream-ordered with each other (the host batch below uses one compute order per device).
+int sg_launch(swb200_ctx* ctx, Device* d, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
+              int32_t* d_score, int32_t* d_ey, int32_t* d_ex, int32_t* d_nops, uint8_t* d_ops, cudaStream_t st)
+{
+    if (n == 0) return SWB200_OK;
+    SgOut out{d_score, d_ey, d_ex, d_nops, d_ops};
+    sg_xdrop_kernel<<<sg_grid(d, n), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1, d2, len, n, d->d_sg_scratch, out);
+    SWB_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return SWB200_OK;
+}
+
+int sg_check(swb200_ctx* ctx, const void* a, const void* b, int len, uint64_t n, const void* score, const void* ey, const void* ex,
+             const void* nops, const void* ops)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    if (len < 1 || len > kSgMaxLen) return fail(ctx, SWB200_ERR_ARG, "seq_len must be in [1, 32768]");
+    if (n && (!a || !b || !score || !ey || !ex)) return fail(ctx, SWB200_ERR_ARG, "NULL array with n > 0");
+    if (n && ((ops == nullptr) != (nops == nullptr))) return fail(ctx, SWB200_ERR_ARG, "ops and n_ops must both be given or both be NULL");
+    return SWB200_OK;
+}
+
+int sg_ensure_slot(swb200_ctx* ctx, Device::SgSlot& s, size_t cap, int len, bool with_ops)
+{
+    if (!s.stream) SWB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (s.cap_pairs >= cap && s.len >= len && (s.with_ops || !with_ops)) return SWB200_OK;
+    SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_seq1); cudaFree(s.d_seq2); cudaFree(s.d_ops); cudaFree(s.d_meta);
+    s.d_seq1 = s.d_seq2 = s.d_ops = nullptr; s.d_meta = nullptr; s.cap_pairs = 0;
+    SWB_CUDA(ctx, cudaMalloc(&s.d_seq1, cap * (size_t)len));
+    SWB_CUDA(ctx, cudaMalloc(&s.d_seq2, cap * (size_t)len));
+    SWB_CUDA(ctx, cudaMalloc(&s.d_meta, 4 * cap * sizeof(int32_t)));
+    if (with_ops) SWB_CUDA(ctx, cudaMalloc(&s.d_ops, cap * 2 * (size_t)len));
+    s.cap_pairs = cap; s.len = len; s.with_ops = with_ops;
+    return SWB200_OK;
+}
+
+// One GPU's share [lo, hi) of a host batch: chunks alternate between two slots; the kernels of
+// both slots are ordered by an event chain (they share the trace scratch), the copies overlap them.
+int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, int len, uint64_t lo, uint64_t hi,
+                 int32_t* score, int32_t* ey, int32_t* ex, int32_t* nops, uint8_t* ops)
+{
+    if (hi <= lo) return SWB200_OK;
+    std::lock_guard<std::mutex> lock(d->mu);
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    int rc = sg_ensure_scratch(ctx, d, len);
+    if (rc != SWB200_OK) return rc;
+    // chunk: about 64 MiB of sequence per array, at least one resident wave of pairs
+    uint64_t chunk = (64ull << 20) / (uint64_t)len;
+    const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK;
+    if (chunk < wave) chunk = wave;
+    if (chunk > hi - lo) chunk = hi - lo;
+    for (auto& s : d->sg_slots) { rc = sg_ensure_slot(ctx, s, chunk, len, ops != nullptr); if (rc != SWB200_OK) return rc; }
+    cudaEvent_t kdone[2] = {nullptr, nullptr};
+    for (auto& e : kdone) SWB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    int si = 0;
+    bool first = true;
+    for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si ^= 1) {
+        Device::SgSlot& s = d->sg_slots[si];
+        const uint64_t m = (hi - c0 < chunk) ? hi - c0 : chunk;
+        SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));                       // this slot's previous chunk is fully back on the host
+        SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq1, seq1 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq2, seq2 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
+        if (!first) SWB_CUDA(ctx, cudaStreamWaitEvent(s.stream, kdone[si ^ 1], 0));   // the other slot's kernel owns the scratch until then
+        int32_t* meta = s.d_meta;
+        rc = sg_launch(ctx, d, s.d_seq1, s.d_seq2, len, m, meta, meta + s.cap_pairs, meta + 2 * s.cap_pairs,
+                       ops ? meta + 3 * s.cap_pairs : nullptr, ops ? s.d_ops : nullptr, s.stream);
+        if (rc != SWB200_OK) return rc;
+        SWB_CUDA(ctx, cudaEventRecord(kdone[si], s.stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(score + c0, meta, m * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(ey + c0, meta + s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
+        SWB_CUDA(ctx, cudaMemcpyAsync(ex + c0, meta + 2 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
+        if (ops) {
+            SWB_CUDA(ctx, cudaMemcpyAsync(nops + c0, meta + 3 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
+            SWB_CUDA(ctx, cudaMemcpyAsync(ops + c0 * 2ull * (uint64_t)len, s.d_ops, m * 2ull * (uint64_t)len, cudaMemcpyDeviceToHost, s.stream));
+        }
+        first = false;
+    }
+    for (auto& s : d->sg_slots) SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+    for (auto& e : kdone) cudaEventDestroy(e);
+    return SWB200_OK;
 }
 
 int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, int gap, const void* out, uint64_t n)
@@ -847,6 +970,61 @@ int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const
 int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, int8_t gap, swb200_kernel_info* info)
 {
     return swb200_kernel_info_len(ctx, device_index, SWB200_SEQ_LEN, sm, gap, info);
+}
+
+int swb200_semiglobal_xdrop_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t seq_len, uint64_t n,
+                                  int32_t* scores, int32_t* end_y, int32_t* end_x, int32_t* n_ops, uint8_t* ops)
+{
+    int rc = sg_check(ctx, seq1, seq2, seq_len, n, scores, end_y, end_x, n_ops, ops);
+    if (rc != SWB200_OK || n == 0) return rc;
+    const size_t G = ctx->devs.size();
+    if (G == 1 || n < 2 * G) return sg_run_range(ctx, ctx->devs[0], seq1, seq2, seq_len, 0, n, scores, end_y, end_x, n_ops, ops);
+    std::vector<std::thread> pool;
+    std::vector<int> rcs(G, SWB200_OK);
+    for (size_t k = 0; k < G; ++k) {
+        const uint64_t lo = n * k / G, hi = n * (k + 1) / G;       // contiguous index ranges, as for the scoring batch
+        pool.emplace_back([=, &rcs] { rcs[k] = sg_run_range(ctx, ctx->devs[k], seq1, seq2, seq_len, lo, hi, scores, end_y, end_x, n_ops, ops); });
+    }
+    for (auto& t : pool) t.join();
+    for (int r : rcs) if (r != SWB200_OK) return r;
+    return SWB200_OK;
+}
+
+int swb200_semiglobal_xdrop_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2, int32_t seq_len,
+                                         uint64_t n, int32_t* d_scores, int32_t* d_end_y, int32_t* d_end_x, int32_t* d_n_ops, uint8_t* d_ops,
+                                         void* cuda_stream)
+{
+    int rc = sg_check(ctx, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops);
+    if (rc != SWB200_OK || n == 0) return rc;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    Device* d = ctx->devs[device_index];
+    std::lock_guard<std::mutex> lock(d->mu);
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    rc = sg_ensure_scratch(ctx, d, seq_len);
+    if (rc != SWB200_OK) return rc;
+    return sg_launch(ctx, d, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops, (cudaStream_t)cuda_stream);
+}
+
+int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kernel_info* info)
+{
+    if (!ctx || !info) return SWB200_ERR_ARG;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    Device* d = ctx->devs[device_index];
+    SWB_CUDA(ctx, cudaSetDevice(d->id));
+    cudaFuncAttributes fa{};
+    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg_xdrop_kernel));
+    int blocks = 0;
+    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg_xdrop_kernel, SG_WARPS_PER_BLOCK * 32, 0));
+    info->fast_path = 0;
+    info->regs_per_thread = fa.numRegs;
+    info->threads_per_block = SG_WARPS_PER_BLOCK * 32;
+    info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
+    info->smem_bytes_per_block = (int)fa.sharedSizeBytes;
+    info->sm_count = d->prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->id);
+    info->sm_clock_khz = khz;
+    return SWB200_OK;
 }
 
 uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }

@@ -116,3 +116,27 @@ inline int SmithWaterman_b200_x32(
                                      reinterpret_cast<int32_t*>(dest.data()), 32));
     return dest[0];
 }
+
+// Drop-in for SemiGlobal_AdaptiveBanded_XDrop_111_32_70 and its AVX2 forms (source.cpp:1836-1838,
+// 1978, 2167, 2355, 2543): same arguments, same pair<score, traceback> -- the traceback runs from
+// (0,0) to the best cell, one (y, x) per step, rebuilt here from the library's move string.
+#include <utility>
+inline std::pair<int, std::vector<std::pair<int, int>>> SemiGlobal_AdaptiveBanded_XDrop_111_32_70_b200(
+    const std::array<uint8_t, 16384>& seq1,
+    const std::array<uint8_t, 16384>& seq2)
+{
+    swb200::Context& c = swb200::default_context();
+    int32_t score = 0, end_y = 0, end_x = 0, n_ops = 0;
+    std::vector<uint8_t> ops(2 * 16384);
+    c.check(swb200_semiglobal_xdrop_batch(c.get(), seq1.data(), seq2.data(), 16384, 1, &score, &end_y, &end_x, &n_ops, ops.data()));
+    std::vector<std::pair<int, int>> traceback;
+    traceback.reserve((size_t)n_ops + 1);
+    int y = 0, x = 0;
+    traceback.emplace_back(y, x);
+    for (int k = 0; k < n_ops; ++k) {
+        if (ops[k] != 2) ++y;
+        if (ops[k] != 1) ++x;
+        traceback.emplace_back(y, x);
+    }
+    return std::make_pair((int)score, std::move(traceback));
+}

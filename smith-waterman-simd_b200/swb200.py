@@ -35,7 +35,8 @@ ABI_SYMBOLS = (
     "swb200_kernel_info_for", "swb200_launch_count", "swb200_set_force_general",
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
-    "swb200_score_batch_111", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
+    "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
+    "swb200_semiglobal_kernel_info", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -124,6 +125,12 @@ def load_library():
     lib.swb200_fnv1a64_i32.argtypes = [vp, u64]
     lib.swb200_score_batch_111.restype = i32
     lib.swb200_score_batch_111.argtypes = [vp, vp, vp, vp, u64]
+    lib.swb200_semiglobal_xdrop_batch.restype = i32
+    lib.swb200_semiglobal_xdrop_batch.argtypes = [vp, vp, vp, i32, u64, vp, vp, vp, vp, vp]
+    lib.swb200_semiglobal_xdrop_batch_device.restype = i32
+    lib.swb200_semiglobal_xdrop_batch_device.argtypes = [vp, i32, vp, vp, i32, u64, vp, vp, vp, vp, vp, vp]
+    lib.swb200_semiglobal_kernel_info.restype = i32
+    lib.swb200_semiglobal_kernel_info.argtypes = [vp, i32, C.POINTER(KernelInfo)]
     lib.swb200_set_host_pack_threads.restype = i32
     lib.swb200_set_host_pack_threads.argtypes = [vp, i32]
     lib.swb200_host_pack_stats.restype = i32
@@ -298,6 +305,40 @@ class Context:
         self._check(self._lib.swb200_score_one_vs_many(self._h, a.ctypes.data, b.ctypes.data, m.ctypes.data, _gap(gap_penalty), out.ctypes.data, n))
         return out[:n]
 
+    # -- adaptive-banded X-drop semi-global aligner (SemiGlobal_AdaptiveBanded_XDrop_111_32_70, source.cpp:1836-1976)
+    def semiglobal_xdrop(self, seq1: np.ndarray, seq2: np.ndarray, traceback: bool = True) -> dict:
+        """seq1, seq2: uint8 [n][len].  Returns score/end_y/end_x int32 [n] and, with traceback, n_ops [n] and
+        ops uint8 [n][2*len] (0 = diagonal, 1 = down, 2 = right, forward order from (0,0))."""
+        a = np.ascontiguousarray(seq1, dtype=np.uint8)
+        b = np.ascontiguousarray(seq2, dtype=np.uint8)
+        if a.ndim != 2 or a.shape != b.shape:
+            raise ValueError("seq1 and seq2 must both be uint8 [n][len]")
+        n, length = a.shape
+        out = {k: np.empty(n, np.int32) for k in ("score", "end_y", "end_x")}
+        n_ops = np.empty(n, np.int32) if traceback else None
+        ops = np.empty((n, 2 * length), np.uint8) if traceback else None
+        self._check(self._lib.swb200_semiglobal_xdrop_batch(
+            self._h, a.ctypes.data, b.ctypes.data, length, n, out["score"].ctypes.data, out["end_y"].ctypes.data, out["end_x"].ctypes.data,
+            n_ops.ctypes.data if traceback else None, ops.ctypes.data if traceback else None))
+        if traceback:
+            out["n_ops"], out["ops"] = n_ops, ops
+        return out
+
+    def semiglobal_xdrop_device(self, d_seq1, d_seq2, d_score, d_end_y, d_end_x, d_n_ops=None, d_ops=None,
+                                device_index: int = 0, stream: Optional[int] = None):
+        import torch
+        n, length = d_seq1.shape
+        if stream is None:
+            stream = torch.cuda.current_stream(d_seq1.device).cuda_stream
+        self._check(self._lib.swb200_semiglobal_xdrop_batch_device(
+            self._h, device_index, d_seq1.data_ptr(), d_seq2.data_ptr(), length, n, d_score.data_ptr(), d_end_y.data_ptr(), d_end_x.data_ptr(),
+            d_n_ops.data_ptr() if d_n_ops is not None else None, d_ops.data_ptr() if d_ops is not None else None, stream))
+
+    def semiglobal_kernel_info(self, device_index: int = 0) -> dict:
+        info = KernelInfo()
+        self._check(self._lib.swb200_semiglobal_kernel_info(self._h, device_index, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in KernelInfo._fields_}
+
     def submit(self, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap_penalty, out: np.ndarray, packed: bool = False) -> int:
         """Asynchronous batch: returns a ticket; the arrays must stay alive and untouched until wait(ticket)."""
         assert seq1.flags.c_contiguous and seq2.flags.c_contiguous and out.flags.c_contiguous
@@ -390,6 +431,16 @@ def default_context() -> Context:
 def SmithWaterman_b200(seq1, seq2, score_matrix, gap_penalty) -> int:
     """Drop-in for the reference's per-pair call (same argument order and meaning)."""
     return default_context().smith_waterman(seq1, seq2, score_matrix, gap_penalty)
+
+
+def SemiGlobal_AdaptiveBanded_XDrop_111_32_70_b200(seq1, seq2):
+    """Drop-in for the reference's aligner (source.cpp:1836-1838): returns (score, [(y, x), ...]) with the
+    traceback from (0,0) to the best cell, exactly the reference's pair<int, vector<pair<int,int>>>."""
+    r = default_context().semiglobal_xdrop(np.asarray(seq1, np.uint8)[None, :], np.asarray(seq2, np.uint8)[None, :])
+    ops = r["ops"][0, :r["n_ops"][0]]
+    ys = np.concatenate([[0], np.cumsum(ops != 2)])
+    xs = np.concatenate([[0], np.cumsum(ops != 1)])
+    return int(r["score"][0]), list(zip(ys.tolist(), xs.tolist()))
 
 
 def SmithWaterman_111_b200(seq1, seq2) -> int:

@@ -1,0 +1,154 @@
+"""GPU parity of the adaptive-banded X-drop semi-global aligner (csrc/sg_kernel.cuh) through the C ABI:
+against the fixtures generated from the reference (scalar + its four AVX2 forms), against the oracle on
+seeded inputs at many lengths, and -- at sizes the oracle does not cover in seconds -- through properties."""
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from sg_common import fnv1a64_bytes, load_cases, ops_to_traceback
+
+pytestmark = pytest.mark.gpu
+NCPU = min(os.cpu_count() or 1, 16)
+
+
+def related_pairs(rng, n, length, sub=0.1, ins=0.1, dele=0.1):
+    """TestSemiGlobal-style inputs (source.cpp:2750-2771) at any length, from numpy's generator."""
+    a = rng.integers(0, 4, (n, length), dtype=np.uint8)
+    b = np.empty_like(a)
+    for i in range(n):
+        p = rng.random(3 * length)
+        out, j, k = [], 0, 0
+        while len(out) < length:
+            if j >= length:
+                out.append(rng.integers(0, 4))
+                continue
+            q = p[k]; k += 1
+            if q < sub: out.append(rng.integers(0, 4)); j += 1
+            elif q < sub + ins: out.append(rng.integers(0, 4))
+            elif q < sub + ins + dele: j += 1
+            else: out.append(a[i, j]); j += 1
+        b[i] = out
+    return a, b
+
+
+def oracle_batch(oracle, a, b):
+    with ThreadPoolExecutor(NCPU) as ex:
+        return list(ex.map(lambda i: oracle.semiglobal_xdrop(a[i], b[i]), range(a.shape[0])))
+
+
+def check_against_oracle(oracle, got, a, b, idx=None):
+    idx = range(a.shape[0]) if idx is None else idx
+    exp = oracle_batch(oracle, a[list(idx)], b[list(idx)])
+    for (score, ey, ex, ops), i in zip(exp, idx):
+        assert (got["score"][i], got["end_y"][i], got["end_x"][i]) == (score, ey, ex), i
+        if "ops" in got:
+            assert got["n_ops"][i] == ops.size, i
+            assert np.array_equal(got["ops"][i, :ops.size], ops), i
+
+
+def test_golden_cases_from_the_reference(ctx):
+    cases = load_cases()
+    a = np.stack([c["seq1"] for c in cases])
+    b = np.stack([c["seq2"] for c in cases])
+    launches0 = ctx.launch_count
+    r = ctx.semiglobal_xdrop(a, b)
+    assert ctx.launch_count == launches0 + 1                    # the sm_100a kernel ran, once, for the whole batch
+    for i, c in enumerate(cases):
+        assert (r["score"][i], r["end_y"][i], r["end_x"][i], r["n_ops"][i]) == (c["score"], c["end_y"], c["end_x"], c["n_ops"]), c["name"]
+        ops = r["ops"][i, :r["n_ops"][i]]
+        assert np.array_equal(ops, c["ops"]), c["name"]
+        assert f"{fnv1a64_bytes(ops_to_traceback(ops).tobytes()):016x}" == c["traceback_fnv1a64"], c["name"]
+    # score-only mode skips the traceback and agrees
+    s = ctx.semiglobal_xdrop(a, b, traceback=False)
+    assert "ops" not in s and all(np.array_equal(s[k], r[k]) for k in ("score", "end_y", "end_x"))
+
+
+def test_reference_build_beside_it(ctx, oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref did not travel")
+    a, b = oracle.ref_semiglobal_test_inputs(40, seed=4242)
+    r = ctx.semiglobal_xdrop(a, b)
+    for i in range(40):
+        score, tb = oracle.ref_semiglobal(4 if i % 2 else 0, a[i], b[i])     # scalar and _simd_mark4 alternately
+        assert r["score"][i] == score
+        assert np.array_equal(ops_to_traceback(r["ops"][i, :r["n_ops"][i]]), tb), i
+
+
+@pytest.mark.parametrize("length", [1, 2, 3, 31, 32, 33, 64, 100, 1000, 4097])
+def test_lengths_against_oracle(ctx, oracle, length):
+    rng = np.random.default_rng(100 + length)
+    n = 64
+    a, b = related_pairs(rng, n, length)
+    a[0] = b[0]                                   # identical
+    a[1] = 0; b[1] = 1                            # nothing matches
+    a[2] = 2; b[2] = 2                            # homopolymer: all ties
+    b[3] = rng.integers(0, 4, length)             # unrelated
+    r = ctx.semiglobal_xdrop(a, b)
+    check_against_oracle(oracle, r, a, b)
+    assert r["score"][0] == length and r["score"][1] == 0 and r["n_ops"][1] == 0
+
+
+def test_more_pairs_than_resident_warps(ctx, oracle):
+    # the grid is persistent (SMs x 8 blocks x 4 warps): every warp walks several pairs and reuses its trace slot
+    info = ctx.semiglobal_kernel_info()
+    resident = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
+    n = 2 * resident + 777
+    rng = np.random.default_rng(9)
+    length = 384
+    a = rng.integers(0, 4, (n, length), dtype=np.uint8)
+    b = np.where(rng.random((n, length)) < 0.85, a, rng.integers(0, 4, (n, length), dtype=np.uint8)).astype(np.uint8)
+    b[::7] = np.roll(a[::7], 5, axis=1)           # shifted copies: the band has to wander
+    r = ctx.semiglobal_xdrop(a, b)
+    idx = np.r_[0:300, resident - 150:resident + 150, n - 300:n]
+    check_against_oracle(oracle, r, a, b, idx.tolist())
+    # properties on all pairs: a path from (0,0) to the end cell whose moves re-score to the reported score
+    ops, n_ops = r["ops"], r["n_ops"]
+    valid = np.arange(ops.shape[1])[None, :] < n_ops[:, None]
+    assert np.array_equal(((ops != 2) & valid).sum(1), r["end_y"]) and np.array_equal(((ops != 1) & valid).sum(1), r["end_x"])
+    for i in range(0, n, 97):
+        o = ops[i, :n_ops[i]]
+        y = np.cumsum(o != 2); x = np.cumsum(o != 1)
+        d = o == 0
+        sc = np.where(a[i, y[d] - 1] == b[i, x[d] - 1], 1, -1).sum() - int((~d).sum())
+        assert sc == r["score"][i], i
+
+
+def test_reference_shape_batch_spans_chunks(ctx, oracle):
+    # len = 16384: more pairs than one staging chunk holds (two slots, kernels chained on the shared scratch)
+    info = ctx.semiglobal_kernel_info()
+    wave = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
+    n = wave + 211
+    rng = np.random.default_rng(77)
+    a = rng.integers(0, 4, (n, 16384), dtype=np.uint8)
+    b = np.where(rng.random((n, 16384)) < 0.9, a, rng.integers(0, 4, (n, 16384), dtype=np.uint8)).astype(np.uint8)
+    for i in range(0, n, 5):
+        k = int(rng.integers(1, 30))
+        b[i] = np.concatenate([a[i, k:], rng.integers(0, 4, k, dtype=np.uint8)])      # a deletion of k bases up front
+    r = ctx.semiglobal_xdrop(a, b)
+    idx = np.r_[0:40, wave - 20:wave + 20, n - 40:n].tolist()
+    check_against_oracle(oracle, r, a, b, idx)
+    s = ctx.semiglobal_xdrop(a, b, traceback=False)
+    assert np.array_equal(s["score"], r["score"]) and np.array_equal(s["end_y"], r["end_y"])
+    assert r["score"].min() > 8000                 # 90 % identity over 16384 bases
+
+
+def test_device_resident_entry_and_errors(ctx, swb, oracle):
+    import torch
+    cases = load_cases()[:5]
+    a = torch.from_numpy(np.stack([c["seq1"] for c in cases])).cuda()
+    b = torch.from_numpy(np.stack([c["seq2"] for c in cases])).cuda()
+    n = len(cases)
+    sc, ey, ex, no = (torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(4))
+    ops = torch.empty((n, 2 * 16384), dtype=torch.uint8, device="cuda")
+    ctx.semiglobal_xdrop_device(a, b, sc, ey, ex, no, ops)
+    torch.cuda.synchronize()
+    for i, c in enumerate(cases):
+        assert (int(sc[i]), int(ey[i]), int(ex[i]), int(no[i])) == (c["score"], c["end_y"], c["end_x"], c["n_ops"])
+        assert np.array_equal(ops[i, :c["n_ops"]].cpu().numpy(), c["ops"])
+    with pytest.raises(swb.SwbError) as e:
+        ctx.semiglobal_xdrop(np.zeros((2, 40000), np.uint8), np.zeros((2, 40000), np.uint8))
+    assert e.value.code == swb.ERR_ARG
+    score, tb = swb.SemiGlobal_AdaptiveBanded_XDrop_111_32_70_b200(cases[0]["seq1"], cases[0]["seq2"])
+    assert score == cases[0]["score"] and np.array_equal(np.array(tb, np.int32), ops_to_traceback(cases[0]["ops"]))
