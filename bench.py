@@ -475,6 +475,157 @@ def run_stream_arm(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- semi-global X-drop aligner
+SG_LEN = 16384
+SG_ROUNDS_NOMINAL = 2 * SG_LEN       # a pair aligned end to end runs one round per anti-diagonal
+SG_TRACE_BYTES_PER_ROUND = 8.125     # 2 x 32-bit masks + 1 move bit, written once and read once by the traceback
+
+
+def sg_cpu_reference(a, b, budget_s=20.0):
+    """The reference's aligner on all host threads (the fastest of its four AVX2 forms on this box)."""
+    from oracle import oracle as O   # allowed: cpu_baseline / --impl reference legs only
+    cores = os.cpu_count() or 1
+    if not O.have_ref():
+        return None
+    names = {1: "_simd (source.cpp:1978-2165)", 2: "_simd_mark2 (2167-2353)", 3: "_simd_mark3 (2355-2541)", 4: "_simd_mark4 (2543-2725)"}
+    probe = min(a.shape[0], 32 * cores)
+    best = None
+    for v in (1, 2, 3, 4):
+        O.ref_semiglobal_batch(v, a[:cores], b[:cores], threads=cores)
+        t = time.perf_counter(); O.ref_semiglobal_batch(v, a[:probe], b[:probe], threads=cores); dt = time.perf_counter() - t
+        if best is None or dt < best[0]:
+            best = (dt, v)
+    dt, v = best
+    m = int(min(a.shape[0], max(probe, probe * budget_s / 3 / dt)))
+    times = []
+    for _ in range(3):
+        t = time.perf_counter(); sc = O.ref_semiglobal_batch(v, a[:m], b[:m], threads=cores); times.append(time.perf_counter() - t)
+    return {"variant": "SemiGlobal_AdaptiveBanded_XDrop_111_32_70" + names[v] + ", unmodified, g++ -O3 -mavx2 (fastest of the four AVX2 forms here)",
+            "cores": cores, "sample_pairs": m, "s_per_pass": min(times), "alignments_per_s": m / min(times), "scores": sc}
+
+
+def run_semiglobal_arm(args):
+    """`--workload semiglobal`: n pairs of 16384-mers related as in the reference's TestSemiGlobal (10 % mismatch /
+    insert / delete, source.cpp:2750-2771) through the adaptive-banded X-drop aligner, score + traceback.
+    value = alignments/s device-resident; e2e = swb200_semiglobal_xdrop_batch with pinned host arrays."""
+    import swb200
+    n = args.pairs if args.pairs != 100_000_000 else 8192
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        a, b = swb200.related_pairs(0, min(n, 4096), SG_LEN)
+        r = sg_cpu_reference(a, b, budget_s=30.0)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libswref.so not built"}))
+            return
+        v = r["alignments_per_s"]
+        print(json.dumps({"impl": "reference", "metric": "alignments_per_s", "value": v, "unit": "alignments/s", "n_gpus": args.gpus, "steps": 3, "warmup": 1,
+                          "ms_per_step": r["s_per_pass"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "semi-global X-drop aligner, 16384-mer pairs, TestSemiGlobal-style 10/10/10 % edits", "pairs_per_step": r["sample_pairs"], "cpu_model": cpu_model()},
+                          "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": r["cores"], "kind": "reference", "variant": r["variant"], "sample": f"{r['sample_pairs']} pairs per pass, best of 3"},
+                          "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- no CPU fallback")
+    torch.cuda.set_device(0)
+    ctx = swb200.Context(devices=[0])
+    info = ctx.semiglobal_kernel_info()
+    pa, pb = swb200.PinnedArray((n, SG_LEN), np.uint8), swb200.PinnedArray((n, SG_LEN), np.uint8)
+    swb200.related_pairs(0, n, SG_LEN, out=(pa.array, pb.array))
+    h_meta = [swb200.PinnedArray((n,), np.int32) for _ in range(4)]
+    h_ops = swb200.PinnedArray((n, 2 * SG_LEN), np.uint8)
+    d_a, d_b = torch.from_numpy(pa.array).cuda(), torch.from_numpy(pb.array).cuda()
+    d_meta = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(4)]
+    d_ops = torch.empty((n, 2 * SG_LEN), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def launch():
+        ctx.semiglobal_xdrop_device(d_a, d_b, d_meta[0], d_meta[1], d_meta[2], d_meta[3], d_ops)
+    for _ in range(max(3, args.warmup)):
+        launch()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        launch()                 # 268 MB of sequence + ~2.1 GB of trace written and read per launch: far beyond L2
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    launches_dev = ctx.launch_count - launches0
+    ms = ev[0].elapsed_time(ev[-1]) / args.steps
+    dev_scores = d_meta[0].cpu().numpy()
+    dev_nops = d_meta[3].cpu().numpy()
+    rounds = (d_meta[1].cpu().numpy().astype(np.int64) + d_meta[2].cpu().numpy()).sum()   # >= end_y + end_x rounds per pair (a lower bound: the band runs on to the edge)
+
+    # e2e: host arrays in, scores + tracebacks out
+    def e2e():
+        ctx._check(ctx._lib.swb200_semiglobal_xdrop_batch(ctx._h, pa.array.ctypes.data, pb.array.ctypes.data, SG_LEN, n,
+                                                          h_meta[0].array.ctypes.data, h_meta[1].array.ctypes.data, h_meta[2].array.ctypes.data,
+                                                          h_meta[3].array.ctypes.data, h_ops.array.ctypes.data))
+    for _ in range(2):
+        e2e()
+    launches1 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    launches_e2e = ctx.launch_count - launches1
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+    e2e_ok = bool(np.array_equal(h_meta[0].array, dev_scores) and np.array_equal(h_meta[3].array, dev_nops))
+
+    # parity on a sample, against the oracle restatement (checker only)
+    from oracle import oracle as O
+    O.build()
+    ok = True
+    for i in range(0, n, max(1, n // 24)):
+        s, ey, ex, ops = O.semiglobal_xdrop(pa.array[i], pb.array[i])
+        ok = ok and s == h_meta[0].array[i] and ops.size == h_meta[3].array[i] and np.array_equal(h_ops.array[i, :ops.size], ops)
+
+    cpu = None if args.no_cpu_baseline else sg_cpu_reference(pa.array, pb.array, budget_s=20.0)
+    if cpu is not None:
+        ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
+    peaks = load_peaks()
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    # issue roofline: one warp instruction per clock per scheduler, 4 schedulers per SM
+    issue_peak = 4 * info["sm_count"] * sm_mhz * 1e6
+    rounds_per_s = n * SG_ROUNDS_NOMINAL / (ms * 1e-3)
+    instr_per_round = float(args.sg_instr_per_round)
+    trace_gbs = n * SG_ROUNDS_NOMINAL * SG_TRACE_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
+    line = {
+        "metric": "alignments_per_s", "value": n / (ms * 1e-3), "unit": "alignments/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "band_gcups": rounds_per_s * 32 / 1e9,
+        "config": {"workload": "SURVEY.md 8(f4): adaptive-banded X-drop semi-global aligner (band 32, X 70, 1/1/1), score + traceback, "
+                               f"{n} pairs of 16384-mers with 10/10/10 % mismatch/insert/delete (TestSemiGlobal's construction, source.cpp:2750-2771)",
+                   "pairs": n, "seq_len": SG_LEN, "l2": "inputs 268 MB + 2.1 GB of trace per launch > 126 MB L2, no flush needed", "kernel": info},
+        "clocks": clocks,
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n * SG_LEN,
+                "d2h_bytes_per_step": n * (16 + 2 * SG_LEN), "api": "swb200_semiglobal_xdrop_batch (C ABI, pinned host arrays; scores, end cells and move strings back)",
+                "equals_device_leg": e2e_ok},
+        "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
+        "roofline": {"bound": "issue", "kernel": "swb::sg_xdrop_kernel", "achieved": rounds_per_s * instr_per_round / 1e12, "peak": issue_peak / 1e12,
+                     "unit": "T warp-instr/s", "frac": rounds_per_s * instr_per_round / issue_peak,
+                     "instr_per_round": instr_per_round, "rounds_per_launch": n * SG_ROUNDS_NOMINAL,
+                     "note": "one warp per pair, one round = one anti-diagonal of 32 cells; the chain of a round is serial, so the bound is the schedulers' issue rate "
+                             "(4 warp-instr/clk/SM), not HBM or the ALU lanes; instr_per_round from the ncu capture in profiles/",
+                     "traffic": None,
+                     "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2}},
+        "verified": {"sample_equals_oracle_score_and_traceback": bool(ok), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n)},
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["alignments_per_s"], "unit": "alignments/s", "cores": cpu["cores"], "kind": "reference", "variant": cpu["variant"],
+                                "cpu_model": cpu_model(), "sample": f"{cpu['sample_pairs']} of {n} pairs per pass, best of 3 passes"}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 # --------------------------------------------------------------------------- length sweep
 def run_sweep_arm(args):
     """BASELINE.json configs[3]: `--workload sweep` -- square pairs of 128, 256 and 512 bases on one
@@ -527,10 +678,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sg-instr-per-round", type=float, default=95.0, help="semiglobal: warp instructions per round of the kernel (from the ncu capture)")
     ap.add_argument("--pack-threads", type=int, default=None, help="host 2-bit packing lanes per GPU in the e2e leg (default: library auto; 0 = off)")
     ap.add_argument("--no-plain-e2e", action="store_true", help="skip the lanes-off comparison run of the e2e leg")
     ap.add_argument("--cpu-table", action="store_true", help="with --impl reference: scalar/simd4/simd7/simd9, 1 thread and all cores")
-    ap.add_argument("--workload", choices=["batch1m", "stream", "sweep"], default="batch1m",
+    ap.add_argument("--workload", choices=["batch1m", "stream", "sweep", "semiglobal"], default="batch1m",
                     help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
@@ -539,7 +691,9 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         log("bench.py: warmup raised to 3 (timing rules)")
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "semiglobal":
+        run_semiglobal_arm(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "stream":
         run_stream_arm(args)

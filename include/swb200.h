@@ -234,6 +234,12 @@ int swb200_gen_counter_pairs(uint64_t seed, uint64_t first, uint64_t n, uint8_t*
 int swb200_gen_counter_pairs_packed(uint64_t seed, uint64_t first, uint64_t n,
                                     uint8_t* seq1_packed, uint8_t* seq2_packed, int threads);
 
+/* Long related pairs in the manner of the reference's TestSemiGlobal (source.cpp:2750-2771): seq2 is seq1
+ * with sub_pct % mismatches, ins_pct % insertions and del_pct % deletions (the reference uses 10/10/10),
+ * counter-based like the stream above.  Host arrays [n][seq_len]. */
+int swb200_gen_related_pairs(uint64_t seed, uint64_t first, uint64_t n, int32_t seq_len, int sub_pct, int ins_pct, int del_pct,
+                             uint8_t* seq1, uint8_t* seq2, int threads);
+
 /* FNV-1a-64 over int32 scores: h = 1469598103934665603; h = (h ^ (uint32)s) * 1099511628211. */
 uint64_t swb200_fnv1a64_i32(const int32_t* scores, uint64_t n);
 

@@ -11,6 +11,9 @@
 //    configurations: pair k is a pure function of (seed, k), so any index range can be
 //    produced by any thread, rank or GPU shard.  One splitmix64
 //    draw yields 32 bases; a pair takes 8 draws.
+//  * swb200_gen_related_pairs: long related pairs in the manner of the reference's TestSemiGlobal
+//    (source.cpp:2750-2771: seq2 = seq1 with 10 % mismatches, 10 % insertions, 10 % deletions), again
+//    counter-based (pair k depends only on (seed, k)) and with the three rates as arguments.
 //  * swb200_fnv1a64_i32: the score checksum SURVEY.md §8(c) defines.
 #include "../../include/swb200.h"
 
@@ -65,9 +68,54 @@ int gen_counter(uint64_t seed, uint64_t first, uint64_t n, uint8_t* seq1, uint8_
     return SWB200_OK;
 }
 
+// TestSemiGlobal's construction (source.cpp:2750-2771) with a per-pair splitmix64 stream instead of
+// the shared mt19937_64: a = iid bases; b walks a, each step drawing p in [0,100).
+void gen_related_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, int len, int sub_pct, int ins_pct, int del_pct,
+                       uint8_t* seq1, uint8_t* seq2)
+{
+    for (uint64_t p = lo; p < hi; ++p) {
+        uint64_t state = splitmix64((first + p) * 0x9E3779B97F4A7C15ull + seed);
+        uint64_t bits = 0; int have = 0;
+        auto draw = [&](int nbits) -> uint32_t {
+            if (have < nbits) { state = splitmix64(state); bits = state; have = 64; }
+            const uint32_t v = (uint32_t)(bits & ((1ull << nbits) - 1));
+            bits >>= nbits; have -= nbits;
+            return v;
+        };
+        auto pct = [&]() -> int { uint32_t v; do { v = draw(7); } while (v >= 100); return (int)v; };   // uniform on 0..99
+        uint8_t* a = seq1 + p * (uint64_t)len;
+        uint8_t* b = seq2 + p * (uint64_t)len;
+        for (int i = 0; i < len; ++i) a[i] = (uint8_t)draw(2);
+        for (int i = 0, j = 0; i < len;) {
+            if (j == len) { b[i++] = (uint8_t)draw(2); continue; }
+            const int q = pct();
+            if (q < sub_pct) { b[i++] = (uint8_t)draw(2); ++j; }
+            else if (q < sub_pct + ins_pct) { b[i++] = (uint8_t)draw(2); }
+            else if (q < sub_pct + ins_pct + del_pct) { ++j; }
+            else { b[i++] = a[j++]; }
+        }
+    }
+}
+
 } // namespace
 
 extern "C" {
+
+int swb200_gen_related_pairs(uint64_t seed, uint64_t first, uint64_t n, int32_t seq_len, int sub_pct, int ins_pct, int del_pct,
+                             uint8_t* seq1, uint8_t* seq2, int threads)
+{
+    if (n && (!seq1 || !seq2)) return SWB200_ERR_ARG;
+    if (seq_len < 1 || sub_pct < 0 || ins_pct < 0 || del_pct < 0 || sub_pct + ins_pct + del_pct > 100) return SWB200_ERR_ARG;
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n) threads = n ? (int)n : 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back(gen_related_range, seed, first, n * (uint64_t)t / threads, n * (uint64_t)(t + 1) / threads, (int)seq_len,
+                          sub_pct, ins_pct, del_pct, seq1, seq2);
+    for (auto& th : pool) th.join();
+    return SWB200_OK;
+}
+
 
 int swb200_gen_reference_stream(uint64_t seed, uint64_t n, uint8_t* seq1, uint8_t* seq2)
 {

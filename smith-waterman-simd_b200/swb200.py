@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
     "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
-    "swb200_semiglobal_kernel_info", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
+    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -121,6 +121,8 @@ def load_library():
         f = getattr(lib, name)
         f.restype = i32
         f.argtypes = [u64, u64, u64, vp, vp, i32]
+    lib.swb200_gen_related_pairs.restype = i32
+    lib.swb200_gen_related_pairs.argtypes = [u64, u64, u64, i32, i32, i32, i32, vp, vp, i32]
     lib.swb200_fnv1a64_i32.restype = u64
     lib.swb200_fnv1a64_i32.argtypes = [vp, u64]
     lib.swb200_score_batch_111.restype = i32
@@ -470,6 +472,19 @@ def counter_pairs(first: int, n: int, seed: int = 10000, packed: bool = False, o
     rc = fn(seed, first, n, a.ctypes.data, b.ctypes.data, threads or min(os.cpu_count() or 1, 16))
     if rc != 0:
         raise SwbError(rc, "swb200_gen_counter_pairs")
+    return a, b
+
+
+def related_pairs(first: int, n: int, seq_len: int = 16384, sub_pct: int = 10, ins_pct: int = 10, del_pct: int = 10,
+                  seed: int = 10000, out=None, threads: int = 0):
+    """Pairs [first, first+n) of TestSemiGlobal-style related sequences (source.cpp:2750-2771), counter-based."""
+    lib = load_library()
+    a, b = out if out is not None else (np.empty((n, seq_len), np.uint8), np.empty((n, seq_len), np.uint8))
+    assert a.shape == (n, seq_len) and b.shape == (n, seq_len) and a.flags.c_contiguous and b.flags.c_contiguous
+    rc = lib.swb200_gen_related_pairs(seed, first, n, seq_len, sub_pct, ins_pct, del_pct, a.ctypes.data, b.ctypes.data,
+                                      threads or min(os.cpu_count() or 1, 16))
+    if rc != 0:
+        raise SwbError(rc, "swb200_gen_related_pairs")
     return a, b
 
 
