@@ -22,13 +22,17 @@
 //     two 32-bit masks -- "this cell's value came from the diagonal" / "... from above", evaluated
 //     with the reference's own comparisons and preference order -- plus the band's pos_y: one 16-byte
 //     record per round (lane 0 stores it) instead of the 32 band values.
-//   * The traceback walks those records backwards, the warp loading them 32 rounds at a time
-//     (the walker itself is serial, as in the reference), and emits one op per step:
-//     0 = diagonal, 1 = down (y+1), 2 = right (x+1), in forward order from (0,0).
+//   * The traceback is a second kernel, ONE THREAD PER PAIR: the walk is serial (as in the reference),
+//     so a warp spent on it would execute every instruction for one live lane.  A thread reads its
+//     pair's records backwards -- consecutive 16-byte records, so seven of eight come from the line
+//     the previous step brought into L1 -- and emits one op per step: 0 = diagonal, 1 = down (y+1),
+//     2 = right (x+1).  The ops land right-aligned in the pair's output row in forward order and
+//     the warp then shifts each of its 32 rows to the left edge together.
 //
 // HBM layout: seq1, seq2 [n][len] byte codes 0..3 (the reference's std::array<uint8_t,16384>, len = 16384);
-// per resident warp a scratch slot of sg_slot_bytes(len); outputs score/end_y/end_x/n_ops [n] int32
-// and ops [n][2*len] bytes (optional).
+// scratch: per resident warp of the forward kernel the padded sequence copies (sg_warp_bytes), per PAIR
+// of a launch the round records (sg_trace_bytes); outputs score/end_y/end_x/n_ops [n] int32 and
+// ops [n][2*len] bytes (optional).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,8 +49,10 @@ constexpr int SG_PAD = 128;         // padded sequence copies hold 2*len + SG_PA
 __host__ __device__ inline uint32_t sg_rounds_cap(int len) { return ((uint32_t)(2 * len + 1) + 31u) & ~31u; }
 // elements (uint16) of one padded sequence copy: positions run to 31 + 2*len + 1 at most (one move per round)
 __host__ __device__ inline size_t sg_padded_len(int len) { return (2 * (size_t)len + SG_PAD + 127) & ~(size_t)127; }
-// per-warp scratch: [rounds_cap] uint4 records, then the padded copies of seq1 and seq2 (uint16 per base)
-__host__ __device__ inline size_t sg_slot_bytes(int len) { return (size_t)sg_rounds_cap(len) * 16 + 2 * sg_padded_len(len) * 2; }
+// per resident warp: the padded copies of seq1 and seq2 (uint16 per base)
+__host__ __device__ inline size_t sg_warp_bytes(int len) { return 2 * sg_padded_len(len) * 2; }
+// per pair of a launch: [rounds_cap] uint4 records {diagonal mask, up mask, pos_y, round}; record 0 = the end cell
+__host__ __device__ inline size_t sg_trace_bytes(int len) { return (size_t)sg_rounds_cap(len) * 16; }
 
 // element `idx` of a 16-bit array as base + 2*idx in one mad.wide (two LEA instructions); left to the compiler the
 // same address costs five ALU-pipe instructions (64-bit add of the lane offset, doubling, carry).
@@ -77,14 +83,13 @@ struct SgOut {
 //   * lane 0 stores the round's record {diagonal mask, up mask, pos_y, round} as one 16-byte store.
 __global__ void __launch_bounds__(SG_WARPS_PER_BLOCK * 32)
 sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
-                uint8_t* __restrict__ scratch, const SgOut out)
+                uint8_t* __restrict__ warp_scratch, uint4* __restrict__ traces, const SgOut out)
 {
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned long long warp = (unsigned long long)blockIdx.x * SG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const unsigned long long n_warps = (unsigned long long)gridDim.x * SG_WARPS_PER_BLOCK;
     const uint32_t rounds_cap = sg_rounds_cap(len);
-    uint4* const trace = reinterpret_cast<uint4*>(scratch + warp * sg_slot_bytes(len));
-    uint16_t* const seq1p = reinterpret_cast<uint16_t*>(trace + rounds_cap);   // seq1p[k] = seq1[k-1]
+    uint16_t* const seq1p = reinterpret_cast<uint16_t*>(warp_scratch + warp * sg_warp_bytes(len));   // seq1p[k] = seq1[k-1]
     uint16_t* const seq2p = seq1p + sg_padded_len(len);                         // seq2p[k] = seq2[k-32]
     const int max_round = 2 * len + 1;          // rounds run while round < MAX_ROUND (source.cpp:1872,1886)
     const unsigned FULL = 0xffffffffu;
@@ -114,6 +119,7 @@ sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ se
             }
         }
         __syncwarp();
+        uint4* const trace = traces + p * rounds_cap;
 
         int res = is31 ? SG_X : SG_NEG;             // dp[31] = X_THRESHOLD (source.cpp:1877)
         int hor = SG_NEG, ver = SG_NEG;
@@ -154,50 +160,113 @@ sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ se
             if (is0) trace[round] = make_uint4(dmask, umask, now_y, (uint32_t)round);
             if (rmax <= 0) break;                                        // everything dropped (source.cpp:1938-1941)
         }
-        __syncwarp();
-
         const int best_lane = 31 - __clz(best_hit);
         const int end_y = best_py + 31 - best_lane;
         const int end_x = (best_round - best_py) - 31 + best_lane;     // pos_x - 31 = round - pos_y (pos_x = 31 + #right moves)
-        if (lane == 0) { out.score[p] = best - SG_X; out.end_y[p] = end_y; out.end_x[p] = end_x; }
-        if (!out.ops) continue;
+        if (is0) {
+            out.score[p] = best - SG_X; out.end_y[p] = end_y; out.end_x[p] = end_x;
+            trace[0] = make_uint4((uint32_t)best_round, (uint32_t)best_py, (uint32_t)end_y, (uint32_t)end_x);   // where the traceback starts
+        }
+        __syncwarp();      // the padded copies are rewritten for the next pair
+    }
+}
 
-        // ---- traceback (source.cpp:1956-1973) over the recorded masks
-        uint8_t* const ops = out.ops + p * 2ull * (unsigned long long)len;
-        int r = best_round, y = end_y, x = end_x;
-        int c_cur = r >> 5;
-        uint4 recA = trace[c_cur * 32 + lane];       // rounds of chunk c_cur; .z = pos_y of the round (source.cpp:1912)
-        uint4 recB = make_uint4(0u, 0u, 0u, 0u);
-        if (c_cur >= 1) recB = trace[(c_cur - 1) * 32 + lane];
-        uint32_t n_ops = 0, opreg = 0;
-        const uint32_t cap = 2u * (uint32_t)len;
-        while ((y | x) != 0 && n_ops < cap) {
-            if ((r >> 5) != c_cur) {                 // r only ever drops into the previous chunk
-                --c_cur;
-                recA = recB;
-                if (c_cur >= 1) recB = trace[(c_cur - 1) * 32 + lane];
+// Traceback (source.cpp:1956-1973) over the recorded masks: thread t walks pair t's records backwards from the
+// end cell to (0,0).  The walk is a chain of dependent 16-byte reads marching down through memory, and the
+// records were written by another kernel (HBM, not L2), so each thread streams its records through a private
+// ring of SG_TB_LINES 128-byte lines in shared memory with cp.async, SG_TB_LINES - 1 lines (about 35 steps)
+// ahead of the walker: a step then costs a shared-memory read, not a DRAM round trip.  The step itself is
+// branch-free, so the 32 walks of a warp stay converged.
+// Step k (k = 0 is the LAST move) is written to row[2*len - 1 - k], so the row ends up holding the
+// forward-ordered op string right-aligned; sg_left_align_kernel then moves it to the left edge.
+constexpr int SG_TB_THREADS = 64;
+constexpr int SG_TB_LINES = 8;
+constexpr size_t SG_TB_SMEM = (size_t)SG_TB_LINES * 8 * SG_TB_THREADS * sizeof(uint4);    // 64 KiB
+
+__device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(SG_TB_THREADS)
+sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
+{
+    extern __shared__ uint4 sg_ring[];          // [line slot][record 0..7][thread]: neighbours in a warp sit in neighbouring banks
+    const unsigned long long p = (unsigned long long)blockIdx.x * SG_TB_THREADS + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t rounds_cap = sg_rounds_cap(len);
+    const uint32_t cap = 2u * (uint32_t)len;
+    const uint4* const trace = traces + p * rounds_cap;
+    uint8_t* const row = out.ops + p * (unsigned long long)cap;
+    uint4* const ring = sg_ring + threadIdx.x;
+    auto slot_of = [&](int line, int rec) -> uint4* { return ring + ((line & (SG_TB_LINES - 1)) * 8 + rec) * SG_TB_THREADS; };
+    auto request = [&](int line) {              // one commit group per line, empty when the walk has run out of lines
+        if (line >= 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sg_cp_async16(slot_of(line, q), trace + line * 8 + q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const uint4 start = trace[0];               // {best round, its pos_y, end_y, end_x}, written by the forward kernel
+    int r = (int)start.x, y = (int)start.z, x = (int)start.w;
+    int lo = (r >> 3) - (SG_TB_LINES - 1);      // lowest line requested so far: the ring holds lines lo .. lo+7
+#pragma unroll
+    for (int q = 0; q < SG_TB_LINES; ++q) request((r >> 3) - q);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    uint32_t n_ops = 0;
+    // A step moves at most two records down, so at most one line per four steps: every fourth step (the same
+    // step for every lane of the warp, so no divergence) a lane asks for one more line if the ring has a free
+    // slot.  A line is therefore requested at least five such batches before the walker enters it, and
+    // wait_group 4 -- all but the four youngest batches have landed -- covers it.
+    while ((y | x) != 0 && n_ops < cap) {
+        if ((n_ops & 3u) == 0u) {
+            const bool room = (r >> 3) <= lo + (SG_TB_LINES - 2);      // the walker has left line lo+7: its slot is free
+            if (room) --lo;
+            if (room && lo >= 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sg_cp_async16(slot_of(lo, q), trace + lo * 8 + q);
             }
-            const int k = r & 31;
-            const uint32_t dm = __shfl_sync(FULL, recA.x, k), um = __shfl_sync(FULL, recA.y, k);
-            const int py = (int)__shfl_sync(FULL, recA.z, k);
-            const int o = 31 - (y - py);             // band element of (y,x) in round r (source.cpp:1947)
-            uint32_t op;
-            if ((dm >> o) & 1u)      { op = 0; --y; --x; r -= 2; }
-            else if ((um >> o) & 1u) { op = 1; --y;      r -= 1; }
-            else                     { op = 2;      --x; r -= 1; }
-            if ((uint32_t)lane == (n_ops & 31u)) opreg = op;
-            ++n_ops;
-            if ((n_ops & 31u) == 0) ops[n_ops - 32u + lane] = (uint8_t)opreg;      // reversed order for now
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 4;" ::: "memory");
         }
-        if ((n_ops & 31u) != 0 && (uint32_t)lane < (n_ops & 31u)) ops[(n_ops & ~31u) + lane] = (uint8_t)opreg;
-        __syncwarp();
-        // reverse in place: forward order from (0,0)
-        for (uint32_t i = lane; i < n_ops / 2; i += 32) {
-            const uint8_t a = ops[i], b = ops[n_ops - 1 - i];
-            ops[i] = b; ops[n_ops - 1 - i] = a;
-        }
-        if (lane == 0) out.n_ops[p] = (int32_t)n_ops;
-        __syncwarp();
+        const uint4 rec = *slot_of(r >> 3, r & 7);      // {diagonal mask, up mask, pos_y of round r, r}
+        const int o = 31 - (y - (int)rec.z);            // band element of (y,x) in round r (source.cpp:1947)
+        const uint32_t d = (rec.x >> o) & 1u;           // diagonal first, then up, else left (source.cpp:1960-1969)
+        const uint32_t u = (rec.y >> o) & 1u & ~d;
+        row[cap - 1u - n_ops] = (uint8_t)(2u - 2u * d - u);             // 0 = diagonal, 1 = down, 2 = right
+        y -= (int)(d | u);
+        x -= (int)(1u - u);
+        r -= 1 + (int)d;
+        ++n_ops;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    out.n_ops[p] = (int32_t)n_ops;
+}
+
+// Moves each row's op string from the right edge (where the traceback left it) to the left edge.  One block per
+// row; a step reads 256 x 16 bytes into registers, synchronises, and writes them `shift` bytes lower: the
+// destination of a step never reaches the source of a later one, so an overlapping move is safe.
+__global__ void __launch_bounds__(256)
+sg_left_align_kernel(const int len, const unsigned long long n, const SgOut out)
+{
+    const unsigned long long p = blockIdx.x;
+    if (p >= n) return;
+    const uint32_t cap = 2u * (uint32_t)len;
+    const uint32_t n_ops = (uint32_t)out.n_ops[p];
+    if (n_ops == 0u || n_ops >= cap) return;
+    uint8_t* const row = out.ops + p * (unsigned long long)cap;
+    const uint32_t shift = cap - n_ops;
+    for (uint32_t base = 0; base < n_ops; base += 256u * 16u) {
+        const uint32_t i0 = base + threadIdx.x * 16u;
+        uint8_t b[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) b[q] = (i0 + q < n_ops) ? row[shift + i0 + q] : (uint8_t)0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) if (i0 + q < n_ops) row[i0 + q] = b[q];
+        __syncthreads();
     }
 }
 

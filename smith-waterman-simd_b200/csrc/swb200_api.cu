@@ -90,14 +90,19 @@ struct Device {
     std::mutex mu;                   // one host batch at a time per GPU
     unsigned long long* d_bad = nullptr;
     // semi-global aligner: per-resident-warp trace slots, and two staging slots for host batches
-    uint8_t* d_sg_scratch = nullptr;
-    size_t sg_scratch_bytes = 0;
+    struct SgScratch {
+        uint8_t* warp = nullptr;         // padded sequence copies, one slot per resident warp of the forward kernel
+        size_t warp_bytes = 0;
+        uint4* traces = nullptr;         // round records, one slot per pair of a launch
+        size_t trace_bytes = 0;
+    } sg_dev;                            // scratch of the device-resident entry
     struct SgSlot {
+        SgScratch scratch;               // each staging slot has its own, so the two slots' kernels are independent
         cudaStream_t stream = nullptr;
         uint8_t *d_seq1 = nullptr, *d_seq2 = nullptr, *d_ops = nullptr;
         int32_t* d_meta = nullptr;       // [4][cap]: score, end_y, end_x, n_ops
         size_t cap_pairs = 0; int len = 0; bool with_ops = false;
-    } sg_slots[2];
+    } sg_slots[4];
     // lane pool (created on first use)
     std::vector<Lane*> lanes;
     std::mutex pool_mu;
@@ -272,6 +277,7 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -483,8 +489,10 @@ int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
         const int rc = lane_alloc(ctx, ln);
         if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
             stop_lanes(d);
-        cudaFree(d->d_sg_scratch);
+        cudaFree(d->sg_dev.warp);
+        cudaFree(d->sg_dev.traces);
         for (auto& g : d->sg_slots) {
+            cudaFree(g.scratch.warp); cudaFree(g.scratch.traces);
             if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
             cudaFree(g.d_seq1); cudaFree(g.d_seq2); cudaFree(g.d_ops); cudaFree(g.d_meta);
         }
@@ -527,7 +535,18 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
 
 // ---------------------------------------------------------------------------------------------
 // Semi-global X-drop aligner (sg_kernel.cuh)
-constexpr int kSgBlocksPerSm = 8;                 // 32 warps = 32 pairs in flight per SM
+constexpr int kSgBlocksPerSmDefault = 8;          // 32 warps = 32 pairs in flight per SM
+
+int sg_blocks_per_sm()
+{
+    static const int v = [] {
+        const char* e = getenv("SWB200_SG_BLOCKS");       // tuning knob (1..16 blocks of 4 warps)
+        const int x = e ? atoi(e) : kSgBlocksPerSmDefault;
+        return x < 1 ? 1 : (x > 16 ? 16 : x);
+    }();
+    return v;
+}
+#define kSgBlocksPerSm sg_blocks_per_sm()
 constexpr int kSgMaxLen = 1 << 15;                // scores stay far inside int32; scratch = 16.3 bytes per base per resident warp
 
 int sg_grid(const Device* d, uint64_t n)
@@ -537,28 +556,62 @@ int sg_grid(const Device* d, uint64_t n)
     return (int)(need < resident ? need : resident);
 }
 
-int sg_ensure_scratch(swb200_ctx* ctx, Device* d, int len)
+constexpr size_t kSgTraceBudget = 4ull << 30;     // round records kept per launch (524 288 B per pair at len 16384: 8192 pairs)
+
+uint64_t sg_pairs_per_launch(int len)
 {
-    const size_t need = (size_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK * sg_slot_bytes(len);
-    if (need <= d->sg_scratch_bytes) return SWB200_OK;
+    const uint64_t v = kSgTraceBudget / sg_trace_bytes(len);
+    return v ? v : 1;
+}
+
+int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len, uint64_t n)
+{
+    const size_t need_warp = (size_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK * sg_warp_bytes(len);
+    const uint64_t pairs = n < sg_pairs_per_launch(len) ? n : sg_pairs_per_launch(len);
+    const size_t need_trace = pairs * sg_trace_bytes(len);
+    const bool grow_warp = need_warp > sc.warp_bytes;
+    const bool grow_trace = need_trace > sc.trace_bytes;
+    if (!grow_warp && !grow_trace) return SWB200_OK;
     SWB_CUDA(ctx, cudaDeviceSynchronize());
-    cudaFree(d->d_sg_scratch);
-    d->d_sg_scratch = nullptr; d->sg_scratch_bytes = 0;
-    SWB_CUDA(ctx, cudaMalloc(&d->d_sg_scratch, need));
-    d->sg_scratch_bytes = need;
+    if (grow_warp) {
+        cudaFree(sc.warp);
+        sc.warp = nullptr; sc.warp_bytes = 0;
+        SWB_CUDA(ctx, cudaMalloc(&sc.warp, need_warp));
+        sc.warp_bytes = need_warp;
+    }
+    if (grow_trace) {
+        cudaFree(sc.traces);
+        sc.traces = nullptr; sc.trace_bytes = 0;
+        SWB_CUDA(ctx, cudaMalloc(&sc.traces, need_trace));
+        sc.trace_bytes = need_trace;
+    }
     return SWB200_OK;
 }
 
-// The launch alone, on device arrays.  Launches on `st` share the device's scratch, so they must be
-// stream-ordered with each other (the host batch below uses one compute order per device).
-int sg_launch(swb200_ctx* ctx, Device* d, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
+// The launches alone, on device arrays: the forward kernel (one warp per pair) and, when ops are wanted, the
+// traceback and left-align kernels (one thread / one block per pair), in equal sub-batches that fit the record
+// scratch.  All launches on one scratch must be stream-ordered with each other.
+int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
               int32_t* d_score, int32_t* d_ey, int32_t* d_ex, int32_t* d_nops, uint8_t* d_ops, cudaStream_t st)
 {
-    if (n == 0) return SWB200_OK;
-    SgOut out{d_score, d_ey, d_ex, d_nops, d_ops};
-    sg_xdrop_kernel<<<sg_grid(d, n), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1, d2, len, n, d->d_sg_scratch, out);
-    SWB_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    const uint64_t cap_pairs = sc.trace_bytes / sg_trace_bytes(len);
+    const uint64_t parts = (n + cap_pairs - 1) / cap_pairs;
+    const uint64_t per = (n + parts - 1) / parts;                 // equal parts: no small remainder launch that leaves the GPU mostly idle
+    for (uint64_t c0 = 0; c0 < n; c0 += per) {
+        const uint64_t m = (n - c0 < per) ? n - c0 : per;
+        SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
+        sg_xdrop_kernel<<<sg_grid(d, m), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
+                                                                           sc.warp, sc.traces, out);
+        SWB_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        if (d_ops) {
+            sg_traceback_kernel<<<(unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS), SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            SWB_CUDA(ctx, cudaGetLastError());
+            sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
+            SWB_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 2;
+        }
+    }
     return SWB200_OK;
 }
 
@@ -595,30 +648,53 @@ int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t*
     if (hi <= lo) return SWB200_OK;
     std::lock_guard<std::mutex> lock(d->mu);
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    int rc = sg_ensure_scratch(ctx, d, len);
-    if (rc != SWB200_OK) return rc;
-    // chunk: about 64 MiB of sequence per array, at least one resident wave of pairs
-    uint64_t chunk = (64ull << 20) / (uint64_t)len;
+    // chunk: half a resident wave of pairs (at least 32 MiB of sequence per array); the range is cut in equal chunks.
+    // Two half-wave forward kernels from different slots fill the machine together, and the short chunks keep the
+    // exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
     const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK;
-    if (chunk < wave) chunk = wave;
-    if (chunk > hi - lo) chunk = hi - lo;
-    for (auto& s : d->sg_slots) { rc = sg_ensure_slot(ctx, s, chunk, len, ops != nullptr); if (rc != SWB200_OK) return rc; }
-    cudaEvent_t kdone[2] = {nullptr, nullptr};
-    for (auto& e : kdone) SWB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    uint64_t chunk = (32ull << 20) / (uint64_t)len;
+    if (chunk < wave / 2) chunk = wave / 2;
+    if (chunk > sg_pairs_per_launch(len)) chunk = sg_pairs_per_launch(len);
+    const uint64_t parts = (hi - lo + chunk - 1) / chunk;
+    chunk = (hi - lo + parts - 1) / parts;
+    int rc;
+    for (auto& s : d->sg_slots) {
+        rc = sg_ensure_slot(ctx, s, chunk, len, ops != nullptr);
+        if (rc == SWB200_OK) rc = sg_ensure_scratch(ctx, d, s.scratch, len, chunk);
+        if (rc != SWB200_OK) return rc;
+    }
+    // The slots are independent streams with their own scratch, so copies overlap kernels and the forward kernels of
+    // neighbouring chunks share the machine.  (Measured with SWB200_SG_TIMELINE: ordering the forward kernels so that a
+    // chunk's traceback runs beside the NEXT chunk's forward kernel does not pay -- the traceback is one dependent
+    // chain per thread, and beside eight forward warps per scheduler each of its steps waits its turn: 2.4 ms alone
+    // became 12 ms.)
+    // SWB200_SG_TIMELINE=1: print, per chunk, when its H2D, kernels and D2H finished (ms after the first enqueue)
+    static const bool timeline = getenv("SWB200_SG_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> marks;
+    size_t n_marked = 0;
+    if (timeline) {
+        marks.resize(4 * (size_t)((hi - lo + chunk - 1) / chunk));
+        for (auto& e : marks) SWB_CUDA(ctx, cudaEventCreate(&e));
+    }
+    auto mark = [&](cudaStream_t st, int which) {
+        if (!timeline) return;
+        cudaEventRecord(marks[4 * n_marked + which], st);
+        if (which == 3) ++n_marked;
+    };
     int si = 0;
-    bool first = true;
-    for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si ^= 1) {
+    for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si = (si + 1) & 3) {
         Device::SgSlot& s = d->sg_slots[si];
         const uint64_t m = (hi - c0 < chunk) ? hi - c0 : chunk;
         SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));                       // this slot's previous chunk is fully back on the host
+        mark(s.stream, 0);
         SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq1, seq1 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
         SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq2, seq2 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
-        if (!first) SWB_CUDA(ctx, cudaStreamWaitEvent(s.stream, kdone[si ^ 1], 0));   // the other slot's kernel owns the scratch until then
+        mark(s.stream, 1);
         int32_t* meta = s.d_meta;
-        rc = sg_launch(ctx, d, s.d_seq1, s.d_seq2, len, m, meta, meta + s.cap_pairs, meta + 2 * s.cap_pairs,
+        rc = sg_launch(ctx, d, s.scratch, s.d_seq1, s.d_seq2, len, m, meta, meta + s.cap_pairs, meta + 2 * s.cap_pairs,
                        ops ? meta + 3 * s.cap_pairs : nullptr, ops ? s.d_ops : nullptr, s.stream);
         if (rc != SWB200_OK) return rc;
-        SWB_CUDA(ctx, cudaEventRecord(kdone[si], s.stream));
+        mark(s.stream, 2);
         SWB_CUDA(ctx, cudaMemcpyAsync(score + c0, meta, m * 4, cudaMemcpyDeviceToHost, s.stream));
         SWB_CUDA(ctx, cudaMemcpyAsync(ey + c0, meta + s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
         SWB_CUDA(ctx, cudaMemcpyAsync(ex + c0, meta + 2 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -626,10 +702,15 @@ int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t*
             SWB_CUDA(ctx, cudaMemcpyAsync(nops + c0, meta + 3 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
             SWB_CUDA(ctx, cudaMemcpyAsync(ops + c0 * 2ull * (uint64_t)len, s.d_ops, m * 2ull * (uint64_t)len, cudaMemcpyDeviceToHost, s.stream));
         }
-        first = false;
+        mark(s.stream, 3);
     }
     for (auto& s : d->sg_slots) SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));
-    for (auto& e : kdone) cudaEventDestroy(e);
+    for (size_t k = 0; k < n_marked; ++k) {
+        float t[4] = {0, 0, 0, 0};
+        for (int w = 0; w < 4; ++w) cudaEventElapsedTime(&t[w], marks[0], marks[4 * k + w]);
+        fprintf(stderr, "[swb200 sg timeline] chunk %zu: enqueue %.2f  h2d done %.2f  kernels done %.2f  d2h done %.2f ms\n", k, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : marks) cudaEventDestroy(e);
     return SWB200_OK;
 }
 
@@ -1000,9 +1081,9 @@ int swb200_semiglobal_xdrop_batch_device(swb200_ctx* ctx, int device_index, cons
     Device* d = ctx->devs[device_index];
     std::lock_guard<std::mutex> lock(d->mu);
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    rc = sg_ensure_scratch(ctx, d, seq_len);
+    rc = sg_ensure_scratch(ctx, d, d->sg_dev, seq_len, n);
     if (rc != SWB200_OK) return rc;
-    return sg_launch(ctx, d, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops, (cudaStream_t)cuda_stream);
+    return sg_launch(ctx, d, d->sg_dev, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops, (cudaStream_t)cuda_stream);
 }
 
 int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kernel_info* info)

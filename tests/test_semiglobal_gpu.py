@@ -54,14 +54,16 @@ def test_golden_cases_from_the_reference(ctx):
     b = np.stack([c["seq2"] for c in cases])
     launches0 = ctx.launch_count
     r = ctx.semiglobal_xdrop(a, b)
-    assert ctx.launch_count == launches0 + 1                    # the sm_100a kernel ran, once, for the whole batch
+    assert ctx.launch_count == launches0 + 3                    # the sm_100a kernels ran: forward, traceback, left-align, once for the whole batch
     for i, c in enumerate(cases):
         assert (r["score"][i], r["end_y"][i], r["end_x"][i], r["n_ops"][i]) == (c["score"], c["end_y"], c["end_x"], c["n_ops"]), c["name"]
         ops = r["ops"][i, :r["n_ops"][i]]
         assert np.array_equal(ops, c["ops"]), c["name"]
         assert f"{fnv1a64_bytes(ops_to_traceback(ops).tobytes()):016x}" == c["traceback_fnv1a64"], c["name"]
     # score-only mode skips the traceback and agrees
+    launches0 = ctx.launch_count
     s = ctx.semiglobal_xdrop(a, b, traceback=False)
+    assert ctx.launch_count == launches0 + 1                    # forward kernel only
     assert "ops" not in s and all(np.array_equal(s[k], r[k]) for k in ("score", "end_y", "end_x"))
 
 
@@ -116,10 +118,10 @@ def test_more_pairs_than_resident_warps(ctx, oracle):
 
 
 def test_reference_shape_batch_spans_chunks(ctx, oracle):
-    # len = 16384: more pairs than one staging chunk holds (two slots, kernels chained on the shared scratch)
+    # len = 16384: five staging chunks of half a resident wave over four independent slots (slot 0 is reused)
     info = ctx.semiglobal_kernel_info()
     wave = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
-    n = wave + 211
+    n = 2 * wave + 211
     rng = np.random.default_rng(77)
     a = rng.integers(0, 4, (n, 16384), dtype=np.uint8)
     b = np.where(rng.random((n, 16384)) < 0.9, a, rng.integers(0, 4, (n, 16384), dtype=np.uint8)).astype(np.uint8)
@@ -127,7 +129,7 @@ def test_reference_shape_batch_spans_chunks(ctx, oracle):
         k = int(rng.integers(1, 30))
         b[i] = np.concatenate([a[i, k:], rng.integers(0, 4, k, dtype=np.uint8)])      # a deletion of k bases up front
     r = ctx.semiglobal_xdrop(a, b)
-    idx = np.r_[0:40, wave - 20:wave + 20, n - 40:n].tolist()
+    idx = np.r_[0:30, wave // 2 - 20:wave // 2 + 20, wave - 20:wave + 20, 2 * wave - 50:2 * wave - 10, n - 30:n].tolist()
     check_against_oracle(oracle, r, a, b, idx)
     s = ctx.semiglobal_xdrop(a, b, traceback=False)
     assert np.array_equal(s["score"], r["score"]) and np.array_equal(s["end_y"], r["end_y"])
