@@ -36,6 +36,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "sg2_core.cuh"
 
 namespace swb {
 
@@ -171,6 +172,55 @@ sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ se
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Forward kernel, four lanes per pair (sg2_core.cuh): a warp advances eight pairs per round.  Quads of a warp
+// run their pairs side by side and pick up the next eight together (pairs of similar length finish together;
+// the bench's and the reference's pairs all run the full 2*len rounds).
+constexpr int SG2_THREADS = 32;
+
+struct Sg2DevEnv {
+    int lane4;
+    __device__ __forceinline__ int q() const { return lane4; }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
+    __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
+};
+
+__global__ void __launch_bounds__(SG2_THREADS)
+sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
+                 uint4* __restrict__ traces, const SgOut out)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    Sg2DevEnv env{(int)(lane & 3u)};
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * SG2_THREADS + threadIdx.x) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * SG2_THREADS) >> 5;
+    const uint32_t rounds_cap = sg_rounds_cap(len);
+    const int max_round = 2 * len + 1;          // rounds run while round < MAX_ROUND (source.cpp:1872,1886)
+    // The warp stays converged (full-mask shuffles): its eight quads take eight consecutive pairs, run their rounds
+    // together until the last of them is done, then take the next eight.  A quad beyond the batch shadows the last
+    // pair and writes its records to the spare row n of the scratch.
+    for (unsigned long long base = warp * 8ull; base < n; base += n_warps * 8ull) {
+        const unsigned long long want = base + (lane >> 2);
+        const bool live = want < n;
+        const unsigned long long p = live ? want : n - 1ull;
+        const uint8_t* const s1 = seq1 + p * (unsigned long long)len;
+        const uint8_t* const s2 = seq2 + p * (unsigned long long)len;
+        uint32_t* const rec_row = reinterpret_cast<uint32_t*>(traces + (live ? p : n) * rounds_cap);
+        Sg2State s;
+        sg2_init(s, env, s1, s2, len);
+        const uint8_t* const role = env.q() == 0 ? s1 : s2;
+        for (int round = 1; round < max_round; ++round) {
+            const bool go = sg2_round(s, env, role, len, round, rec_row);
+            if (!__any_sync(0xffffffffu, go)) break;
+        }
+        int32_t score, end_y, end_x;
+        const uint32_t rec0 = sg2_finish(s, env, score, end_y, end_x);
+        if (live) {
+            rec_row[env.q()] = rec0;
+            if (env.q() == 0) { out.score[p] = score; out.end_y[p] = end_y; out.end_x[p] = end_x; }
+        }
+    }
+}
+
 // Traceback (source.cpp:1956-1973) over the recorded masks: thread t walks pair t's records backwards from the
 // end cell to (0,0).  The walk is a chain of dependent 16-byte reads marching down through memory, and the
 // records were written by another kernel (HBM, not L2), so each thread streams its records through a private
@@ -189,6 +239,7 @@ __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
+template <int FMT>      // record format: 1 = {diagonal mask, up mask, pos_y, round} (warp per pair), 2 = four lane words (sg2_core.cuh)
 __global__ void __launch_bounds__(SG_TB_THREADS)
 sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
 {
@@ -231,14 +282,18 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 4;" ::: "memory");
         }
-        const uint4 rec = *slot_of(r >> 3, r & 7);      // {diagonal mask, up mask, pos_y of round r, r}
-        const int o = 31 - (y - (int)rec.z);            // band element of (y,x) in round r (source.cpp:1947)
-        const uint32_t d = (rec.x >> o) & 1u;           // diagonal first, then up, else left (source.cpp:1960-1969)
-        const uint32_t u = (rec.y >> o) & 1u & ~d;
-        row[cap - 1u - n_ops] = (uint8_t)(2u - 2u * d - u);             // 0 = diagonal, 1 = down, 2 = right
-        y -= (int)(d | u);
-        x -= (int)(1u - u);
-        r -= 1 + (int)d;
+        const uint4 rec = *slot_of(r >> 3, r & 7);
+        if (FMT == 2) {
+            row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(rec.x, rec.y, rec.z, rec.w, y, x, r);
+        } else {                                        // {diagonal mask, up mask, pos_y of round r, r}
+            const int o = 31 - (y - (int)rec.z);            // band element of (y,x) in round r (source.cpp:1947)
+            const uint32_t d = (rec.x >> o) & 1u;           // diagonal first, then up, else left (source.cpp:1960-1969)
+            const uint32_t u = (rec.y >> o) & 1u & ~d;
+            row[cap - 1u - n_ops] = (uint8_t)(2u - 2u * d - u);             // 0 = diagonal, 1 = down, 2 = right
+            y -= (int)(d | u);
+            x -= (int)(1u - u);
+            r -= 1 + (int)d;
+        }
         ++n_ops;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -277,7 +277,8 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -547,6 +548,15 @@ int sg_blocks_per_sm()
     return v;
 }
 #define kSgBlocksPerSm sg_blocks_per_sm()
+
+int sg_forward_version()
+{
+    static const int v = [] {
+        const char* e = getenv("SWB200_SG_FORWARD");      // 2 = four lanes per pair (sg2_core.cuh), 1 = warp per pair
+        return (e && atoi(e) == 1) ? 1 : 2;
+    }();
+    return v;
+}
 constexpr int kSgMaxLen = 1 << 15;                // scores stay far inside int32; scratch = 16.3 bytes per base per resident warp
 
 int sg_grid(const Device* d, uint64_t n)
@@ -556,7 +566,7 @@ int sg_grid(const Device* d, uint64_t n)
     return (int)(need < resident ? need : resident);
 }
 
-constexpr size_t kSgTraceBudget = 4ull << 30;     // round records kept per launch (524 288 B per pair at len 16384: 8192 pairs)
+constexpr size_t kSgTraceBudget = 10ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 20 460 pairs)
 
 uint64_t sg_pairs_per_launch(int len)
 {
@@ -568,7 +578,7 @@ int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len
 {
     const size_t need_warp = (size_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK * sg_warp_bytes(len);
     const uint64_t pairs = n < sg_pairs_per_launch(len) ? n : sg_pairs_per_launch(len);
-    const size_t need_trace = pairs * sg_trace_bytes(len);
+    const size_t need_trace = (pairs + 1) * sg_trace_bytes(len);      // + the spare row of sg2_xdrop_kernel
     const bool grow_warp = need_warp > sc.warp_bytes;
     const bool grow_trace = need_trace > sc.trace_bytes;
     if (!grow_warp && !grow_trace) return SWB200_OK;
@@ -594,18 +604,27 @@ int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len
 int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
               int32_t* d_score, int32_t* d_ey, int32_t* d_ex, int32_t* d_nops, uint8_t* d_ops, cudaStream_t st)
 {
-    const uint64_t cap_pairs = sc.trace_bytes / sg_trace_bytes(len);
+    const uint64_t cap_pairs = sc.trace_bytes / sg_trace_bytes(len) - 1;
     const uint64_t parts = (n + cap_pairs - 1) / cap_pairs;
     const uint64_t per = (n + parts - 1) / parts;                 // equal parts: no small remainder launch that leaves the GPU mostly idle
     for (uint64_t c0 = 0; c0 < n; c0 += per) {
         const uint64_t m = (n - c0 < per) ? n - c0 : per;
         SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
-        sg_xdrop_kernel<<<sg_grid(d, m), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
-                                                                           sc.warp, sc.traces, out);
+        const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);
+        if (sg_forward_version() == 2) {
+            const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
+            const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * 24;
+            sg2_xdrop_kernel<<<(unsigned)(need < cap ? need : cap), SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
+                                                                                         sc.traces, out);
+        } else {
+            sg_xdrop_kernel<<<sg_grid(d, m), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
+                                                                               sc.warp, sc.traces, out);
+        }
         SWB_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (d_ops) {
-            sg_traceback_kernel<<<(unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS), SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            if (sg_forward_version() == 2) sg_traceback_kernel<2><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            else sg_traceback_kernel<1><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
             sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
@@ -1093,13 +1112,20 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
     Device* d = ctx->devs[device_index];
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     cudaFuncAttributes fa{};
-    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg_xdrop_kernel));
     int blocks = 0;
-    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg_xdrop_kernel, SG_WARPS_PER_BLOCK * 32, 0));
+    if (sg_forward_version() == 2) {
+        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel));
+        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel, SG2_THREADS, 0));
+        info->threads_per_block = SG2_THREADS;
+        info->blocks_per_sm = blocks < 24 ? blocks : 24;
+    } else {
+        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg_xdrop_kernel));
+        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg_xdrop_kernel, SG_WARPS_PER_BLOCK * 32, 0));
+        info->threads_per_block = SG_WARPS_PER_BLOCK * 32;
+        info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
+    }
     info->fast_path = 0;
     info->regs_per_thread = fa.numRegs;
-    info->threads_per_block = SG_WARPS_PER_BLOCK * 32;
-    info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
     info->smem_bytes_per_block = (int)fa.sharedSizeBytes;
     info->sm_count = d->prop.multiProcessorCount;
     int khz = 0;

@@ -140,3 +140,60 @@ def test_emu_one_vs_many_matches_x32_golden():
             for fg in (0, 1):
                 assert lib.swemu_one_vs_many(q.ctypes.data, t.ctypes.data, m.ctypes.data, 1, out.ctypes.data, n, fg) >= 0
                 assert np.array_equal(out, z["scores"][it][:n].astype(np.int32)), (it, n, fg)
+
+
+# --------------------------------------------------------------------------- semi-global aligner (csrc/sg2_core.cuh)
+SG2_SRC = os.path.join(ROOT, "tests", "emu", "sg2_emu.cpp")
+SG2_LIB = os.path.join(ROOT, "tests", "emu", "libsg2emu.so")
+
+
+@pytest.fixture(scope="module")
+def sg2():
+    """The four-lanes-per-pair round of the semi-global kernel, run on the host as four coroutines in lock step."""
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{CSRC}", "-o", SG2_LIB, SG2_SRC], check=True)
+    lib = C.CDLL(SG2_LIB)
+    lib.swemu_sg2.restype = C.c_int
+    lib.swemu_sg2.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+
+    def run(a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        b = np.ascontiguousarray(b, dtype=np.uint8)
+        n = a.size
+        meta = np.zeros(4, np.int32)
+        ops = np.zeros(2 * n, np.uint8)
+        rc = lib.swemu_sg2(a.ctypes.data, b.ctypes.data, n, meta[0:].ctypes.data, meta[1:].ctypes.data, meta[2:].ctypes.data,
+                           ops.ctypes.data, meta[3:].ctypes.data)
+        assert rc == 0, rc
+        return int(meta[0]), int(meta[1]), int(meta[2]), ops[:meta[3]].copy()
+    return run
+
+
+def test_sg2_emu_equals_the_reference_fixtures(sg2):
+    from sg_common import load_cases
+    for c in load_cases():
+        score, ey, ex, ops = sg2(c["seq1"], c["seq2"])
+        assert (score, ey, ex, ops.size) == (c["score"], c["end_y"], c["end_x"], c["n_ops"]), c["name"]
+        assert np.array_equal(ops, c["ops"]), c["name"]
+
+
+def test_sg2_emu_equals_the_oracle_at_many_lengths(sg2, oracle):
+    rng = np.random.default_rng(20261018)
+    for length in (1, 2, 3, 7, 8, 9, 30, 31, 32, 33, 63, 64, 65, 100, 255, 256, 700, 1500):
+        for kind in range(4):
+            a = rng.integers(0, 4, length, dtype=np.uint8)
+            if kind == 0:
+                b = rng.integers(0, 4, length, dtype=np.uint8)                 # unrelated: the X-drop ends the pair early
+            elif kind == 1:
+                b = a.copy()                                                    # identical: the band runs down the diagonal
+            else:
+                rate = 0.03 if kind == 2 else 0.25
+                b = a.copy()
+                hit = rng.random(length) < rate
+                b[hit] = rng.integers(0, 4, int(hit.sum()), dtype=np.uint8)
+                if length > 8:
+                    cut = int(rng.integers(1, length // 2))
+                    b = np.concatenate([b[cut:], rng.integers(0, 4, cut, dtype=np.uint8)])   # a shift: gaps at the start
+            exp = oracle.semiglobal_xdrop(a, b)
+            got = sg2(a, b)
+            assert got[:3] == exp[:3], (length, kind)
+            assert np.array_equal(got[3], exp[3]), (length, kind)
