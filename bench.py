@@ -478,7 +478,20 @@ def run_stream_arm(args):
 # --------------------------------------------------------------------------- semi-global X-drop aligner
 SG_LEN = 16384
 SG_ROUNDS_NOMINAL = 2 * SG_LEN       # a pair aligned end to end runs one round per anti-diagonal
-SG_TRACE_BYTES_PER_ROUND = 8.125     # 2 x 32-bit masks + 1 move bit, written once and read once by the traceback
+SG_TRACE_BYTES_PER_ROUND = 8.125     # 64 direction bits + 1 move bit, written once and read once by the traceback
+SG_RECORD_BYTES_PER_ROUND = 16       # what the kernels move: one 16-byte record per round, written by the forward kernel, read by the traceback
+
+
+def sg_instr_counts():
+    """Warp instructions per warp-round (eight pairs advance one round) of the forward kernel, from the committed ncu
+    capture: total and ALU-pipe.  Fallback = the SASS count of the loop body."""
+    path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v7_summary.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v7_summary.json"
+    except (OSError, KeyError, ValueError):
+        return 163.0, 85.0, "SASS count of the loop body (cuobjdump)"
 
 
 def sg_cpu_reference(a, b, budget_s=20.0):
@@ -509,7 +522,7 @@ def run_semiglobal_arm(args):
     insert / delete, source.cpp:2750-2771) through the adaptive-banded X-drop aligner, score + traceback.
     value = alignments/s device-resident; e2e = swb200_semiglobal_xdrop_batch with pinned host arrays."""
     import swb200
-    n = args.pairs if args.pairs != 100_000_000 else 8192
+    n = args.pairs if args.pairs != 100_000_000 else 16384
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
@@ -542,9 +555,20 @@ def run_semiglobal_arm(args):
 
     def launch():
         ctx.semiglobal_xdrop_device(d_a, d_b, d_meta[0], d_meta[1], d_meta[2], d_meta[3], d_ops)
+
+    def launch_forward_only():              # score and end cell only: the forward kernel alone
+        ctx.semiglobal_xdrop_device(d_a, d_b, d_meta[0], d_meta[1], d_meta[2])
     for _ in range(max(3, args.warmup)):
         launch()
     torch.cuda.synchronize()
+    fwd_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launch_forward_only()
+    fwd_ev[0].record(stream)
+    for i in range(args.steps):
+        launch_forward_only()
+        fwd_ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    fwd_ms = fwd_ev[0].elapsed_time(fwd_ev[-1]) / args.steps
     sampler = ClockSampler(0)
     sampler.start()
     launches0 = ctx.launch_count
@@ -592,31 +616,39 @@ def run_semiglobal_arm(args):
         ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
     peaks = load_peaks()
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    # issue roofline: one warp instruction per clock per scheduler, 4 schedulers per SM
-    issue_peak = 4 * info["sm_count"] * sm_mhz * 1e6
+    # roofline of the forward kernel (the dominant one): its ALU pipe.  A warp-round advances eight pairs by one round;
+    # it needs `alu_wr` ALU-pipe warp instructions (ncu), and an SM retires 2 of those per clock (63.5 lanes, INT_PEAK.json).
+    instr_wr, alu_wr, instr_src = sg_instr_counts()
+    int_peak = json.load(open(os.path.join(ROOT, "profiles", "INT_PEAK.json")))
+    lanes = float(int_peak.get("alu_lanes_per_clk_per_sm", 63.5))
+    alu_peak = lanes * info["sm_count"] * sm_mhz * 1e6            # thread-level ALU-pipe instructions per second
+    warp_rounds_per_s = (n / 8.0) * SG_ROUNDS_NOMINAL / (fwd_ms * 1e-3)
+    alu_achieved = warp_rounds_per_s * alu_wr * 32.0
     rounds_per_s = n * SG_ROUNDS_NOMINAL / (ms * 1e-3)
-    instr_per_round = float(args.sg_instr_per_round)
-    trace_gbs = n * SG_ROUNDS_NOMINAL * SG_TRACE_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
+    trace_gbs = n * SG_ROUNDS_NOMINAL * SG_RECORD_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
     line = {
         "metric": "alignments_per_s", "value": n / (ms * 1e-3), "unit": "alignments/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "band_gcups": rounds_per_s * 32 / 1e9,
         "config": {"workload": "SURVEY.md 8(f4): adaptive-banded X-drop semi-global aligner (band 32, X 70, 1/1/1), score + traceback, "
                                f"{n} pairs of 16384-mers with 10/10/10 % mismatch/insert/delete (TestSemiGlobal's construction, source.cpp:2750-2771)",
-                   "pairs": n, "seq_len": SG_LEN, "l2": "inputs 268 MB + 2.1 GB of trace per launch > 126 MB L2, no flush needed", "kernel": info},
+                   "pairs": n, "seq_len": SG_LEN, "l2": f"inputs {2 * n * SG_LEN / 1e6:.0f} MB + {n * SG_ROUNDS_NOMINAL * 16 / 1e9:.1f} GB of round records per launch > 126 MB L2, no flush needed",
+                   "kernel": info},
         "clocks": clocks,
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n * SG_LEN,
                 "d2h_bytes_per_step": n * (16 + 2 * SG_LEN), "api": "swb200_semiglobal_xdrop_batch (C ABI, pinned host arrays; scores, end cells and move strings back)",
                 "equals_device_leg": e2e_ok},
         "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
-        "roofline": {"bound": "issue", "kernel": "swb::sg_xdrop_kernel", "achieved": rounds_per_s * instr_per_round / 1e12, "peak": issue_peak / 1e12,
-                     "unit": "T warp-instr/s", "frac": rounds_per_s * instr_per_round / issue_peak,
-                     "instr_per_round": instr_per_round, "rounds_per_launch": n * SG_ROUNDS_NOMINAL,
-                     "note": "one warp per pair, one round = one anti-diagonal of 32 cells; the chain of a round is serial, so the bound is the schedulers' issue rate "
-                             "(4 warp-instr/clk/SM), not HBM or the ALU lanes; instr_per_round from the ncu capture in profiles/",
+        "roofline": {"bound": "int_alu", "kernel": "swb::sg2_xdrop_kernel (forward pass; timed alone as the score-only call)",
+                     "achieved": alu_achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tinstr/s (thread-level ALU-pipe instructions)",
+                     "frac": alu_achieved / alu_peak, "avg_launch_ms": fwd_ms, "share_of_step": fwd_ms / ms,
+                     "alu_instr_per_warp_round": alu_wr, "instr_per_warp_round": instr_wr, "instr_src": instr_src,
+                     "warp_rounds_per_launch": (n / 8.0) * SG_ROUNDS_NOMINAL,
+                     "note": "four lanes per pair: one warp instruction serves eight pairs; a round is one serial chain per pair, so the kernel is bound by "
+                             "how many ALU-pipe instructions a round needs and by how many warps there are to overlap the chains (n / 8 warps), not by HBM",
                      "traffic": None,
                      "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2}},
+                             "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2, "record_bytes_per_round": SG_RECORD_BYTES_PER_ROUND * 2}},
         "verified": {"sample_equals_oracle_score_and_traceback": bool(ok), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n)},
     }
     if cpu is not None:
@@ -678,7 +710,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sg-instr-per-round", type=float, default=95.0, help="semiglobal: warp instructions per round of the kernel (from the ncu capture)")
     ap.add_argument("--pack-threads", type=int, default=None, help="host 2-bit packing lanes per GPU in the e2e leg (default: library auto; 0 = off)")
     ap.add_argument("--no-plain-e2e", action="store_true", help="skip the lanes-off comparison run of the e2e leg")
     ap.add_argument("--cpu-table", action="store_true", help="with --impl reference: scalar/simd4/simd7/simd9, 1 thread and all cores")

@@ -10,22 +10,26 @@
 // traceback masks are packed two cells per instruction and a warp advances EIGHT pairs per round.
 //   * Values live in the X-drop frame: u = value - T with T = max(best - 70, 1) (the reference's own
 //     trick for its 8-bit AVX2 forms, offset_diff at source.cpp:2661-2665), so every live cell is in 0..70
-//     and int16 never overflows at any length.  A dropped cell is the sentinel F = 0x807F (-32641):
-//         t2 = max(diag + sd, hor, ver)                   VIADD.16x2 + VIMNMX3.S16x2
-//         R  = umin(max(t2 - c, F), F)                    VIADDMNMX.S16x2 + VIMNMX.U16x2
-//     where sd = score + 1 - (T's last increment), c = 1 + (T's increment this round); the unsigned
-//     minimum maps every negative value (unsigned >= 0x807F) to F and keeps 0..72 -- the X-drop and the
-//     reference's "0 = dropped" in one instruction, with no compare/select.
+//     and int16 never overflows at any length.  Registers hold 4u; a dropped cell is the sentinel
+//     F = 0xC000 (-16384):
+//         t  = max(diag + sd, hor + 1, ver + 2)           VIADD.16x2 (FMA pipe) + VIMNMX3.S16x2
+//         t2 = t & ~3                                     LOP3
+//         R  = umin(max(t2 - 4c, F), F)                   VIADDMNMX.S16x2 + VIMNMX.U16x2
+//         R + (1,1), R + (2,2)                            2 x VIADD.16x2 (FMA pipe): next round's hor / ver
+//     where sd = 4 (score + 1 - (T's last increment)) + 3, c = 1 + (T's increment this round).  The two
+//     low bits are a TAG that rides through the maximum: among equal values the diagonal (3) beats up (2)
+//     beats left (1) -- the reference's traceback preference (source.cpp:1960-1969) -- so t & 3 IS the
+//     traceback evidence of the cell and no compare is needed.  The unsigned minimum maps every negative
+//     value (unsigned >= 0xC000; none is below F) to F and keeps 0..288: the X-drop and the reference's "0 = dropped" in
+//     one instruction, with no compare/select.
 //   * The band shift of the reference (alignr/permute2x128, source.cpp:2622,2632) is a funnel shift by
 //     16 or 0 bits per word (the amount is the direction, so the pairs of a warp do not diverge) plus ONE
 //     shuffle between neighbouring lanes that carries the boundary cell and the boundary base together.
 //   * The 32 bases of either sequence under the band are two registers per lane (a byte per cell); they
 //     shift by 8 or 0 bits; the match score of two cells is one PRMT through an 8-byte table indexed by
 //     a XOR b (the reference's pshufb table, source.cpp:2640-2641).
-//   * Traceback evidence, not band values, is stored (as in the warp-per-pair kernel): per cell "came from
-//     the diagonal" (t2 == diag + sd) and "came from above" (t2 == ver), as two packed compares (HSET2)
-//     gathered by one PRMT and three bit-selects: 4 bytes per lane per round, 16 bytes per pair per
-//     round, pos_y in the spare bits.
+//   * Traceback evidence, not band values, is stored: the 2-bit tag of every cell, gathered with four
+//     multiply-adds on the FMA pipe: 4 bytes per lane per round (16 per pair), pos_y in the spare bytes.
 //
 // Every function is SWB_HD and templated on an Env that supplies the lane index and the two shuffles, so
 // the same text runs on the device (real shuffles) and in tests/emu (four coroutines in lock step).
@@ -39,18 +43,17 @@
 namespace swb {
 
 #if defined(__CUDA_ARCH__)
-// 0xFFFF in every half where a == b.  HSET2 compares the halves as fp16; that equals integer equality because the
-// operands here are never NaN patterns (0x7C01.., 0xFC01..) and never 0x8000 (-0.0 == +0.0): live cells are
-// 0..72 and everything else lies in 0x8070..0x8082 (F and the few values around it).
-SWB_HD uint32_t veq2(uint32_t a, uint32_t b)
-{
-    return __heq2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-}
 SWB_HD uint32_t vminu2(uint32_t a, uint32_t b) { return __vminu2(a, b); }        // VIMNMX.U16x2
+// `keep` unless `take`, then the byte at p: a predicated load, no branch (the quads of a warp stay in step)
+SWB_HD uint32_t ld_u8_if(const uint8_t* p, bool take, uint32_t keep)
+{
+    asm volatile("{ .reg .pred t; setp.ne.u32 t, %2, 0; @t ld.global.nc.u8 %0, [%1]; }" : "+r"(keep) : "l"(p), "r"((uint32_t)take));
+    return keep;
+}
 SWB_HD uint32_t fsl(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }   // SHF.L.W
 SWB_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }   // SHF.R.W
 #else
-SWB_HD uint32_t veq2(uint32_t a, uint32_t b) { return (((a ^ b) & 0xffffu) ? 0u : 0xffffu) | (((a ^ b) >> 16) ? 0u : 0xffff0000u); }
+SWB_HD uint32_t ld_u8_if(const uint8_t* p, bool take, uint32_t keep) { return take ? (uint32_t)*p : keep; }
 SWB_HD uint32_t vminu2(uint32_t a, uint32_t b)
 {
     const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
@@ -61,22 +64,25 @@ SWB_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31u; return s ?
 #endif
 
 constexpr int SG2_X = 70;                          // X_THRESHOLD, source.cpp:1848
-constexpr uint32_t SG2_F = 0x807Fu;                // dropped / never reached
-constexpr uint32_t SG2_FF = 0x807F807Fu;
+constexpr uint32_t SG2_F = 0xC000u;                // dropped / never reached: far below every live value, and far enough
+constexpr uint32_t SG2_FF = 0xC000C000u;           //   from -32768 that no sum formed from it wraps around
+constexpr uint32_t SG2_UNTAG = 0xFFFCFFFCu;
 constexpr uint32_t SG2_PAD_A = 0xC4u;              // base bytes: code * 0x11, seq1 side has bit 7 set; the pads (4, 5)
 constexpr uint32_t SG2_PAD_B = 0x55u;              //   differ from every base and from each other (source.cpp:1913-1915)
 
 struct Sg2State {
-    uint32_t R[4];        // this round's cells 8q..8q+7 (word k = cells 2k | 2k+1 << 16), frame T, dropped = F
-    uint32_t H[4], V[4];  // the previous round's left / upper neighbours (views of the round before it)
+    uint32_t R1[4], R2[4];  // this round's cells 8q..8q+7 (word k = cells 2k | 2k+1 << 16): 4 (value - T), dropped = F,
+                          //   tagged 1 (as a left neighbour) and 2 (as an upper neighbour)
+    uint32_t H[4], V[4];  // the previous round's left / upper neighbours (views of the round before it), tagged 1 / 2
     uint32_t A[2], B[2];  // bases under the band: seq1 (byte c = cell c) and seq2
-    uint32_t Rb[4];       // t2 of the best round (to find the end cell)
+    uint32_t Rb[4];       // t2 of the best round (to find the end cell); best_m = its maximum
     uint32_t lut_lo, lut_hi;   // sd table: index 0 = match
     uint32_t right;       // the next round moves right (else down)
     uint32_t got;         // what enters this lane from its neighbour in the next round: bits 0-15 cell, 16-23 base
-    uint32_t next_raw;    // lanes 0 and 3: the next base to enter the band (code, or 4 / 5 = pad), loaded a round ahead
+    uint32_t next_raw;    // lanes 0 and 3: the next base to enter the band (code, or 4 / 5 = pad) ...
+    uint32_t next2_raw;   // ... and the one after it: a base is loaded two entries before it is used
     uint32_t role_base;   // F | (0x80 << 16 in lane 0)
-    int32_t cidx;         // index of next_raw in seq1 (lane 0) / seq2 (lane 3)
+    int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (lane 3)
     int32_t pos_y, pos_x; // the band's upper-right cell: (pos_y, pos_x - 31), source.cpp:1873-1874
     int32_t best, T, best_round, best_py, best_m;
 };
@@ -90,11 +96,11 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
 {
     const int q = env.q();
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { s.R[w] = SG2_FF; s.H[w] = SG2_FF; s.V[w] = SG2_FF; }
+    for (int w = 0; w < 4; ++w) { s.Rb[w] = SG2_FF; s.H[w] = SG2_FF + 0x00010001u; s.V[w] = SG2_FF + 0x00020002u; }
     s.T = 1;                                         // max(70 - 70, 1)
-    if (q == 3) s.R[3] = ((uint32_t)(SG2_X - 1) << 16) | SG2_F;
+    if (q == 3) s.Rb[3] = ((uint32_t)(4 * (SG2_X - 1)) << 16) | SG2_F;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) s.Rb[w] = s.R[w];
+    for (int w = 0; w < 4; ++w) { s.R1[w] = s.Rb[w] + 0x00010001u; s.R2[w] = s.Rb[w] + 0x00020002u; }
     // cell i holds seq1p[31 - i] = seq1[30 - i] (i = 31: pad) and seq2p[i] = pad
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -108,21 +114,23 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
         s.A[k] = a;
         s.B[k] = SG2_PAD_B * 0x01010101u;
     }
-    s.lut_lo = 2u; s.lut_hi = 0u;
+    s.lut_lo = 0x0303030Bu - 0x02020202u; s.lut_hi = 0x03030303u - 0x02020202u;      // round 1 moves right: diag carries tag 2
     s.pos_y = 0; s.pos_x = 31;
-    s.best = SG2_X; s.best_round = 0; s.best_py = 0; s.best_m = SG2_X - 1;
+    s.best = SG2_X; s.best_round = 0; s.best_py = 0; s.best_m = 4 * (SG2_X - 1);
     // bases enter at cell 0 on a down move (lane 0: seq1p[pos_y + 31] = seq1[pos_y + 30]) and at cell 31 on a
     // right move (lane 3: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
     s.role_base = SG2_F | (q == 0 ? 0x800000u : 0u);
     s.right = 1u;
     s.got = SG2_F | (SG2_PAD_B << 16);
-    s.cidx = 31;
-    s.next_raw = 4u;
+    s.cidx = 32;
+    s.next_raw = s.next2_raw = 4u;
     if (q == 0 && 31 < len) s.next_raw = seq1[31];
+    if (q == 0 && 32 < len) s.next2_raw = seq1[32];
     if (q == 3) {
         s.got = SG2_F | ((0 < len ? (uint32_t)seq2[0] : 5u) * 0x110000u);
-        s.cidx = 1;
+        s.cidx = 2;
         s.next_raw = (1 < len) ? (uint32_t)seq2[1] : 5u;
+        s.next2_raw = (2 < len) ? (uint32_t)seq2[2] : 5u;
     }
 }
 
@@ -145,10 +153,11 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     uint32_t D[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) D[w] = right ? s.V[w] : s.H[w];       // source.cpp:1892,1903
-    const uint32_t gh = got << 16, ga = got << 8, gb = got >> 16;
-    const uint32_t sD = right ? 0u : 16u, sR = 16u - sD, cD = sD >> 1, cR = sR >> 1;
-    s.H[3] = fsl(s.R[2], s.R[3], sD); s.H[2] = fsl(s.R[1], s.R[2], sD); s.H[1] = fsl(s.R[0], s.R[1], sD); s.H[0] = fsl(gh, s.R[0], sD);
-    s.V[0] = fsr(s.R[0], s.R[1], sR); s.V[1] = fsr(s.R[1], s.R[2], sR); s.V[2] = fsr(s.R[2], s.R[3], sR); s.V[3] = fsr(s.R[3], got, sR);
+    const uint32_t one = env.one(), zero = env.zero();     // a 1 and a 0 the compiler cannot see: they keep bookkeeping on the FMA pipe
+    const uint32_t gh = got * (one << 16) + 0x00010000u, ga = got << 8, gb = got >> 16, gv = got * one + 2u;
+    const uint32_t sR = s.right * (one << 4), sD = 16u - sR, cR = s.right * (one << 3), cD = 8u - cR;      // shift amounts: 16 / 8 or 0
+    s.H[3] = fsl(s.R1[2], s.R1[3], sD); s.H[2] = fsl(s.R1[1], s.R1[2], sD); s.H[1] = fsl(s.R1[0], s.R1[1], sD); s.H[0] = fsl(gh, s.R1[0], sD);
+    s.V[0] = fsr(s.R2[0], s.R2[1], sR); s.V[1] = fsr(s.R2[1], s.R2[2], sR); s.V[2] = fsr(s.R2[2], s.R2[3], sR); s.V[3] = fsr(s.R2[3], gv, sR);
     s.A[1] = fsl(s.A[0], s.A[1], cD); s.A[0] = fsl(ga, s.A[0], cD);
     s.B[0] = fsr(s.B[0], s.B[1], cR); s.B[1] = fsr(s.B[1], gb, cR);
     s.pos_y += right ? 0 : 1;
@@ -158,13 +167,13 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     uint32_t sd[4];
     sd[0] = prmt(s.lut_lo, s.lut_hi, x0); sd[1] = prmt(s.lut_lo, s.lut_hi, x0 >> 16);
     sd[2] = prmt(s.lut_lo, s.lut_hi, x1); sd[3] = prmt(s.lut_lo, s.lut_hi, x1 >> 16);
-    // ---- the cells (source.cpp:1916-1926) and what the traceback will find for them (source.cpp:1960-1969)
-    uint32_t t2[4], P[4];
+    // ---- the cells (source.cpp:1916-1926); the tag of the winner is what the traceback will find (source.cpp:1960-1969)
+    uint32_t t[4], t2[4], dsum[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        const uint32_t dsum = vadd2(D[w], sd[w]);
-        t2[w] = vmax3(dsum, s.H[w], s.V[w]);
-        P[w] = prmt(veq2(dsum, t2[w]), veq2(s.V[w], t2[w]), 0x6420u);       // 0xFF where equal: bytes d.lo d.hi u.lo u.hi
+        dsum[w] = vadd2(D[w], sd[w]);
+        t[w] = vmax3(dsum[w], s.H[w], s.V[w]);
+        t2[w] = t[w] & SG2_UNTAG;
     }
     // ---- the shuffle stage
     uint32_t m = vmax2(vmax3(t2[0], t2[1], t2[2]), t2[3]);
@@ -172,44 +181,58 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     const uint32_t m1 = env.shfl_xor(m, 1), m2 = env.shfl_xor(m, 2), m3 = env.shfl_xor(m, 3);
     const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[3], 3);
     const uint32_t gn = env.shfl(xr, q + 1), gp = env.shfl(xd, q - 1);
-    // ---- the record (independent of the shuffles)
-    const uint32_t y01 = (P[0] & 0x55555555u) | (P[1] & 0xAAAAAAAAu), y23 = (P[2] & 0x55555555u) | (P[3] & 0xAAAAAAAAu);
-    const uint32_t y = (y01 & 0x33333333u) | (y23 & 0xCCCCCCCCu);          // bit k of every nibble = word k
-    const uint32_t spread = (((uint32_t)s.pos_y & 0xffu) << 4) | (((uint32_t)s.pos_y & 0xff00u) << 12);
-    rec_row[4 * round + q] = (y & 0xF00FF00Fu) | spread;
-    // ---- round maximum (source.cpp:1925)
+    // ---- the record (independent of the shuffles): tags of cells 0,2,4,6 in byte 0, of 1,3,5,7 in byte 2, pos_y in bytes 1 and 3
+    // (tag = t - t2, no borrow between the halves: clearing bits never raises a half; summed as multiply-adds)
+    {
+        const uint32_t c4 = one << 2, c16 = one << 4, c64 = one << 6, mone = 0u - one;
+        // (dsum enters with weight 0: a second use keeps its add a VIADD on the FMA pipe instead of a fused add-max on the ALU pipe)
+        uint32_t neg = t2[0] * one + t2[1] * c4 + (dsum[0] + dsum[1] + dsum[2] + dsum[3]) * zero;
+        uint32_t acc = prmt((uint32_t)s.pos_y, 0u, 0x1404u) + t[0] * one;
+        neg = t2[2] * c16 + neg; acc = t[1] * c4 + acc;
+        neg = t2[3] * c64 + neg; acc = t[2] * c16 + acc;
+        acc = t[3] * c64 + acc;
+        rec_row[4 * round + q] = neg * mone + acc;
+    }
+    // ---- round maximum (source.cpp:1925).  In the X-drop frame the best so far sits at 69 or 70, a cell is at most
+    // two above it, and the threshold moves exactly when a cell reaches 72 -- so the amount subtracted this round,
+    // c = 1 + off, comes from one packed compare; the bookkeeping of the best (below) is off the critical path.
     m = vmax2(vmax3(m, m1, m2), m3);
+    const uint32_t z = vaddmax2(m, 0xFEE1FEE1u, 0u);       // max(m - 287, 0) per half: 1 iff the half is 4 * 72
+    const uint32_t off = (z | (z >> 16)) & 1u;
+    // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
+    const uint32_t nc = 0xFFFCFFFCu - off * 0x00040004u;   // (-4c, -4c)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t r = vminu2(vaddmax2(t2[w], nc, SG2_FF), SG2_FF);
+        s.R1[w] = vadd2(r, 0x00010001u);
+        s.R2[w] = vadd2(r, 0x00020002u);
+    }
+    // ---- the next round's direction and what enters this lane then
+    const int32_t t31 = sg2_half(e31, 1);
+    const bool rn = sg2_half(e0, 0) < t31 && t31 > (int32_t)(4u * off);   // t31 - 4c >= 0 (multiples of 4)
+    const bool edge = rn ? (q == 3) : (q == 0);            // the band's end: a dropped cell and a new base come in
+    uint32_t cand = rn ? gn : gp;
+    if (edge) cand = s.next_raw * 0x110000u + s.role_base;
+    s.got = vminu2(vaddmax2(cand, nc & 0xffffu, 0x80000000u | SG2_F), 0xFFFF0000u | SG2_F);   // drop the cell; the upper half (base, stray byte) passes
+    s.right = rn ? 1u : 0u;
+    // the base after next, branch-free: shift the two staged bases, load the new one under a predicate
+    s.cidx += edge ? 1 : 0;
+    s.next_raw = edge ? s.next2_raw : s.next_raw;
+    s.next2_raw = ld_u8_if(role_seq + s.cidx, edge && (uint32_t)s.cidx < (uint32_t)len, edge ? (q == 0 ? 4u : 5u) : s.next2_raw);
+    // ---- the best so far (source.cpp:1928-1931: strict, the FIRST round that reaches it)
     const int32_t rmax = sg2_half(m, 0) > sg2_half(m, 1) ? sg2_half(m, 0) : sg2_half(m, 1);
-    const int32_t amax = rmax - 1 + s.T;                   // with the reference's +70 offset
-    if (amax > s.best) {                                   // strict: the FIRST round that reaches the best (source.cpp:1928-1931)
+    const int32_t amax = (rmax >> 2) - 1 + s.T;            // with the reference's +70 offset
+    if (amax > s.best) {
         s.best = amax; s.best_round = round; s.best_py = s.pos_y; s.best_m = rmax;
 #pragma unroll
         for (int w = 0; w < 4; ++w) s.Rb[w] = t2[w];
     }
-    const int32_t Tn = (s.best - SG2_X > 1) ? s.best - SG2_X : 1;
-    const uint32_t off = (uint32_t)(Tn - s.T);             // 0 or 1
-    s.T = Tn;
-    // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
-    const uint32_t nc = 0xFFFFFFFFu - off * 0x00010001u;   // (-c, -c), c = 1 + off
-#pragma unroll
-    for (int w = 0; w < 4; ++w) s.R[w] = vminu2(vaddmax2(t2[w], nc, SG2_FF), SG2_FF);
-    // ---- the next round's direction and what enters this lane then
-    const int32_t t31 = sg2_half(e31, 1);
-    const bool rn = sg2_half(e0, 0) < t31 && t31 > (int32_t)off;          // t31 - c >= 0
-    const bool edge = rn ? (q == 3) : (q == 0);            // the band's end: a dropped cell and a new base come in
-    uint32_t cand = rn ? gn : gp;
-    if (edge) {
-        cand = s.next_raw * 0x110000u + s.role_base;
-        ++s.cidx;
-        s.next_raw = (q == 0) ? 4u : 5u;
-        if ((uint32_t)s.cidx < (uint32_t)len) s.next_raw = role_seq[s.cidx];
-    }
-    s.got = vminu2(vaddmax2(cand, nc & 0xffffu, SG2_FF), SG2_FF);          // drop the cell, leave the base
-    s.right = rn ? 1u : 0u;
-    // next round's diagonal inputs are one frame older: sd = score + 1 - off
-    const uint32_t noff = 0u - off;
-    s.lut_lo = (noff & 0xFFFFFF03u) ^ 2u;                  // off = 0: 02 00 00 00, off = 1: 01 FF FF FF
-    s.lut_hi = noff;
+    s.T += (int32_t)off;                                   // T = max(best - 70, 1)
+    // next round's diagonal inputs are one frame older and carry the tag of the view they come from (ver 2 on a
+    // right move, hor 1 on a down move): sd = 4 (score + 1 - off) + 3 - that tag
+    const uint32_t dtag = (rn ? 2u : 1u) * 0x01010101u;
+    s.lut_lo = 0x0303030Bu - off * 0x03030404u - dtag;     // off = 0: 0B 03 03 03, off = 1: 07 FF FF FF, less the tag
+    s.lut_hi = 0x03030303u - off * 0x03030304u - dtag;     //          03 03 03 03,          FF FF FF FF
     return amax > 0;
 }
 
@@ -235,16 +258,14 @@ SWB_HD uint32_t sg2_finish(const Sg2State& s, Env& env, int32_t& score, int32_t&
 // rec = the four lane words of round r = y + x.  Returns the op: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).
 SWB_HD uint32_t sg2_tb_step(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int& y, int& x, int& r)
 {
-    const int py = (int)(((r0 >> 4) & 0xffu) | ((r0 >> 12) & 0xff00u));
+    const int py = (int)(((r0 >> 8) & 0xffu) | ((r0 >> 16) & 0xff00u));
     const int o = 31 - (y - py);                           // band element of (y, x) in round r (source.cpp:1947)
     const uint32_t w = (o & 16) ? ((o & 8) ? r3 : r2) : ((o & 8) ? r1 : r0);
-    const int pos = ((o & 7) >> 1) + 12 * (o & 1);
-    const uint32_t d = (w >> pos) & 1u;
-    const uint32_t u = (w >> (pos + 16)) & 1u & ~d;
-    y -= (int)(d | u);
-    x -= (int)(1u - u);
-    r -= 1 + (int)d;
-    return 2u - 2u * d - u;
+    const uint32_t code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;      // 3 = diagonal, 2 = up, 1 = left
+    y -= (int)(code >> 1);
+    x -= (int)(code != 2u);
+    r -= 1 + (int)(code == 3u);
+    return 3u - code;
 }
 
 } // namespace swb

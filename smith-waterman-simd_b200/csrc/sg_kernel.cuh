@@ -11,28 +11,26 @@
 // (source.cpp:1928-1931, 1953-1954), traceback preferring diagonal > up > left (source.cpp:1958-1971).
 //
 // This is not a translation of the AVX2 code.  The mapping is the one the band suggests on a GPU:
-//   * ONE WARP PER PAIR, lane i = band element i (31 = upper-right end).  The reference's byte
-//     shifts across a 256-bit register (alignr/permute2x128, source.cpp:2622,2632) are SHFL.UP/DOWN,
-//     its five-step horizontal max (source.cpp:2656-2660) is one REDUX.MAX, and the direction
-//     decision reads lanes 0 and 31.
-//   * Values are plain int32 with the reference's +70 offset (0 = dropped / never reached), so the
-//     8-bit renormalisation of the AVX2 forms (offset_diff, source.cpp:2661-2665) does not exist.
-//   * The reference keeps the whole band history (1 MB of uint8 per pair, source.cpp:2591) and
-//     re-derives each traceback step by comparing scores.  Here the forward pass records, per round,
-//     two 32-bit masks -- "this cell's value came from the diagonal" / "... from above", evaluated
-//     with the reference's own comparisons and preference order -- plus the band's pos_y: one 16-byte
-//     record per round (lane 0 stores it) instead of the 32 band values.
-//   * The traceback is a second kernel, ONE THREAD PER PAIR: the walk is serial (as in the reference),
-//     so a warp spent on it would execute every instruction for one live lane.  A thread reads its
-//     pair's records backwards -- consecutive 16-byte records, so seven of eight come from the line
-//     the previous step brought into L1 -- and emits one op per step: 0 = diagonal, 1 = down (y+1),
-//     2 = right (x+1).  The ops land right-aligned in the pair's output row in forward order and
-//     the warp then shifts each of its 32 rows to the left edge together.
+//   * FOUR LANES PER PAIR, eight band cells per lane in packed int16x2 registers (sg2_core.cuh): a warp advances
+//     eight pairs per round.  The reference's byte shifts across a 256-bit register (alignr/permute2x128,
+//     source.cpp:2622,2632) are funnel shifts inside a lane plus one shuffle between neighbouring lanes; its
+//     five-step horizontal max (source.cpp:2656-2660) is three shuffles and two packed max.
+//   * Values live in the X-drop frame (value - max(best - 70, 1)), as in the reference's 8-bit AVX2 forms
+//     (offset_diff, source.cpp:2661-2665), so int16 holds at any length; a dropped cell is a sentinel that one
+//     unsigned minimum produces.
+//   * The reference keeps the whole band history (1 MB of uint8 per pair, source.cpp:2591) and re-derives each
+//     traceback step by comparing scores.  Here the forward pass records, per round and cell, the OUTCOME of those
+//     comparisons -- "this cell's value came from the diagonal" / "... from above", evaluated with the reference's
+//     own comparisons and preference order -- plus the band's pos_y: 16 bytes per round (4 per lane).
+//   * The traceback is a second kernel, ONE THREAD PER PAIR: the walk is serial (as in the reference), so a warp
+//     spent on it would execute every instruction for one live lane.  A thread reads its pair's records backwards
+//     -- consecutive 16-byte records, streamed through shared memory ahead of the walk -- and emits one op per
+//     step: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).  The ops land right-aligned in the pair's output row in
+//     forward order and a third kernel shifts each row to the left edge.
 //
 // HBM layout: seq1, seq2 [n][len] byte codes 0..3 (the reference's std::array<uint8_t,16384>, len = 16384);
-// scratch: per resident warp of the forward kernel the padded sequence copies (sg_warp_bytes), per PAIR
-// of a launch the round records (sg_trace_bytes); outputs score/end_y/end_x/n_ops [n] int32 and
-// ops [n][2*len] bytes (optional).
+// scratch: per PAIR of a launch the round records (sg_trace_bytes) plus one spare row; outputs
+// score/end_y/end_x/n_ops [n] int32 and ops [n][2*len] bytes (optional).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,31 +38,10 @@
 
 namespace swb {
 
-constexpr int SG_BAND = 32;         // BANDWIDTH, source.cpp:1848
-constexpr int SG_X = 70;            // X_THRESHOLD, source.cpp:1848
-constexpr int SG_WARPS_PER_BLOCK = 4;
-constexpr int SG_NEG = -(1 << 28);  // a dropped / never reached cell (the reference's 0); any valid value is >= 1
-constexpr int SG_PAD = 128;         // padded sequence copies hold 2*len + SG_PAD elements: the band never indexes beyond that
-
 // rounds are numbered 0 .. 2*len (MAX_ROUND = (len+1)*2-1, source.cpp:1872); rounded up to a chunk of 32
 __host__ __device__ inline uint32_t sg_rounds_cap(int len) { return ((uint32_t)(2 * len + 1) + 31u) & ~31u; }
-// elements (uint16) of one padded sequence copy: positions run to 31 + 2*len + 1 at most (one move per round)
-__host__ __device__ inline size_t sg_padded_len(int len) { return (2 * (size_t)len + SG_PAD + 127) & ~(size_t)127; }
-// per resident warp: the padded copies of seq1 and seq2 (uint16 per base)
-__host__ __device__ inline size_t sg_warp_bytes(int len) { return 2 * sg_padded_len(len) * 2; }
-// per pair of a launch: [rounds_cap] uint4 records {diagonal mask, up mask, pos_y, round}; record 0 = the end cell
+// per pair of a launch: [rounds_cap] uint4 records (four lane words, sg2_core.cuh); record 0 = where the traceback starts
 __host__ __device__ inline size_t sg_trace_bytes(int len) { return (size_t)sg_rounds_cap(len) * 16; }
-
-// element `idx` of a 16-bit array as base + 2*idx in one mad.wide (two LEA instructions); left to the compiler the
-// same address costs five ALU-pipe instructions (64-bit add of the lane offset, doubling, carry).
-__device__ __forceinline__ int sg_ld16(const uint16_t* base, unsigned idx)
-{
-    unsigned long long addr;
-    unsigned short v;
-    asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(addr) : "r"(idx), "l"(base));
-    asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(addr) : "memory");
-    return (int)v;
-}
 
 struct SgOut {
     int32_t* score;     // [n]  best score (offset removed)
@@ -74,104 +51,6 @@ struct SgOut {
     uint8_t* ops;       // [n][2*len], nullable: score and end cell only
 };
 
-// Instruction count is what bounds this kernel (one dependent chain per round, thousands of warps to
-// hide its latency), so the round is written for few instructions, not for a short chain:
-//   * dropped cells are a large negative constant, so "if (x != 0)" guards vanish and
-//     v = max(diag + s, hor - 1, ver - 1) = max(diag + s + 1, max(hor, ver)) - 1 is 4 instructions;
-//   * only the shuffle and the one sequence character that the chosen direction needs are issued;
-//   * sequences are copied once per pair into padded scratch (the reference's seq1p/seq2p,
-//     source.cpp:1859-1870), so a character is one address add and one load, no bounds test;
-//   * lane 0 stores the round's record {diagonal mask, up mask, pos_y, round} as one 16-byte store.
-__global__ void __launch_bounds__(SG_WARPS_PER_BLOCK * 32)
-sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
-                uint8_t* __restrict__ warp_scratch, uint4* __restrict__ traces, const SgOut out)
-{
-    const int lane = (int)(threadIdx.x & 31u);
-    const unsigned long long warp = (unsigned long long)blockIdx.x * SG_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * SG_WARPS_PER_BLOCK;
-    const uint32_t rounds_cap = sg_rounds_cap(len);
-    uint16_t* const seq1p = reinterpret_cast<uint16_t*>(warp_scratch + warp * sg_warp_bytes(len));   // seq1p[k] = seq1[k-1]
-    uint16_t* const seq2p = seq1p + sg_padded_len(len);                         // seq2p[k] = seq2[k-32]
-    const int max_round = 2 * len + 1;          // rounds run while round < MAX_ROUND (source.cpp:1872,1886)
-    const unsigned FULL = 0xffffffffu;
-    // this lane's window into the padded copies: element `lane` of a band at (pos_y, pos_x) reads
-    // seq1p[pos_y + 31 - lane] and seq2p[pos_x - 31 + lane] (source.cpp:1913).
-    const uint16_t* const pa = seq1p + 31 - lane;
-    const uint16_t* const pb = seq2p - 31 + lane;
-    const int plen = (int)sg_padded_len(len);
-    // The pads behind the sequences never change: written once per launch.  The two pads differ so that
-    // pad never matches pad and one compare gives the score (source.cpp:1913-1915: padding scores -MISMATCH).
-    // The reference stops a pair when the band's corner leaves the padded arrays (source.cpp:1897,1908); every
-    // cell of such a round lies outside the matrix and can change neither the score nor the traceback, so
-    // here the pads are simply long enough for any walk and those few rounds run until the X-drop ends them.
-    for (int k = len + lane; k < plen; k += 32) { seq1p[k] = 0xF0; seq2p[k] = 0xF1; }
-    // edge lanes receive a dropped cell from outside the band (source.cpp:1895,1906)
-    const bool is31 = lane == 31, is0 = lane == 0;
-
-    for (unsigned long long p = warp; p < n; p += n_warps) {
-        // ---- padded copies of this pair
-        {
-            const uint8_t* const s1 = seq1 + p * (unsigned long long)len;
-            const uint8_t* const s2 = seq2 + p * (unsigned long long)len;
-            for (int k = lane; k < len + 64; k += 32) {
-                const int k1 = k - 1, k2 = k - 32;
-                seq1p[k] = ((unsigned)k1 < (unsigned)len) ? (uint16_t)__ldg(s1 + k1) : (uint16_t)0xF0;
-                seq2p[k] = ((unsigned)k2 < (unsigned)len) ? (uint16_t)__ldg(s2 + k2) : (uint16_t)0xF1;
-            }
-        }
-        __syncwarp();
-        uint4* const trace = traces + p * rounds_cap;
-
-        int res = is31 ? SG_X : SG_NEG;             // dp[31] = X_THRESHOLD (source.cpp:1877)
-        int hor = SG_NEG, ver = SG_NEG;
-        unsigned now_y = 0, now_x = 31;
-        int best = SG_X, best_round = 0, best_py = 0, thr = 1;
-        uint32_t best_hit = 0x80000000u;
-        int ca = pa[now_y], cb = pb[now_x];
-
-        int round = 1;
-        for (; round < max_round; ++round) {
-            // ---- direction (source.cpp:1883-1911): right iff result[0] < result[31]
-            const int r31 = __shfl_sync(FULL, res, 31);
-            int diag;
-            if (__any_sync(FULL, is0 && res < r31)) {
-                diag = ver; hor = res;
-                ver = __shfl_down_sync(FULL, res, 1);                    // result[i+1]
-                if (is31) ver = SG_NEG;
-                cb = sg_ld16(pb, ++now_x);
-            } else {
-                diag = hor; ver = res;
-                hor = __shfl_up_sync(FULL, res, 1);                      // result[i-1]
-                if (is0) hor = SG_NEG;
-                ca = sg_ld16(pa, ++now_y);
-            }
-            // ---- the 32 cells of the round (source.cpp:1916-1926)
-            const int dsum = diag + ((ca == cb) ? 2 : 0);                // diag + s + 1
-            const int v1 = max(dsum, max(hor, ver));
-            const int v = v1 - 1;
-            const int rmax = __reduce_max_sync(FULL, v);
-            // what the reference's traceback will find for this cell (source.cpp:1960-1969): diagonal first, then up
-            const uint32_t dmask = __ballot_sync(FULL, v1 == dsum), umask = __ballot_sync(FULL, v1 == ver);
-            if (best < rmax) {                                           // strict: the FIRST round that reaches the best (source.cpp:1928-1931)
-                best = rmax; best_round = round; best_py = (int)now_y;
-                best_hit = __ballot_sync(FULL, v == rmax);               // its upper-right-most cell is the end (source.cpp:1953-1954)
-                thr = max(best - SG_X, 1);
-            }
-            res = (v < thr) ? SG_NEG : v;                                // X-drop, and values <= 0 are "dropped" too (source.cpp:1918,1933-1936)
-            if (is0) trace[round] = make_uint4(dmask, umask, now_y, (uint32_t)round);
-            if (rmax <= 0) break;                                        // everything dropped (source.cpp:1938-1941)
-        }
-        const int best_lane = 31 - __clz(best_hit);
-        const int end_y = best_py + 31 - best_lane;
-        const int end_x = (best_round - best_py) - 31 + best_lane;     // pos_x - 31 = round - pos_y (pos_x = 31 + #right moves)
-        if (is0) {
-            out.score[p] = best - SG_X; out.end_y[p] = end_y; out.end_x[p] = end_x;
-            trace[0] = make_uint4((uint32_t)best_round, (uint32_t)best_py, (uint32_t)end_y, (uint32_t)end_x);   // where the traceback starts
-        }
-        __syncwarp();      // the padded copies are rewritten for the next pair
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Forward kernel, four lanes per pair (sg2_core.cuh): a warp advances eight pairs per round.  Quads of a warp
 // run their pairs side by side and pick up the next eight together (pairs of similar length finish together;
@@ -179,18 +58,20 @@ sg_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ se
 constexpr int SG2_THREADS = 32;
 
 struct Sg2DevEnv {
-    int lane4;
+    int lane4; uint32_t one_, zero_;
     __device__ __forceinline__ int q() const { return lane4; }
+    __device__ __forceinline__ uint32_t one() const { return one_; }
+    __device__ __forceinline__ uint32_t zero() const { return zero_; }
     __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
     __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 };
 
 __global__ void __launch_bounds__(SG2_THREADS)
 sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
-                 uint4* __restrict__ traces, const SgOut out)
+                 uint4* __restrict__ traces, const SgOut out, const uint32_t one, const uint32_t zero)
 {
     const unsigned lane = threadIdx.x & 31u;
-    Sg2DevEnv env{(int)(lane & 3u)};
+    Sg2DevEnv env{(int)(lane & 3u), one, zero};
     const unsigned long long warp = ((unsigned long long)blockIdx.x * SG2_THREADS + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * SG2_THREADS) >> 5;
     const uint32_t rounds_cap = sg_rounds_cap(len);
@@ -210,7 +91,7 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
         const uint8_t* const role = env.q() == 0 ? s1 : s2;
         for (int round = 1; round < max_round; ++round) {
             const bool go = sg2_round(s, env, role, len, round, rec_row);
-            if (!__any_sync(0xffffffffu, go)) break;
+            if ((round & 3) == 0 && !__any_sync(0xffffffffu, go)) break;      // a finished pair stays finished: asking every fourth round is enough
         }
         int32_t score, end_y, end_x;
         const uint32_t rec0 = sg2_finish(s, env, score, end_y, end_x);
@@ -239,7 +120,6 @@ __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
-template <int FMT>      // record format: 1 = {diagonal mask, up mask, pos_y, round} (warp per pair), 2 = four lane words (sg2_core.cuh)
 __global__ void __launch_bounds__(SG_TB_THREADS)
 sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
 {
@@ -283,17 +163,7 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
             asm volatile("cp.async.wait_group 4;" ::: "memory");
         }
         const uint4 rec = *slot_of(r >> 3, r & 7);
-        if (FMT == 2) {
-            row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(rec.x, rec.y, rec.z, rec.w, y, x, r);
-        } else {                                        // {diagonal mask, up mask, pos_y of round r, r}
-            const int o = 31 - (y - (int)rec.z);            // band element of (y,x) in round r (source.cpp:1947)
-            const uint32_t d = (rec.x >> o) & 1u;           // diagonal first, then up, else left (source.cpp:1960-1969)
-            const uint32_t u = (rec.y >> o) & 1u & ~d;
-            row[cap - 1u - n_ops] = (uint8_t)(2u - 2u * d - u);             // 0 = diagonal, 1 = down, 2 = right
-            y -= (int)(d | u);
-            x -= (int)(1u - u);
-            r -= 1 + (int)d;
-        }
+        row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(rec.x, rec.y, rec.z, rec.w, y, x, r);      // 0 = diagonal, 1 = down, 2 = right
         ++n_ops;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -89,11 +89,9 @@ struct Device {
     Slot slots[kSlots];
     std::mutex mu;                   // one host batch at a time per GPU
     unsigned long long* d_bad = nullptr;
-    // semi-global aligner: per-resident-warp trace slots, and two staging slots for host batches
+    // semi-global aligner: round-record scratch, and four staging slots for host batches
     struct SgScratch {
-        uint8_t* warp = nullptr;         // padded sequence copies, one slot per resident warp of the forward kernel
-        size_t warp_bytes = 0;
-        uint4* traces = nullptr;         // round records, one slot per pair of a launch
+        uint4* traces = nullptr;         // round records, one row per pair of a launch + one spare row
         size_t trace_bytes = 0;
     } sg_dev;                            // scratch of the device-resident entry
     struct SgSlot {
@@ -277,8 +275,7 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -490,13 +487,6 @@ int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
         const int rc = lane_alloc(ctx, ln);
         if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
             stop_lanes(d);
-        cudaFree(d->sg_dev.warp);
-        cudaFree(d->sg_dev.traces);
-        for (auto& g : d->sg_slots) {
-            cudaFree(g.scratch.warp); cudaFree(g.scratch.traces);
-            if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
-            cudaFree(g.d_seq1); cudaFree(g.d_seq2); cudaFree(g.d_ops); cudaFree(g.d_meta);
-        }
             d->pool_stop = false;
             return rc;
         }
@@ -536,35 +526,8 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
 
 // ---------------------------------------------------------------------------------------------
 // Semi-global X-drop aligner (sg_kernel.cuh)
-constexpr int kSgBlocksPerSmDefault = 8;          // 32 warps = 32 pairs in flight per SM
-
-int sg_blocks_per_sm()
-{
-    static const int v = [] {
-        const char* e = getenv("SWB200_SG_BLOCKS");       // tuning knob (1..16 blocks of 4 warps)
-        const int x = e ? atoi(e) : kSgBlocksPerSmDefault;
-        return x < 1 ? 1 : (x > 16 ? 16 : x);
-    }();
-    return v;
-}
-#define kSgBlocksPerSm sg_blocks_per_sm()
-
-int sg_forward_version()
-{
-    static const int v = [] {
-        const char* e = getenv("SWB200_SG_FORWARD");      // 2 = four lanes per pair (sg2_core.cuh), 1 = warp per pair
-        return (e && atoi(e) == 1) ? 1 : 2;
-    }();
-    return v;
-}
-constexpr int kSgMaxLen = 1 << 15;                // scores stay far inside int32; scratch = 16.3 bytes per base per resident warp
-
-int sg_grid(const Device* d, uint64_t n)
-{
-    const uint64_t resident = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
-    const uint64_t need = (n + SG_WARPS_PER_BLOCK - 1) / SG_WARPS_PER_BLOCK;
-    return (int)(need < resident ? need : resident);
-}
+constexpr int kSgMaxLen = 1 << 15;                // pos_y <= len + 1 must fit the 16 bits it has in a round record
+constexpr int kSgBlocksPerSm = 24;                // resident warps per SM of the forward kernel (one warp = eight pairs)
 
 constexpr size_t kSgTraceBudget = 10ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 20 460 pairs)
 
@@ -576,20 +539,12 @@ uint64_t sg_pairs_per_launch(int len)
 
 int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len, uint64_t n)
 {
-    const size_t need_warp = (size_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK * sg_warp_bytes(len);
     const uint64_t pairs = n < sg_pairs_per_launch(len) ? n : sg_pairs_per_launch(len);
     const size_t need_trace = (pairs + 1) * sg_trace_bytes(len);      // + the spare row of sg2_xdrop_kernel
-    const bool grow_warp = need_warp > sc.warp_bytes;
     const bool grow_trace = need_trace > sc.trace_bytes;
-    if (!grow_warp && !grow_trace) return SWB200_OK;
+    if (!grow_trace) return SWB200_OK;
     SWB_CUDA(ctx, cudaDeviceSynchronize());
-    if (grow_warp) {
-        cudaFree(sc.warp);
-        sc.warp = nullptr; sc.warp_bytes = 0;
-        SWB_CUDA(ctx, cudaMalloc(&sc.warp, need_warp));
-        sc.warp_bytes = need_warp;
-    }
-    if (grow_trace) {
+    {
         cudaFree(sc.traces);
         sc.traces = nullptr; sc.trace_bytes = 0;
         SWB_CUDA(ctx, cudaMalloc(&sc.traces, need_trace));
@@ -611,20 +566,14 @@ int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* 
         const uint64_t m = (n - c0 < per) ? n - c0 : per;
         SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
         const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);
-        if (sg_forward_version() == 2) {
-            const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
-            const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * 24;
-            sg2_xdrop_kernel<<<(unsigned)(need < cap ? need : cap), SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
-                                                                                         sc.traces, out);
-        } else {
-            sg_xdrop_kernel<<<sg_grid(d, m), SG_WARPS_PER_BLOCK * 32, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
-                                                                               sc.warp, sc.traces, out);
-        }
+        const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
+        const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
+        sg2_xdrop_kernel<<<(unsigned)(need < cap ? need : cap), SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
+                                                                                     sc.traces, out, 1u, 0u);
         SWB_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (d_ops) {
-            if (sg_forward_version() == 2) sg_traceback_kernel<2><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
-            else sg_traceback_kernel<1><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            sg_traceback_kernel<<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
             sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
@@ -670,7 +619,7 @@ int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t*
     // chunk: half a resident wave of pairs (at least 32 MiB of sequence per array); the range is cut in equal chunks.
     // Two half-wave forward kernels from different slots fill the machine together, and the short chunks keep the
     // exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
-    const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm * SG_WARPS_PER_BLOCK;
+    const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * 64;      // pairs that give every scheduler two warps of the forward kernel
     uint64_t chunk = (32ull << 20) / (uint64_t)len;
     if (chunk < wave / 2) chunk = wave / 2;
     if (chunk > sg_pairs_per_launch(len)) chunk = sg_pairs_per_launch(len);
@@ -843,6 +792,12 @@ void swb200_shutdown(swb200_ctx* ctx)
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         cudaFree(d->d_bad);
+        cudaFree(d->sg_dev.traces);
+        for (auto& g : d->sg_slots) {
+            if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
+            cudaFree(g.scratch.traces);
+            cudaFree(g.d_seq1); cudaFree(g.d_seq2); cudaFree(g.d_ops); cudaFree(g.d_meta);
+        }
         delete d;
     }
     delete ctx;
@@ -1113,17 +1068,10 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     cudaFuncAttributes fa{};
     int blocks = 0;
-    if (sg_forward_version() == 2) {
-        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel));
-        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel, SG2_THREADS, 0));
-        info->threads_per_block = SG2_THREADS;
-        info->blocks_per_sm = blocks < 24 ? blocks : 24;
-    } else {
-        SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg_xdrop_kernel));
-        SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg_xdrop_kernel, SG_WARPS_PER_BLOCK * 32, 0));
-        info->threads_per_block = SG_WARPS_PER_BLOCK * 32;
-        info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
-    }
+    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel));
+    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel, SG2_THREADS, 0));
+    info->threads_per_block = SG2_THREADS;
+    info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
     info->fast_path = 0;
     info->regs_per_thread = fa.numRegs;
     info->smem_bytes_per_block = (int)fa.sharedSizeBytes;

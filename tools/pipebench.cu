@@ -27,6 +27,12 @@ __device__ __forceinline__ unsigned f_iadd3(unsigned a,unsigned b,unsigned c){un
 __device__ __forceinline__ unsigned f_lds(unsigned addr){unsigned d; asm volatile("ld.volatile.shared.u32 %0,[%1];":"=r"(d):"r"(addr)); return d;}
 __device__ __forceinline__ unsigned f_shfl(unsigned a){unsigned d; asm volatile("shfl.sync.up.b32 %0,%1,1,0,0xffffffff;":"=r"(d):"r"(a)); return d;}
 
+__device__ __forceinline__ unsigned f_shf(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("shf.l.wrap.b32 %0,%1,%2,%3;":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_hset2(unsigned a,unsigned b){unsigned d; asm volatile("set.eq.u32.f16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
+__device__ __forceinline__ unsigned f_imadhi(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("mad.hi.u32 %0,%1,%2,%3;":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_sel(unsigned a,unsigned b,unsigned c){unsigned d; asm volatile("{.reg .pred t; setp.ne.u32 t,%3,0; selp.b32 %0,%1,%2,t;}":"=r"(d):"r"(a),"r"(b),"r"(c)); return d;}
+__device__ __forceinline__ unsigned f_vminu(unsigned a,unsigned b){unsigned d; asm volatile("min.u16x2 %0,%1,%2;":"=r"(d):"r"(a),"r"(b)); return d;}
+
 constexpr int NCH = 8;      // independent chains per thread
 constexpr int UNROLL = 8;   // body repetitions per loop iteration
 
@@ -116,6 +122,16 @@ __global__ void __launch_bounds__(256) bench(unsigned* out, const unsigned* in, 
                     x[c] = f_hmnmx2(f_hmnmx2(t, y[c]), r);
                 }
                 if (MIX == 28) { x[c] = f_hmnmx2(x[c], y[c]); y[c] = f_viaddmnmx(y[c], p, x[c]); }        // HMNMX2 + VIADDMNMX
+                if (MIX == 29) { x[c] = f_shf(x[c], y[c], q); y[c] = f_shf(y[c], x[c], p); }               // SHF.L.W variable
+                if (MIX == 30) { x[c] = f_hset2(x[c], y[c]); y[c] = f_hset2(y[c], p); }                  // HSET2
+                if (MIX == 31) { x[c] = f_hset2(x[c], y[c]); y[c] = f_prmt(y[c], p, x[c]); }             // HSET2 + PRMT
+                if (MIX == 32) { x[c] = f_shf(x[c], y[c], q); y[c] = f_imad(y[c], m17, x[c]); }          // SHF + IMAD
+                if (MIX == 33) { x[c] = f_imadhi(x[c], m17, y[c]); y[c] = f_imadhi(y[c], m17, p); }      // IMAD.HI
+                if (MIX == 34) { x[c] = f_sel(x[c], y[c], p); y[c] = f_sel(y[c], q, x[c]); }             // ISETP + SEL
+                if (MIX == 35) { x[c] = f_shfl(x[c]); y[c] = f_shfl(y[c]); }                             // SHFL
+                if (MIX == 36) { x[c] = f_imadhi(x[c], m17, y[c]); y[c] = f_prmt(y[c], p, x[c]); }       // IMAD.HI + PRMT
+                if (MIX == 37) { x[c] = f_vminu(x[c], y[c]); y[c] = f_vminu(y[c], p); }                  // VIMNMX.U16x2
+                if (MIX == 38) { x[c] = f_shf(x[c], y[c], q); y[c] = f_prmt(y[c], p, x[c]); }            // SHF + PRMT
                 if (MIX == 14) { x[c] = f_vimnmx3(x[c], p, q); y[c] = f_imad(y[c], m17, q); y[c] = f_imad(y[c], m17, p);} // 1 ALU : 2 FMA
             }
         }
@@ -153,6 +169,8 @@ static const MixInfo MI[] = {
     {"VIMNMX(2src) + VIADD.16x2(2src)", 2, 0}, {"VIADD.16x2 + VIADDMNMX", 2, 0}, {"PRMT + VIMNMX3", 2, 0}, {"PRMT + VIADDMNMX", 2, 0},
     {"VIADDMNMX + VIMNMX3", 2, 0}, {"general cell: PRMT+VIMNMX+VIADD+VIADDMNMX.RELU", 4, 0}, {"VIMNMX(2src) + PRMT", 2, 0}, {"VIADD.16x2 + PRMT", 2, 0},
     {"HMNMX2 x2", 0, 2}, {"HMNMX2 + PRMT", 1, 1}, {"HMNMX2 + IMAD", 0, 2}, {"HMNMX2 + VIADD.16x2", 0, 2}, {"split cell: PRMT+VIADDMNMX (ALU) + 2 HMNMX2", 2, 2}, {"HMNMX2 + VIADDMNMX", 1, 1},
+    {"SHF.L.W (variable) x2", 2, 0}, {"HSET2 x2", 0, 2}, {"HSET2 + PRMT", 1, 1}, {"SHF + IMAD", 1, 1}, {"IMAD.HI x2", 0, 2},
+    {"(ISETP+SEL) x2", 4, 0}, {"SHFL x2", 0, 2}, {"IMAD.HI + PRMT", 1, 1}, {"VIMNMX.U16x2 x2", 2, 0}, {"SHF + PRMT", 2, 0},
 };
 
 template<int MIX> int run(int sms, int wps, unsigned* d_out, unsigned* d_in, long long* d_cyc, int clock_khz)
@@ -188,8 +206,9 @@ template<int MIX> int run(int sms, int wps, unsigned* d_out, unsigned* d_in, lon
     return 0;
 }
 
-int main()
+int main(int argc, char** argv)
 {
+    const bool only_new = argc > 1;      // any argument: only the mixes added for the semi-global kernel
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", prop.name, prop.multiProcessorCount, clk);
@@ -206,6 +225,12 @@ int main()
     }
     const int sms = prop.multiProcessorCount;
     for (int wps : {2, 4, 8}) {
+        run<29>(sms, wps, d_out, d_in, d_cyc, clk); run<30>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<31>(sms, wps, d_out, d_in, d_cyc, clk); run<32>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<33>(sms, wps, d_out, d_in, d_cyc, clk); run<34>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<35>(sms, wps, d_out, d_in, d_cyc, clk); run<36>(sms, wps, d_out, d_in, d_cyc, clk);
+        run<37>(sms, wps, d_out, d_in, d_cyc, clk); run<38>(sms, wps, d_out, d_in, d_cyc, clk);
+        if (only_new) continue;
         run<0>(sms, wps, d_out, d_in, d_cyc, clk); run<1>(sms, wps, d_out, d_in, d_cyc, clk);
         run<2>(sms, wps, d_out, d_in, d_cyc, clk); run<3>(sms, wps, d_out, d_in, d_cyc, clk);
         run<4>(sms, wps, d_out, d_in, d_cyc, clk); run<5>(sms, wps, d_out, d_in, d_cyc, clk);
