@@ -29,7 +29,8 @@
 //     shift by 8 or 0 bits; the match score of two cells is one PRMT through an 8-byte table indexed by
 //     a XOR b (the reference's pshufb table, source.cpp:2640-2641).
 //   * Traceback evidence, not band values, is stored: the 2-bit tag of every cell, gathered with four
-//     multiply-adds on the FMA pipe: 4 bytes per lane per round (16 per pair), pos_y in the spare bytes.
+//     multiply-adds on the FMA pipe: 4 bytes per lane per round (16 per pair); a spare byte says which way the
+//     band moved in this round and the one before, which is all the traceback needs to follow a cell.
 //
 // Every function is SWB_HD and templated on an Env that supplies the lane index and the two shuffles, so
 // the same text runs on the device (real shuffles) and in tests/emu (four coroutines in lock step).
@@ -83,7 +84,8 @@ struct Sg2State {
     uint32_t next2_raw;   // ... and the one after it: a base is loaded two entries before it is used
     uint32_t role_base;   // F | (0x80 << 16 in lane 0)
     int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (lane 3)
-    int32_t pos_y, pos_x; // the band's upper-right cell: (pos_y, pos_x - 31), source.cpp:1873-1874
+    int32_t pos_y;        // the band's upper-right cell is (pos_y, round - pos_y), source.cpp:1873-1874
+    uint32_t prev_down;   // the previous round moved down
     int32_t best, T, best_round, best_py, best_m;
 };
 
@@ -115,7 +117,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
         s.B[k] = SG2_PAD_B * 0x01010101u;
     }
     s.lut_lo = 0x0303030Bu - 0x02020202u; s.lut_hi = 0x03030303u - 0x02020202u;      // round 1 moves right: diag carries tag 2
-    s.pos_y = 0; s.pos_x = 31;
+    s.pos_y = 0; s.prev_down = 0u;
     s.best = SG2_X; s.best_round = 0; s.best_py = 0; s.best_m = 4 * (SG2_X - 1);
     // bases enter at cell 0 on a down move (lane 0: seq1p[pos_y + 31] = seq1[pos_y + 30]) and at cell 31 on a
     // right move (lane 3: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
@@ -160,8 +162,10 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     s.V[0] = fsr(s.R2[0], s.R2[1], sR); s.V[1] = fsr(s.R2[1], s.R2[2], sR); s.V[2] = fsr(s.R2[2], s.R2[3], sR); s.V[3] = fsr(s.R2[3], gv, sR);
     s.A[1] = fsl(s.A[0], s.A[1], cD); s.A[0] = fsl(ga, s.A[0], cD);
     s.B[0] = fsr(s.B[0], s.B[1], cR); s.B[1] = fsr(s.B[1], gb, cR);
-    s.pos_y += right ? 0 : 1;
-    s.pos_x += right ? 1 : 0;
+    const uint32_t down = one - s.right;
+    s.pos_y += (int32_t)down;
+    const uint32_t moves = (down + s.prev_down * (one << 1)) * (one << 8);      // byte 1: bit 0 = this round moved down, bit 1 = the one before
+    s.prev_down = down;
     // ---- scores: selector byte of a cell = (a ^ b) in the low nibble, 8 | (a ^ b) in the high one (sign replication)
     const uint32_t x0 = s.A[0] ^ s.B[0], x1 = s.A[1] ^ s.B[1];
     uint32_t sd[4];
@@ -181,13 +185,13 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     const uint32_t m1 = env.shfl_xor(m, 1), m2 = env.shfl_xor(m, 2), m3 = env.shfl_xor(m, 3);
     const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[3], 3);
     const uint32_t gn = env.shfl(xr, q + 1), gp = env.shfl(xd, q - 1);
-    // ---- the record (independent of the shuffles): tags of cells 0,2,4,6 in byte 0, of 1,3,5,7 in byte 2, pos_y in bytes 1 and 3
+    // ---- the record (independent of the shuffles): tags of cells 0,2,4,6 in byte 0, of 1,3,5,7 in byte 2, the two moves in byte 1
     // (tag = t - t2, no borrow between the halves: clearing bits never raises a half; summed as multiply-adds)
     {
         const uint32_t c4 = one << 2, c16 = one << 4, c64 = one << 6, mone = 0u - one;
         // (dsum enters with weight 0: a second use keeps its add a VIADD on the FMA pipe instead of a fused add-max on the ALU pipe)
         uint32_t neg = t2[0] * one + t2[1] * c4 + (dsum[0] + dsum[1] + dsum[2] + dsum[3]) * zero;
-        uint32_t acc = prmt((uint32_t)s.pos_y, 0u, 0x1404u) + t[0] * one;
+        uint32_t acc = t[0] * one + moves;
         neg = t2[2] * c16 + neg; acc = t[1] * c4 + acc;
         neg = t2[3] * c64 + neg; acc = t[2] * c16 + acc;
         acc = t[3] * c64 + acc;
@@ -237,7 +241,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
 }
 
 // After the last round: the end cell is the upper-right-most cell of the best round that holds the best
-// score (source.cpp:1953-1954).  Returns this lane's word of record 0 = {best round, its pos_y, end_y, end_x}.
+// score (source.cpp:1953-1954).  Returns this lane's word of record 0 = {best round, band element of the end cell, end_y, end_x}.
 template <class Env>
 SWB_HD uint32_t sg2_finish(const Sg2State& s, Env& env, int32_t& score, int32_t& end_y, int32_t& end_x)
 {
@@ -251,20 +255,20 @@ SWB_HD uint32_t sg2_finish(const Sg2State& s, Env& env, int32_t& score, int32_t&
     score = s.best - SG2_X;
     end_y = s.best_py + 31 - loc;
     end_x = (s.best_round - s.best_py) - 31 + loc;         // pos_x = 31 + (number of right moves)
-    return (uint32_t)(q == 0 ? s.best_round : q == 1 ? s.best_py : q == 2 ? end_y : end_x);
+    return (uint32_t)(q == 0 ? s.best_round : q == 1 ? loc : q == 2 ? end_y : end_x);
 }
 
-// One traceback step on a record (source.cpp:1958-1971): diagonal first, then up, else left.
-// rec = the four lane words of round r = y + x.  Returns the op: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).
-SWB_HD uint32_t sg2_tb_step(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int& y, int& x, int& r)
+// One traceback step (source.cpp:1958-1971): the walker stands on band element o of round r; w = word o >> 3 of that
+// round's record.  The tag says where the cell came from (3 diagonal, 2 up, 1 left -- the reference's preference order
+// was applied by the forward pass); the move bits say how the band had shifted, which gives the element index of the
+// predecessor in ITS round:  up: o + 1 - down(r),  left: o - down(r),  diagonal (two rounds back): o + 1 - down(r) - down(r-1).
+// Round 0 is the cell (0,0): the walk ends at r == 0.  Returns the op: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).
+SWB_HD uint32_t sg2_tb_step(uint32_t w, int& o, int& r)
 {
-    const int py = (int)(((r0 >> 8) & 0xffu) | ((r0 >> 16) & 0xff00u));
-    const int o = 31 - (y - py);                           // band element of (y, x) in round r (source.cpp:1947)
-    const uint32_t w = (o & 16) ? ((o & 8) ? r3 : r2) : ((o & 8) ? r1 : r0);
-    const uint32_t code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;      // 3 = diagonal, 2 = up, 1 = left
-    y -= (int)(code >> 1);
-    x -= (int)(code != 2u);
-    r -= 1 + (int)(code == 3u);
+    const uint32_t code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;
+    const uint32_t diag = code == 3u ? 1u : 0u;
+    o += (int)(code >> 1) - (int)((w >> 8) & 1u) - (int)((w >> 9) & diag);
+    r -= 1 + (int)diag;
     return 3u - code;
 }
 

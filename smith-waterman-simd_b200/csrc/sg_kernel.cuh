@@ -140,8 +140,8 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const uint4 start = trace[0];               // {best round, its pos_y, end_y, end_x}, written by the forward kernel
-    int r = (int)start.x, y = (int)start.z, x = (int)start.w;
+    const uint4 start = trace[0];               // {best round, band element of the end cell, end_y, end_x}, written by the forward kernel
+    int r = (int)start.x, o = (int)start.y;
     int lo = (r >> 3) - (SG_TB_LINES - 1);      // lowest line requested so far: the ring holds lines lo .. lo+7
 #pragma unroll
     for (int q = 0; q < SG_TB_LINES; ++q) request((r >> 3) - q);
@@ -151,8 +151,8 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
     // step for every lane of the warp, so no divergence) a lane asks for one more line if the ring has a free
     // slot.  A line is therefore requested at least five such batches before the walker enters it, and
     // wait_group 4 -- all but the four youngest batches have landed -- covers it.
-    while ((y | x) != 0 && n_ops < cap) {
-        if ((n_ops & 3u) == 0u) {
+    while (r > 0 && n_ops < cap) {              // round 0 is the cell (0,0)
+        {
             const bool room = (r >> 3) <= lo + (SG_TB_LINES - 2);      // the walker has left line lo+7: its slot is free
             if (room) --lo;
             if (room && lo >= 0) {
@@ -162,9 +162,14 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 4;" ::: "memory");
         }
-        const uint4 rec = *slot_of(r >> 3, r & 7);
-        row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(rec.x, rec.y, rec.z, rec.w, y, x, r);      // 0 = diagonal, 1 = down, 2 = right
-        ++n_ops;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (r > 0 && n_ops < cap) {
+                const uint32_t w = reinterpret_cast<const uint32_t*>(slot_of(r >> 3, r & 7))[o >> 3];   // the lane word that holds element o
+                row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(w, o, r);                                  // 0 = diagonal, 1 = down, 2 = right
+                ++n_ops;
+            }
+        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     out.n_ops[p] = (int32_t)n_ops;

@@ -89,15 +89,15 @@ extern "C" int swemu_sg2(const uint8_t* seq1, const uint8_t* seq2, int len, int3
     *score = Q.score; *end_y = Q.end_y; *end_x = Q.end_x;
     // traceback over the records, as the device's traceback kernel does
     const uint32_t* rec = Q.rec.data();
-    int r = (int)rec[0], y = (int)rec[2], x = (int)rec[3];
-    if (y != Q.end_y || x != Q.end_x) return -4;
+    int r = (int)rec[0], o = (int)rec[1];
+    if ((int)rec[2] != Q.end_y || (int)rec[3] != Q.end_x) return -4;
     std::vector<uint8_t> rev;
-    while ((y | x) != 0) {
+    while (r > 0) {
         if ((int)rev.size() >= 2 * len) return -2;
-        if (r < 1) return -3;
-        const uint32_t* w = rec + 4 * (size_t)r;
-        rev.push_back((uint8_t)sg2_tb_step(w[0], w[1], w[2], w[3], y, x, r));
+        if (o < 0 || o > 31) return -3;
+        rev.push_back((uint8_t)sg2_tb_step(rec[4 * (size_t)r + (o >> 3)], o, r));
     }
+    if (r != 0 || o != 31) return -5;       // (0,0) is element 31 of round 0
     *n_ops = (int32_t)rev.size();
     for (size_t k = 0; k < rev.size(); ++k) ops[k] = rev[rev.size() - 1 - k];
     return 0;
