@@ -117,7 +117,7 @@ constexpr size_t SG_TB_SMEM = (size_t)SG_TB_LINES * 8 * SG_TB_THREADS * sizeof(u
 __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem_src)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
 __global__ void __launch_bounds__(SG_TB_THREADS)
