@@ -539,13 +539,28 @@ def run_semiglobal_arm(args):
                           "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     import torch
+    import torch.distributed as dist
+    from sharding import max_over_ranks, sum_over_ranks
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- no CPU fallback")
-    torch.cuda.set_device(0)
-    ctx = swb200.Context(devices=[0])
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ddist = dist if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ctx = swb200.Context(devices=[local_rank])
     info = ctx.semiglobal_kernel_info()
     pa, pb = swb200.PinnedArray((n, SG_LEN), np.uint8), swb200.PinnedArray((n, SG_LEN), np.uint8)
-    swb200.related_pairs(0, n, SG_LEN, out=(pa.array, pb.array))
+    swb200.related_pairs(rank * n, n, SG_LEN, out=(pa.array, pb.array))       # rank r aligns pairs [r n, (r+1) n): weak scaling, no collective
     h_meta = [swb200.PinnedArray((n,), np.int32) for _ in range(4)]
     h_ops = swb200.PinnedArray((n, 2 * SG_LEN), np.uint8)
     d_a, d_b = torch.from_numpy(pa.array).cuda(), torch.from_numpy(pb.array).cuda()
@@ -569,8 +584,9 @@ def run_semiglobal_arm(args):
         fwd_ev[i + 1].record(stream)
     torch.cuda.synchronize()
     fwd_ms = fwd_ev[0].elapsed_time(fwd_ev[-1]) / args.steps
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
     launches0 = ctx.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.perf_counter()
@@ -578,10 +594,11 @@ def run_semiglobal_arm(args):
     for i in range(args.steps):
         launch()                 # 268 MB of sequence + ~2.1 GB of trace written and read per launch: far beyond L2
         ev[i + 1].record(stream)
-    torch.cuda.synchronize()
+    barrier()
     t_wall1 = time.perf_counter()
     launches_dev = ctx.launch_count - launches0
-    ms = ev[0].elapsed_time(ev[-1]) / args.steps
+    ms = max_over_ranks(ev[0].elapsed_time(ev[-1]) / args.steps, ddist)
+    n_total = sum_over_ranks(n, ddist)
     dev_scores = d_meta[0].cpu().numpy()
     dev_nops = d_meta[3].cpu().numpy()
     rounds = (d_meta[1].cpu().numpy().astype(np.int64) + d_meta[2].cpu().numpy()).sum()   # >= end_y + end_x rounds per pair (a lower bound: the band runs on to the edge)
@@ -593,13 +610,19 @@ def run_semiglobal_arm(args):
                                                           h_meta[3].array.ctypes.data, h_ops.array.ctypes.data))
     for _ in range(2):
         e2e()
+    barrier()
     launches1 = ctx.launch_count
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, ddist)
     launches_e2e = ctx.launch_count - launches1
     sampler.stop()
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     clocks = sampler.summary(t_wall0, t_wall1)
     e2e_ok = bool(np.array_equal(h_meta[0].array, dev_scores) and np.array_equal(h_meta[3].array, dev_nops))
 
@@ -627,15 +650,15 @@ def run_semiglobal_arm(args):
     rounds_per_s = n * SG_ROUNDS_NOMINAL / (ms * 1e-3)
     trace_gbs = n * SG_ROUNDS_NOMINAL * SG_RECORD_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
     line = {
-        "metric": "alignments_per_s", "value": n / (ms * 1e-3), "unit": "alignments/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": "alignments_per_s", "value": n_total / (ms * 1e-3), "unit": "alignments/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "band_gcups": rounds_per_s * 32 / 1e9,
         "config": {"workload": "SURVEY.md 8(f4): adaptive-banded X-drop semi-global aligner (band 32, X 70, 1/1/1), score + traceback, "
                                f"{n} pairs of 16384-mers with 10/10/10 % mismatch/insert/delete (TestSemiGlobal's construction, source.cpp:2750-2771)",
-                   "pairs": n, "seq_len": SG_LEN, "l2": f"inputs {2 * n * SG_LEN / 1e6:.0f} MB + {n * SG_ROUNDS_NOMINAL * 16 / 1e9:.1f} GB of round records per launch > 126 MB L2, no flush needed",
+                   "pairs": n, "pairs_per_gpu": n, "sharding": "contiguous index ranges, no collective", "seq_len": SG_LEN, "l2": f"inputs {2 * n * SG_LEN / 1e6:.0f} MB + {n * SG_ROUNDS_NOMINAL * 16 / 1e9:.1f} GB of round records per launch > 126 MB L2, no flush needed",
                    "kernel": info},
         "clocks": clocks,
-        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n * SG_LEN,
+        "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "alignments/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n * SG_LEN,
                 "d2h_bytes_per_step": n * (16 + 2 * SG_LEN), "api": "swb200_semiglobal_xdrop_batch (C ABI, pinned host arrays; scores, end cells and move strings back)",
                 "equals_device_leg": e2e_ok},
         "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
@@ -656,6 +679,8 @@ def run_semiglobal_arm(args):
                                 "cpu_model": cpu_model(), "sample": f"{cpu['sample_pairs']} of {n} pairs per pass, best of 3 passes"}
     print(json.dumps(line), flush=True)
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- length sweep
