@@ -728,6 +728,85 @@ def run_sweep_arm(args):
     ctx.close()
 
 
+# --------------------------------------------------------------------------- 8(f2), 8(f3): one-vs-many and fixed 1/1/1
+def run_variants_arm(args):
+    """`--workload variants`: the two call shapes of SURVEY.md 8(f2)/(f3) -- 1 M queries against ONE target
+    (SmithWaterman_8b111x32mark*, source.cpp:1227-1234) and 1 M independent pairs at the fixed 1/-1/1 scoring
+    (SmithWaterman_111 / _8bit111simd, source.cpp:1073-1225) -- through the C ABI with pinned host arrays, plus the
+    1/-1/1 kernel device-resident.  CPU beside them: the reference's x32mark3 (one thread: it has no batch driver) and its
+    general simd9 on all cores at the same scoring."""
+    import torch
+    import swb200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- no CPU fallback")
+    torch.cuda.set_device(0)
+    ctx = swb200.Context(devices=[0])
+    n = PAIRS_PER_GPU
+    pa, pb = swb200.PinnedArray((n, 128), np.uint8), swb200.PinnedArray((n, 128), np.uint8)
+    ps = swb200.PinnedArray((n,), np.int32)
+    swb200.reference_stream(n, out=(pa.array, pb.array))
+    target = pb.array[0].copy()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return 1e3 * (time.perf_counter() - t0) / reps
+    rows = []
+    ms = timed(lambda: ctx.score_batch_111(pa.array, pb.array, out=ps.array), args.steps)
+    s111 = ps.array.copy()
+    rows.append({"call": "swb200_score_batch_111 (host arrays, 1 M pairs)", "ms_per_step": ms, "gcups": n * CELLS_PER_PAIR / ms / 1e6,
+                 "alignments_per_s": n / (ms * 1e-3), "h2d_bytes_per_step": 2 * n * 128, "d2h_bytes_per_step": 4 * n})
+    ms = timed(lambda: ctx.score_one_vs_many(pa.array, target, out=ps.array), args.steps)
+    sx = ps.array.copy()
+    rows.append({"call": "swb200_score_one_vs_many (host arrays, 1 M queries x 1 target, 1/-1/1)", "ms_per_step": ms, "gcups": n * CELLS_PER_PAIR / ms / 1e6,
+                 "alignments_per_s": n / (ms * 1e-3), "h2d_bytes_per_step": n * 128 + 128, "d2h_bytes_per_step": 4 * n})
+    d_a, d_b = torch.from_numpy(pa.array).cuda(), torch.from_numpy(pb.array).cuda()
+    d_s = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ctx.score_batch_device(d_a, d_b, swb200.MATRIX_111, swb200.GAP_111, d_s)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ctx.score_batch_device(d_a, d_b, swb200.MATRIX_111, swb200.GAP_111, d_s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    rows.append({"call": "swb200_score_batch_device at 1/-1/1 (device-resident, 1 M pairs)", "ms_per_step": ms, "gcups": n * CELLS_PER_PAIR / ms / 1e6,
+                 "alignments_per_s": n / (ms * 1e-3), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    ok = bool(np.array_equal(d_s.cpu().numpy(), s111))
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O   # allowed: cpu_baseline leg only
+        if O.have_ref():
+            cores = os.cpu_count() or 1
+            m = 4096                      # x32mark3: 128 calls of 32 queries against the same target, one thread
+            t0 = time.perf_counter()
+            got = np.concatenate([O.ref_x32(3, pa.array[k:k + 32], target) for k in range(0, m, 32)])
+            dt = time.perf_counter() - t0
+            ok = ok and bool(np.array_equal(got, sx[:m]))
+            m9 = 200_000
+            O.ref_score_batch(9, pa.array[:m9], pb.array[:m9], swb200.MATRIX_111, 1, threads=cores)
+            t0 = time.perf_counter()
+            g9 = O.ref_score_batch(9, pa.array[:m9], pb.array[:m9], swb200.MATRIX_111, 1, threads=cores)
+            dt9 = time.perf_counter() - t0
+            ok = ok and bool(np.array_equal(g9, s111[:m9]))
+            cpu = {"x32mark3_1_thread": {"gcups": m * CELLS_PER_PAIR / dt / 1e9, "sample": f"{m} queries, one thread, ctypes call per 32"},
+                   "simd9_all_cores": {"gcups": m9 * CELLS_PER_PAIR / dt9 / 1e9, "cores": cores, "sample": f"{m9} pairs"}, "cpu_model": cpu_model()}
+    line = {"metric": "GCUPS", "unit": "GCUPS", "value": rows[2]["gcups"], "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": rows[2]["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+            "config": {"workload": "SURVEY.md 8(f2)/(f3): one-vs-many and fixed 1/-1/1 scoring, 1 M 128-mers of the reference stream"},
+            "e2e": {"value": rows[0]["gcups"], "unit": "GCUPS", "h2d_bytes_per_step": rows[0]["h2d_bytes_per_step"], "d2h_bytes_per_step": rows[0]["d2h_bytes_per_step"]},
+            "variants": rows, "verified": {"equal_to_device_and_reference": ok}, "gpu_launches": int(ctx.launch_count)}
+    if cpu is not None:
+        line["cpu_baseline"] = dict(cpu, kind="reference", unit="GCUPS", value=cpu["simd9_all_cores"]["gcups"], cores=cpu["simd9_all_cores"]["cores"],
+                                    sample=cpu["simd9_all_cores"]["sample"])
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -738,7 +817,7 @@ def main():
     ap.add_argument("--pack-threads", type=int, default=None, help="host 2-bit packing lanes per GPU in the e2e leg (default: library auto; 0 = off)")
     ap.add_argument("--no-plain-e2e", action="store_true", help="skip the lanes-off comparison run of the e2e leg")
     ap.add_argument("--cpu-table", action="store_true", help="with --impl reference: scalar/simd4/simd7/simd9, 1 thread and all cores")
-    ap.add_argument("--workload", choices=["batch1m", "stream", "sweep", "semiglobal"], default="batch1m",
+    ap.add_argument("--workload", choices=["batch1m", "stream", "sweep", "semiglobal", "variants"], default="batch1m",
                     help="batch1m = the headline 1M-pair batch (default); stream = configs[2]/[4] streaming of --pairs pairs")
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
@@ -755,6 +834,8 @@ def main():
         run_stream_arm(args)
     elif args.workload == "sweep":
         run_sweep_arm(args)
+    elif args.workload == "variants":
+        run_variants_arm(args)
     else:
         run_b200_arm(args)
 
