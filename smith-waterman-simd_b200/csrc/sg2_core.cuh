@@ -137,7 +137,9 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
 }
 
 // One round (source.cpp:1886-1942).  `role_seq` = seq1 in lane 0, seq2 in lane 3 (unused elsewhere);
-// `rec_row` = this pair's records as uint32 [round][4].  Returns false when every cell is <= 0 (source.cpp:1938);
+// `rec_row` = this pair's records: lane word q of round r at rec_row[rec_stride * r + q] (rec_stride = 4 when a pair's
+// records are contiguous, 128 when 32 pairs are interleaved round by round).  Returns false when every cell is <= 0
+// (source.cpp:1938);
 // a pair in that state is inert -- further rounds change neither its best nor its cells -- so the quads of a warp
 // may keep running together until the last one is done.
 // All communication of a round is ONE stage of seven independent shuffles issued right after the cells are
@@ -147,7 +149,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
 //     result[0] < result[31]   <=>   t2[0] < t2[31]  and  t2[31] - c >= 0
 // (with c the amount subtracted this round; dropped cells compare as the smallest value).
 template <class Env>
-SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row)
+SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride)
 {
     const int q = env.q();
     const bool right = s.right != 0u;                      // source.cpp:1889
@@ -195,7 +197,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
         neg = t2[2] * c16 + neg; acc = t[1] * c4 + acc;
         neg = t2[3] * c64 + neg; acc = t[2] * c16 + acc;
         acc = t[3] * c64 + acc;
-        rec_row[4 * round + q] = neg * mone + acc;
+        rec_row[rec_stride * round + q] = neg * mone + acc;
     }
     // ---- round maximum (source.cpp:1925).  In the X-drop frame the best so far sits at 69 or 70, a cell is at most
     // two above it, and the threshold moves exactly when a cell reaches 72 -- so the amount subtracted this round,

@@ -23,13 +23,15 @@
 //     comparisons -- "this cell's value came from the diagonal" / "... from above", evaluated with the reference's
 //     own comparisons and preference order -- plus the band's pos_y: 16 bytes per round (4 per lane).
 //   * The traceback is a second kernel, ONE THREAD PER PAIR: the walk is serial (as in the reference), so a warp
-//     spent on it would execute every instruction for one live lane.  A thread reads its pair's records backwards
-//     -- consecutive 16-byte records, streamed through shared memory ahead of the walk -- and emits one op per
-//     step: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).  The ops land right-aligned in the pair's output row in
+//     spent on it would execute every instruction for one live lane.  The records of 32 pairs are interleaved
+//     round by round, and the 32 walkers of a warp march down the ROUNDS together (a walker acts in the rounds its
+//     path visits), so every record fetch of the warp is one contiguous 512-byte read.  One op per step:
+//     0 = diagonal, 1 = down (y+1), 2 = right (x+1).  The ops land right-aligned in the pair's output row in
 //     forward order and a third kernel shifts each row to the left edge.
 //
 // HBM layout: seq1, seq2 [n][len] byte codes 0..3 (the reference's std::array<uint8_t,16384>, len = 16384);
-// scratch: per PAIR of a launch the round records (sg_trace_bytes) plus one spare row; outputs
+// scratch: per GROUP of 32 pairs of a launch the round records [round][32 pairs][16 bytes] (sg_group_bytes), plus
+// one spare group; outputs
 // score/end_y/end_x/n_ops [n] int32 and ops [n][2*len] bytes (optional).
 #pragma once
 #include <cuda_runtime.h>
@@ -42,6 +44,10 @@ namespace swb {
 __host__ __device__ inline uint32_t sg_rounds_cap(int len) { return ((uint32_t)(2 * len + 1) + 31u) & ~31u; }
 // per pair of a launch: [rounds_cap] uint4 records (four lane words, sg2_core.cuh); record 0 = where the traceback starts
 __host__ __device__ inline size_t sg_trace_bytes(int len) { return (size_t)sg_rounds_cap(len) * 16; }
+// the records of pairs 32 g .. 32 g + 31 form one group, interleaved: [round][pair & 31] uint4
+constexpr int SG_GROUP = 32;
+__host__ __device__ inline size_t sg_group_bytes(int len) { return sg_trace_bytes(len) * SG_GROUP; }
+__host__ __device__ inline size_t sg_groups_for(unsigned long long pairs) { return (size_t)((pairs + SG_GROUP - 1) / SG_GROUP) + 1; }   // + the spare group
 
 struct SgOut {
     int32_t* score;     // [n]  best score (offset removed)
@@ -78,19 +84,20 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
     const int max_round = 2 * len + 1;          // rounds run while round < MAX_ROUND (source.cpp:1872,1886)
     // The warp stays converged (full-mask shuffles): its eight quads take eight consecutive pairs, run their rounds
     // together until the last of them is done, then take the next eight.  A quad beyond the batch shadows the last
-    // pair and writes its records to the spare row n of the scratch.
+    // pair and writes its records to the spare group of the scratch.
     for (unsigned long long base = warp * 8ull; base < n; base += n_warps * 8ull) {
         const unsigned long long want = base + (lane >> 2);
         const bool live = want < n;
         const unsigned long long p = live ? want : n - 1ull;
         const uint8_t* const s1 = seq1 + p * (unsigned long long)len;
         const uint8_t* const s2 = seq2 + p * (unsigned long long)len;
-        uint32_t* const rec_row = reinterpret_cast<uint32_t*>(traces + (live ? p : n) * rounds_cap);
+        const unsigned long long slot = live ? want : ((n + SG_GROUP - 1) / SG_GROUP) * SG_GROUP + (want & (SG_GROUP - 1));
+        uint32_t* const rec_row = reinterpret_cast<uint32_t*>(traces + (slot / SG_GROUP) * rounds_cap * SG_GROUP + (slot & (SG_GROUP - 1)));
         Sg2State s;
         sg2_init(s, env, s1, s2, len);
         const uint8_t* const role = env.q() == 0 ? s1 : s2;
         for (int round = 1; round < max_round; ++round) {
-            const bool go = sg2_round(s, env, role, len, round, rec_row);
+            const bool go = sg2_round(s, env, role, len, round, rec_row, 4 * SG_GROUP);
             if ((round & 3) == 0 && !__any_sync(0xffffffffu, go)) break;      // a finished pair stays finished: asking every fourth round is enough
         }
         int32_t score, end_y, end_x;
@@ -102,77 +109,80 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
     }
 }
 
-// Traceback (source.cpp:1956-1973) over the recorded masks: thread t walks pair t's records backwards from the
-// end cell to (0,0).  The walk is a chain of dependent 16-byte reads marching down through memory, and the
-// records were written by another kernel (HBM, not L2), so each thread streams its records through a private
-// ring of SG_TB_LINES 128-byte lines in shared memory with cp.async, SG_TB_LINES - 1 lines (about 35 steps)
-// ahead of the walker: a step then costs a shared-memory read, not a DRAM round trip.  The step itself is
-// branch-free, so the 32 walks of a warp stay converged.
-// Step k (k = 0 is the LAST move) is written to row[2*len - 1 - k], so the row ends up holding the
-// forward-ordered op string right-aligned; sg_left_align_kernel then moves it to the left edge.
+// Traceback (source.cpp:1956-1973) over the recorded tags, one thread per pair, the 32 walkers of a warp in step BY
+// ROUND: the warp marches from the highest best round of its 32 pairs down to round 1, and a walker acts in round r
+// when its path stands in round r (a diagonal step skips one round, a finished or not yet started walker idles).
+// With the records of the warp's 32 pairs interleaved round by round, lane i's record of round r sits at
+// group[r][i]: the warp's fetch of a round is ONE contiguous 512-byte read, streamed through a shared-memory ring
+// SG_TB_DEPTH rounds ahead with cp.async (eight rounds per commit group).  Each lane reads back only what it wrote
+// into the ring itself, so no barrier is needed.
+// Step k (k = 0 is the LAST move) is written to row[2*len - 1 - k], so the row ends up holding the forward-ordered op
+// string right-aligned; sg_left_align_kernel then moves it to the left edge.
 constexpr int SG_TB_THREADS = 64;
-constexpr int SG_TB_LINES = 8;
-constexpr size_t SG_TB_SMEM = (size_t)SG_TB_LINES * 8 * SG_TB_THREADS * sizeof(uint4);    // 64 KiB
+constexpr int SG_TB_DEPTH = 64;
+constexpr size_t SG_TB_SMEM = (size_t)SG_TB_DEPTH * SG_TB_THREADS * sizeof(uint4);    // 64 KiB
 
 __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem_src)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
 __global__ void __launch_bounds__(SG_TB_THREADS)
 sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
 {
-    extern __shared__ uint4 sg_ring[];          // [line slot][record 0..7][thread]: neighbours in a warp sit in neighbouring banks
-    const unsigned long long p = (unsigned long long)blockIdx.x * SG_TB_THREADS + threadIdx.x;
-    if (p >= n) return;
+    extern __shared__ uint4 sg_ring[];          // [warp of the block][round & (DEPTH-1)][lane]
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long g = ((unsigned long long)blockIdx.x * SG_TB_THREADS + threadIdx.x) >> 5;      // group = warp
+    if (g * SG_GROUP >= n) return;              // the whole warp
+    const unsigned long long p = g * SG_GROUP + lane;
+    const bool live = p < n;
     const uint32_t rounds_cap = sg_rounds_cap(len);
     const uint32_t cap = 2u * (uint32_t)len;
-    const uint4* const trace = traces + p * rounds_cap;
-    uint8_t* const row = out.ops + p * (unsigned long long)cap;
-    uint4* const ring = sg_ring + threadIdx.x;
-    auto slot_of = [&](int line, int rec) -> uint4* { return ring + ((line & (SG_TB_LINES - 1)) * 8 + rec) * SG_TB_THREADS; };
-    auto request = [&](int line) {              // one commit group per line, empty when the walk has run out of lines
-        if (line >= 0) {
+    const uint4* const grp = traces + g * rounds_cap * SG_GROUP + lane;                 // round r: grp[r * 32]
+    uint4* const ring = sg_ring + (threadIdx.x >> 5) * (SG_TB_DEPTH * 32) + lane;       // round r: ring[(r & 63) * 32]
+    uint8_t* const row = out.ops + (live ? p : 0ull) * (unsigned long long)cap;
+
+    const uint4 start = live ? grp[0] : make_uint4(0u, 31u, 0u, 0u);      // {best round, band element of the end cell, end_y, end_x}
+    int rw = (int)start.x, o = (int)start.y;    // the walker stands on element o of round rw
+    int rtop = rw;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) sg_cp_async16(slot_of(line, q), trace + line * 8 + q);
+    for (int d = 16; d >= 1; d >>= 1) rtop = max(rtop, __shfl_xor_sync(0xffffffffu, rtop, d));
+    rtop |= 7;                                  // blocks of eight rounds, aligned: rtop, rtop - 8, ...
+#pragma unroll 1
+    for (int k = 0; k < SG_TB_DEPTH; k += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = rtop - k - q;
+            if (r >= 1) sg_cp_async16(ring + (r & (SG_TB_DEPTH - 1)) * 32, grp + (size_t)r * 32);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    const uint4 start = trace[0];               // {best round, band element of the end cell, end_y, end_x}, written by the forward kernel
-    int r = (int)start.x, o = (int)start.y;
-    int lo = (r >> 3) - (SG_TB_LINES - 1);      // lowest line requested so far: the ring holds lines lo .. lo+7
-#pragma unroll
-    for (int q = 0; q < SG_TB_LINES; ++q) request((r >> 3) - q);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     uint32_t n_ops = 0;
-    // A step moves at most two records down, so at most one line per four steps: every fourth step (the same
-    // step for every lane of the warp, so no divergence) a lane asks for one more line if the ring has a free
-    // slot.  A line is therefore requested at least five such batches before the walker enters it, and
-    // wait_group 4 -- all but the four youngest batches have landed -- covers it.
-    while (r > 0 && n_ops < cap) {              // round 0 is the cell (0,0)
-        {
-            const bool room = (r >> 3) <= lo + (SG_TB_LINES - 2);      // the walker has left line lo+7: its slot is free
-            if (room) --lo;
-            if (room && lo >= 0) {
+#pragma unroll 1
+    for (int rb = rtop; rb >= 1; rb -= 8) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(SG_TB_DEPTH / 8 - 1) : "memory");      // this block of rounds has landed
+        uint4 rec[8];                           // the eight records first (their addresses do not depend on the walk) ...
 #pragma unroll
-                for (int q = 0; q < 8; ++q) sg_cp_async16(slot_of(lo, q), trace + lo * 8 + q);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 4;" ::: "memory");
-        }
+        for (int q = 0; q < 8; ++q) rec[q] = ring[((rb - q) & (SG_TB_DEPTH - 1)) * 32];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (r > 0 && n_ops < cap) {
-                const uint32_t w = reinterpret_cast<const uint32_t*>(slot_of(r >> 3, r & 7))[o >> 3];   // the lane word that holds element o
-                row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(w, o, r);                                  // 0 = diagonal, 1 = down, 2 = right
+        for (int q = 0; q < 8; ++q) {           // ... then the dependent chain: element -> lane word -> tag -> next element
+            const int r = rb - q;
+            if (rw == r && r >= 1 && n_ops < cap) {
+                const uint32_t w = (o & 16) ? ((o & 8) ? rec[q].w : rec[q].z) : ((o & 8) ? rec[q].y : rec[q].x);
+                row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(w, o, rw);                 // 0 = diagonal, 1 = down, 2 = right
                 ++n_ops;
             }
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {           // refill the slots just read with the rounds DEPTH further down
+            const int r = rb - SG_TB_DEPTH - q;
+            if (r >= 1) sg_cp_async16(ring + (r & (SG_TB_DEPTH - 1)) * 32, grp + (size_t)r * 32);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    out.n_ops[p] = (int32_t)n_ops;
+    if (live) out.n_ops[p] = (int32_t)n_ops;
 }
 
 // Moves each row's op string from the right edge (where the traceback left it) to the left edge.  One block per

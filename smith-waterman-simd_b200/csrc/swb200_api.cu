@@ -533,14 +533,14 @@ constexpr size_t kSgTraceBudget = 10ull << 30;    // round records kept per laun
 
 uint64_t sg_pairs_per_launch(int len)
 {
-    const uint64_t v = kSgTraceBudget / sg_trace_bytes(len);
-    return v ? v : 1;
+    const uint64_t groups = kSgTraceBudget / sg_group_bytes(len);
+    return groups > 1 ? (groups - 1) * SG_GROUP : SG_GROUP;
 }
 
 int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len, uint64_t n)
 {
     const uint64_t pairs = n < sg_pairs_per_launch(len) ? n : sg_pairs_per_launch(len);
-    const size_t need_trace = (pairs + 1) * sg_trace_bytes(len);      // + the spare row of sg2_xdrop_kernel
+    const size_t need_trace = sg_groups_for(pairs) * sg_group_bytes(len);      // groups of 32 pairs + the spare group of sg2_xdrop_kernel
     const bool grow_trace = need_trace > sc.trace_bytes;
     if (!grow_trace) return SWB200_OK;
     SWB_CUDA(ctx, cudaDeviceSynchronize());
@@ -559,13 +559,13 @@ int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len
 int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
               int32_t* d_score, int32_t* d_ey, int32_t* d_ex, int32_t* d_nops, uint8_t* d_ops, cudaStream_t st)
 {
-    const uint64_t cap_pairs = sc.trace_bytes / sg_trace_bytes(len) - 1;
+    const uint64_t cap_pairs = (sc.trace_bytes / sg_group_bytes(len) - 1) * SG_GROUP;
     const uint64_t parts = (n + cap_pairs - 1) / cap_pairs;
     const uint64_t per = (n + parts - 1) / parts;                 // equal parts: no small remainder launch that leaves the GPU mostly idle
     for (uint64_t c0 = 0; c0 < n; c0 += per) {
         const uint64_t m = (n - c0 < per) ? n - c0 : per;
         SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
-        const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);
+        const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);      // a warp per group of 32 pairs
         const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
         const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
         sg2_xdrop_kernel<<<(unsigned)(need < cap ? need : cap), SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
