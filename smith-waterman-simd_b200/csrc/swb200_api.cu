@@ -529,7 +529,7 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
 constexpr int kSgMaxLen = 1 << 15;                // pos_y <= len + 1 must fit the 16 bits it has in a round record
 constexpr int kSgBlocksPerSm = 24;                // resident warps per SM of the forward kernel (one warp = eight pairs)
 
-constexpr size_t kSgTraceBudget = 10ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 20 460 pairs)
+constexpr size_t kSgTraceBudget = 40ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 81 800 pairs)
 
 uint64_t sg_pairs_per_launch(int len)
 {
