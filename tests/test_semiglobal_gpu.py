@@ -93,12 +93,14 @@ def test_lengths_against_oracle(ctx, oracle, length):
 
 
 def test_more_pairs_than_resident_warps(ctx, oracle):
-    # the grid is persistent (SMs x 8 blocks x 4 warps): every warp walks several pairs and reuses its trace slot
+    # the forward grid is persistent (SMs x resident blocks of one warp, eight pairs per warp): with more than eight
+    # pairs per resident warp every warp takes a second batch of eight; 777 is not a multiple of 8 or 32, so the last
+    # warp has quads beyond the batch (they shadow the last pair into the spare group) and the last traceback warp is partial
     info = ctx.semiglobal_kernel_info()
-    resident = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
-    n = 2 * resident + 777
+    resident = 8 * info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
+    n = resident + 777
     rng = np.random.default_rng(9)
-    length = 384
+    length = 96
     a = rng.integers(0, 4, (n, length), dtype=np.uint8)
     b = np.where(rng.random((n, length)) < 0.85, a, rng.integers(0, 4, (n, length), dtype=np.uint8)).astype(np.uint8)
     b[::7] = np.roll(a[::7], 5, axis=1)           # shifted copies: the band has to wander
@@ -117,10 +119,27 @@ def test_more_pairs_than_resident_warps(ctx, oracle):
         assert sc == r["score"][i], i
 
 
+def test_staging_slots_are_reused(ctx, oracle):
+    # len = 2048: the host path cuts the batch into chunks of 16384 pairs (32 MiB per array) over four independent
+    # slots; a fifth chunk reuses slot 0 after its first chunk is back on the host
+    n = 4 * 16384 + 5003
+    length = 2048
+    rng = np.random.default_rng(78)
+    a = rng.integers(0, 4, (n, length), dtype=np.uint8)
+    b = np.where(rng.random((n, length)) < 0.88, a, rng.integers(0, 4, (n, length), dtype=np.uint8)).astype(np.uint8)
+    b[::9] = np.roll(a[::9], -7, axis=1)
+    r = ctx.semiglobal_xdrop(a, b)
+    idx = np.r_[0:40, 16384 - 20:16384 + 20, 3 * 16384 - 20:3 * 16384 + 20, 4 * 16384 - 20:4 * 16384 + 60, n - 40:n].tolist()
+    check_against_oracle(oracle, r, a, b, idx)
+    ops, n_ops = r["ops"], r["n_ops"]
+    valid = np.arange(ops.shape[1])[None, :] < n_ops[:, None]
+    assert np.array_equal(((ops != 2) & valid).sum(1), r["end_y"]) and np.array_equal(((ops != 1) & valid).sum(1), r["end_x"])
+
+
 def test_reference_shape_batch_spans_chunks(ctx, oracle):
-    # len = 16384: five staging chunks of half a resident wave over four independent slots (slot 0 is reused)
+    # len = 16384: two staging chunks (half a wave of the forward kernel each), the second one partial
     info = ctx.semiglobal_kernel_info()
-    wave = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
+    wave = info["sm_count"] * 32
     n = 2 * wave + 211
     rng = np.random.default_rng(77)
     a = rng.integers(0, 4, (n, 16384), dtype=np.uint8)
