@@ -553,7 +553,7 @@ int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len
     return SWB200_OK;
 }
 
-// The launches alone, on device arrays: the forward kernel (one warp per pair) and, when ops are wanted, the
+// The launches alone, on device arrays: the forward kernel (four lanes per pair) and, when ops are wanted, the
 // traceback and left-align kernels (one thread / one block per pair), in equal sub-batches that fit the record
 // scratch.  All launches on one scratch must be stream-ordered with each other.
 int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
@@ -608,17 +608,17 @@ int sg_ensure_slot(swb200_ctx* ctx, Device::SgSlot& s, size_t cap, int len, bool
     return SWB200_OK;
 }
 
-// One GPU's share [lo, hi) of a host batch: chunks alternate between two slots; the kernels of
-// both slots are ordered by an event chain (they share the trace scratch), the copies overlap them.
+// One GPU's share [lo, hi) of a host batch: chunks go round four slots, each an independent stream with its own
+// staging buffers and record scratch, so copies overlap kernels.
 int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, int len, uint64_t lo, uint64_t hi,
                  int32_t* score, int32_t* ey, int32_t* ex, int32_t* nops, uint8_t* ops)
 {
     if (hi <= lo) return SWB200_OK;
     std::lock_guard<std::mutex> lock(d->mu);
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    // chunk: half a resident wave of pairs (at least 32 MiB of sequence per array); the range is cut in equal chunks.
-    // Two half-wave forward kernels from different slots fill the machine together, and the short chunks keep the
-    // exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
+    // chunk: 32 pairs per SM (one forward warp per scheduler), at least 32 MiB of sequence per array; the range is cut
+    // in equal chunks.  The forward kernels of the four slots run side by side (a chunk alone leaves most issue slots
+    // idle), and the short chunks keep the exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
     const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * 64;      // pairs that give every scheduler two warps of the forward kernel
     uint64_t chunk = (32ull << 20) / (uint64_t)len;
     if (chunk < wave / 2) chunk = wave / 2;
