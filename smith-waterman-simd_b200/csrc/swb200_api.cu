@@ -619,6 +619,10 @@ int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t*
     // chunk: 32 pairs per SM (one forward warp per scheduler), at least 32 MiB of sequence per array; the range is cut
     // in equal chunks.  The forward kernels of the four slots run side by side (a chunk alone leaves most issue slots
     // idle), and the short chunks keep the exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
+    // Measured with SWB200_SG_TIMELINE on 16384 pairs (31.4 ms): the four forward kernels share the issue slots evenly and
+    // finish together at ~23.8 ms, so three result copies (2.4 ms each) are exposed.  Two alternatives made no difference:
+    // stream priorities (every block is resident anyway), and letting only two chunks' forward kernels run at a time (the
+    // chunks then finish in order, but each traceback runs beside forward warps and slows down: 31.3 ms).
     const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * 64;      // pairs that give every scheduler two warps of the forward kernel
     uint64_t chunk = (32ull << 20) / (uint64_t)len;
     if (chunk < wave / 2) chunk = wave / 2;
