@@ -522,7 +522,9 @@ def run_semiglobal_arm(args):
     insert / delete, source.cpp:2750-2771) through the adaptive-banded X-drop aligner, score + traceback.
     value = alignments/s device-resident; e2e = swb200_semiglobal_xdrop_batch with pinned host arrays."""
     import swb200
-    n = args.pairs if args.pairs != 100_000_000 else 16384
+    # default batch: 8 pairs x 4 warps per scheduler x 4 schedulers x 148 SMs = 18944 pairs -- the forward kernel runs one warp per
+    # eight pairs, and a batch that is not a multiple of 148 x 32 pairs leaves some schedulers a warp short (16384 pairs: 3.46 per scheduler)
+    n = args.pairs if args.pairs != 100_000_000 else 148 * 128
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
