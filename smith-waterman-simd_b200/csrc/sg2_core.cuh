@@ -159,12 +159,12 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     for (int w = 0; w < 4; ++w) D[w] = right ? s.V[w] : s.H[w];       // source.cpp:1892,1903
     const uint32_t one = env.one(), zero = env.zero();     // a 1 and a 0 the compiler cannot see: they keep bookkeeping on the FMA pipe
     const uint32_t gh = got * (one << 16) + 0x00010000u, ga = got << 8, gb = got >> 16, gv = got * one + 2u;
-    const uint32_t sR = s.right * (one << 4), sD = 16u - sR, cR = s.right * (one << 3), cD = 8u - cR;      // shift amounts: 16 / 8 or 0
+    const uint32_t down = s.right * (0u - one) + one;      // 1 - right, as a multiply-add
+    const uint32_t sR = s.right * (one << 4), sD = down * (one << 4), cR = s.right * (one << 3), cD = down * (one << 3);      // shift amounts: 16 / 8 or 0
     s.H[3] = fsl(s.R1[2], s.R1[3], sD); s.H[2] = fsl(s.R1[1], s.R1[2], sD); s.H[1] = fsl(s.R1[0], s.R1[1], sD); s.H[0] = fsl(gh, s.R1[0], sD);
     s.V[0] = fsr(s.R2[0], s.R2[1], sR); s.V[1] = fsr(s.R2[1], s.R2[2], sR); s.V[2] = fsr(s.R2[2], s.R2[3], sR); s.V[3] = fsr(s.R2[3], gv, sR);
     s.A[1] = fsl(s.A[0], s.A[1], cD); s.A[0] = fsl(ga, s.A[0], cD);
     s.B[0] = fsr(s.B[0], s.B[1], cR); s.B[1] = fsr(s.B[1], gb, cR);
-    const uint32_t down = one - s.right;
     s.pos_y += (int32_t)down;
     const uint32_t moves = (down + s.prev_down * (one << 1)) * (one << 8);      // byte 1: bit 0 = this round moved down, bit 1 = the one before
     s.prev_down = down;
@@ -183,6 +183,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     }
     // ---- the shuffle stage
     uint32_t m = vmax2(vmax3(t2[0], t2[1], t2[2]), t2[3]);
+    m = vmax2(m, prmt(m, m, 0x1032u));                     // both halves: the maximum of this lane's eight cells
     const uint32_t xr = prmt(t2[0], s.B[0], 0x0410u), xd = prmt(t2[3], s.A[1], 0x0732u);
     const uint32_t m1 = env.shfl_xor(m, 1), m2 = env.shfl_xor(m, 2), m3 = env.shfl_xor(m, 3);
     const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[3], 3);
@@ -203,8 +204,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     // two above it, and the threshold moves exactly when a cell reaches 72 -- so the amount subtracted this round,
     // c = 1 + off, comes from one packed compare; the bookkeeping of the best (below) is off the critical path.
     m = vmax2(vmax3(m, m1, m2), m3);
-    const uint32_t z = vaddmax2(m, 0xFEE1FEE1u, 0u);       // max(m - 287, 0) per half: 1 iff the half is 4 * 72
-    const uint32_t off = (z | (z >> 16)) & 1u;
+    const uint32_t off = vaddmax2(m, 0xFEE1FEE1u, 0u) & 1u;        // max(m - 287, 0): 1 iff the maximum is 4 * 72
     // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
     const uint32_t nc = 0xFFFCFFFCu - off * 0x00040004u;   // (-4c, -4c)
 #pragma unroll
@@ -226,7 +226,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     s.next_raw = edge ? s.next2_raw : s.next_raw;
     s.next2_raw = ld_u8_if(role_seq + s.cidx, edge && (uint32_t)s.cidx < (uint32_t)len, edge ? (q == 0 ? 4u : 5u) : s.next2_raw);
     // ---- the best so far (source.cpp:1928-1931: strict, the FIRST round that reaches it)
-    const int32_t rmax = sg2_half(m, 0) > sg2_half(m, 1) ? sg2_half(m, 0) : sg2_half(m, 1);
+    const int32_t rmax = sg2_half(m, 0);
     const int32_t amax = (rmax >> 2) - 1 + s.T;            // with the reference's +70 offset
     if (amax > s.best) {
         s.best = amax; s.best_round = round; s.best_py = s.pos_y; s.best_m = rmax;

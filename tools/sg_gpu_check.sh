@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 (timeout 600 python -m pytest tests/test_semiglobal_gpu.py -x -q 2>&1 | tail -3)
-for P in 8192 16384; do
+for P in 8192 18944; do
   timeout 300 python bench.py --workload semiglobal --no-cpu-baseline --pairs $P > gpurun_out/bench_sg2_$P.json 2> gpurun_out/bench_sg2_$P.err
   tail -c 300 gpurun_out/bench_sg2_$P.err
   python -c "
