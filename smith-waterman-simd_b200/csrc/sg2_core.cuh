@@ -76,7 +76,7 @@ struct Sg2State {
                           //   tagged 1 (as a left neighbour) and 2 (as an upper neighbour)
     uint32_t H[4], V[4];  // the previous round's left / upper neighbours (views of the round before it), tagged 1 / 2
     uint32_t A[2], B[2];  // bases under the band: seq1 (byte c = cell c) and seq2
-    uint32_t Rb[4];       // t2 of the best round (to find the end cell); best_m = its maximum
+    uint32_t Rb[4];       // t2 of the best round (to find the end cell)
     uint32_t lut_lo, lut_hi;   // sd table: index 0 = match
     uint32_t right;       // the next round moves right (else down)
     uint32_t got;         // what enters this lane from its neighbour in the next round: bits 0-15 cell, 16-23 base
@@ -86,7 +86,7 @@ struct Sg2State {
     int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (lane 3)
     int32_t pos_y;        // the band's upper-right cell is (pos_y, round - pos_y), source.cpp:1873-1874
     uint32_t prev_down;   // the previous round moved down
-    int32_t best, T, best_round, best_py, best_m;
+    int32_t best, T, best_round, best_py;
 };
 
 SWB_HD int32_t sg2_half(uint32_t w, int hi) { return (int32_t)(int16_t)(hi ? (w >> 16) : (w & 0xffffu)); }
@@ -118,7 +118,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
     }
     s.lut_lo = 0x0303030Bu - 0x02020202u; s.lut_hi = 0x03030303u - 0x02020202u;      // round 1 moves right: diag carries tag 2
     s.pos_y = 0; s.prev_down = 0u;
-    s.best = SG2_X; s.best_round = 0; s.best_py = 0; s.best_m = 4 * (SG2_X - 1);
+    s.best = SG2_X; s.best_round = 0; s.best_py = 0;
     // bases enter at cell 0 on a down move (lane 0: seq1p[pos_y + 31] = seq1[pos_y + 30]) and at cell 31 on a
     // right move (lane 3: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
     s.role_base = SG2_F | (q == 0 ? 0x800000u : 0u);
@@ -148,7 +148,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
 // receiver applies the drop itself, and the direction test is restated on t2:
 //     result[0] < result[31]   <=>   t2[0] < t2[31]  and  t2[31] - c >= 0
 // (with c the amount subtracted this round; dropped cells compare as the smallest value).
-template <class Env>
+template <bool RECORD, class Env>
 SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride)
 {
     const int q = env.q();
@@ -157,7 +157,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     uint32_t D[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) D[w] = right ? s.V[w] : s.H[w];       // source.cpp:1892,1903
-    const uint32_t one = env.one(), zero = env.zero();     // a 1 and a 0 the compiler cannot see: they keep bookkeeping on the FMA pipe
+    const uint32_t one = env.one();                        // a 1 the compiler cannot see: it keeps bookkeeping adds and shifts multiply-adds
     const uint32_t gh = got * (one << 16) + 0x00010000u, ga = got << 8, gb = got >> 16, gv = got * one + 2u;
     const uint32_t down = s.right * (0u - one) + one;      // 1 - right, as a multiply-add
     const uint32_t sR = s.right * (one << 4), sD = down * (one << 4), cR = s.right * (one << 3), cD = down * (one << 3);      // shift amounts: 16 / 8 or 0
@@ -174,11 +174,10 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     sd[0] = prmt(s.lut_lo, s.lut_hi, x0); sd[1] = prmt(s.lut_lo, s.lut_hi, x0 >> 16);
     sd[2] = prmt(s.lut_lo, s.lut_hi, x1); sd[3] = prmt(s.lut_lo, s.lut_hi, x1 >> 16);
     // ---- the cells (source.cpp:1916-1926); the tag of the winner is what the traceback will find (source.cpp:1960-1969)
-    uint32_t t[4], t2[4], dsum[4];
+    uint32_t t[4], t2[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        dsum[w] = vadd2(D[w], sd[w]);
-        t[w] = vmax3(dsum[w], s.H[w], s.V[w]);
+        t[w] = vmax3(vadd2(D[w], sd[w]), s.H[w], s.V[w]);
         t2[w] = t[w] & SG2_UNTAG;
     }
     // ---- the shuffle stage
@@ -190,10 +189,9 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     const uint32_t gn = env.shfl(xr, q + 1), gp = env.shfl(xd, q - 1);
     // ---- the record (independent of the shuffles): tags of cells 0,2,4,6 in byte 0, of 1,3,5,7 in byte 2, the two moves in byte 1
     // (tag = t - t2, no borrow between the halves: clearing bits never raises a half; summed as multiply-adds)
-    {
+    if (RECORD) {
         const uint32_t c4 = one << 2, c16 = one << 4, c64 = one << 6, mone = 0u - one;
-        // (dsum enters with weight 0: a second use keeps its add a VIADD on the FMA pipe instead of a fused add-max on the ALU pipe)
-        uint32_t neg = t2[0] * one + t2[1] * c4 + (dsum[0] + dsum[1] + dsum[2] + dsum[3]) * zero;
+        uint32_t neg = t2[0] * one + t2[1] * c4;
         uint32_t acc = t[0] * one + moves;
         neg = t2[2] * c16 + neg; acc = t[1] * c4 + acc;
         neg = t2[3] * c64 + neg; acc = t[2] * c16 + acc;
@@ -229,7 +227,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     const int32_t rmax = sg2_half(m, 0);
     const int32_t amax = (rmax >> 2) - 1 + s.T;            // with the reference's +70 offset
     if (amax > s.best) {
-        s.best = amax; s.best_round = round; s.best_py = s.pos_y; s.best_m = rmax;
+        s.best = amax; s.best_round = round; s.best_py = s.pos_y;
 #pragma unroll
         for (int w = 0; w < 4; ++w) s.Rb[w] = t2[w];
     }
@@ -248,10 +246,15 @@ template <class Env>
 SWB_HD uint32_t sg2_finish(const Sg2State& s, Env& env, int32_t& score, int32_t& end_y, int32_t& end_x)
 {
     const int q = env.q();
+    uint32_t m = vmax2(vmax3(s.Rb[0], s.Rb[1], s.Rb[2]), s.Rb[3]);        // the best round's maximum, once more
+    m = vmax2(m, prmt(m, m, 0x1032u));
+    m = vmax2(m, env.shfl_xor(m, 1));
+    m = vmax2(m, env.shfl_xor(m, 2));
+    const int32_t best_m = sg2_half(m, 0);
     int32_t loc = -1;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        if (sg2_half(s.Rb[c >> 1], c & 1) == s.best_m) loc = 8 * q + c;
+        if (sg2_half(s.Rb[c >> 1], c & 1) == best_m) loc = 8 * q + c;
     int32_t o = (int32_t)env.shfl_xor((uint32_t)loc, 1); loc = loc > o ? loc : o;
     o = (int32_t)env.shfl_xor((uint32_t)loc, 2); loc = loc > o ? loc : o;
     score = s.best - SG2_X;

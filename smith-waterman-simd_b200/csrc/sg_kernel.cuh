@@ -64,20 +64,20 @@ struct SgOut {
 constexpr int SG2_THREADS = 32;
 
 struct Sg2DevEnv {
-    int lane4; uint32_t one_, zero_;
+    int lane4; uint32_t one_;
     __device__ __forceinline__ int q() const { return lane4; }
     __device__ __forceinline__ uint32_t one() const { return one_; }
-    __device__ __forceinline__ uint32_t zero() const { return zero_; }
     __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
     __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 };
 
+template <bool RECORD>         // false: score and end cell only, no round records are written
 __global__ void __launch_bounds__(SG2_THREADS)
 sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
-                 uint4* __restrict__ traces, const SgOut out, const uint32_t one, const uint32_t zero)
+                 uint4* __restrict__ traces, const SgOut out, const uint32_t one)
 {
     const unsigned lane = threadIdx.x & 31u;
-    Sg2DevEnv env{(int)(lane & 3u), one, zero};
+    Sg2DevEnv env{(int)(lane & 3u), one};
     const unsigned long long warp = ((unsigned long long)blockIdx.x * SG2_THREADS + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * SG2_THREADS) >> 5;
     const uint32_t rounds_cap = sg_rounds_cap(len);
@@ -97,13 +97,13 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
         sg2_init(s, env, s1, s2, len);
         const uint8_t* const role = env.q() == 0 ? s1 : s2;
         for (int round = 1; round < max_round; ++round) {
-            const bool go = sg2_round(s, env, role, len, round, rec_row, 4 * SG_GROUP);
+            const bool go = sg2_round<RECORD>(s, env, role, len, round, rec_row, 4 * SG_GROUP);
             if ((round & 3) == 0 && !__any_sync(0xffffffffu, go)) break;      // a finished pair stays finished: asking every fourth round is enough
         }
         int32_t score, end_y, end_x;
         const uint32_t rec0 = sg2_finish(s, env, score, end_y, end_x);
         if (live) {
-            rec_row[env.q()] = rec0;
+            if (RECORD) rec_row[env.q()] = rec0;
             if (env.q() == 0) { out.score[p] = score; out.end_y[p] = end_y; out.end_x[p] = end_x; }
         }
     }

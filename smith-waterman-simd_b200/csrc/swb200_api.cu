@@ -568,8 +568,9 @@ int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* 
         const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);      // a warp per group of 32 pairs
         const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
         const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
-        sg2_xdrop_kernel<<<(unsigned)(need < cap ? need : cap), SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m,
-                                                                                     sc.traces, out, 1u, 0u);
+        const unsigned fgrid = (unsigned)(need < cap ? need : cap);
+        if (d_ops) sg2_xdrop_kernel<true><<<fgrid, SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m, sc.traces, out, 1u);
+        else sg2_xdrop_kernel<false><<<fgrid, SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m, sc.traces, out, 1u);
         SWB_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (d_ops) {
@@ -1072,8 +1073,8 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     cudaFuncAttributes fa{};
     int blocks = 0;
-    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel));
-    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel, SG2_THREADS, 0));
+    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true>));
+    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true>, SG2_THREADS, 0));
     info->threads_per_block = SG2_THREADS;
     info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
     info->fast_path = 0;

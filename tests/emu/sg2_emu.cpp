@@ -30,7 +30,6 @@ struct HostEnv {
     Quad* quad; int lane;
     int q() const { return lane; }
     uint32_t one() const { return 1u; }
-    uint32_t zero() const { return 0u; }
     uint32_t shfl(uint32_t v, int src)
     {
         const int ph = quad->phase[lane]++ & 1;
@@ -54,7 +53,7 @@ void lane_main(int lane)
     int round = 1;
     // On the device a finished pair keeps running rounds beside the live pairs of its warp: run EVERY round here, so
     // that a finished pair that is not inert (a best, a threshold or a record that still moves) shows up as a mismatch.
-    for (; round < max_round; ++round) sg2_round(s, env, role, Q.len, round, Q.rec.data(), 4);
+    for (; round < max_round; ++round) sg2_round<true>(s, env, role, Q.len, round, Q.rec.data(), 4);
     int32_t sc, ey, ex;
     Q.rec[lane] = sg2_finish(s, env, sc, ey, ex);
     if (lane == 0) { Q.score = sc; Q.end_y = ey; Q.end_x = ex; Q.rounds_run = round; }
