@@ -166,13 +166,16 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
 #pragma unroll
         for (int q = 0; q < 8; ++q) rec[q] = ring[((rb - q) & (SG_TB_DEPTH - 1)) * 32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {           // ... then the dependent chain: element -> lane word -> tag -> next element
-            const int r = rb - q;
-            if (rw == r && r >= 1 && n_ops < cap) {
-                const uint32_t w = (o & 16) ? ((o & 8) ? rec[q].w : rec[q].z) : ((o & 8) ? rec[q].y : rec[q].x);
-                row[cap - 1u - n_ops] = (uint8_t)sg2_tb_step(w, o, rw);                 // 0 = diagonal, 1 = down, 2 = right
-                ++n_ops;
-            }
+        for (int q = 0; q < 8; ++q) {           // ... then the dependent chain: element -> lane word -> tag -> next element,
+            const int r = rb - q;               //     branch-free (selects and one predicated store)
+            const bool act = rw == r && r >= 1 && n_ops < cap;
+            const uint32_t w = (o & 16) ? ((o & 8) ? rec[q].w : rec[q].z) : ((o & 8) ? rec[q].y : rec[q].x);
+            int o2 = o, r2 = rw;
+            const uint32_t op = sg2_tb_step(w, o2, r2);                                 // 0 = diagonal, 1 = down, 2 = right
+            if (act) row[cap - 1u - n_ops] = (uint8_t)op;
+            o = act ? o2 : o;
+            rw = act ? r2 : rw;
+            n_ops += act ? 1u : 0u;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {           // refill the slots just read with the rounds DEPTH further down
