@@ -485,13 +485,13 @@ SG_RECORD_BYTES_PER_ROUND = 16       # what the kernels move: one 16-byte record
 def sg_instr_counts():
     """Warp instructions per warp-round (eight pairs advance one round) of the forward kernel, from the committed ncu
     capture: total and ALU-pipe.  Fallback = the SASS count of the loop body."""
-    path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v7_summary.json")
+    path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v10_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v7_summary.json"
+        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v10_summary.json"
     except (OSError, KeyError, ValueError):
-        return 163.0, 85.0, "SASS count of the loop body (cuobjdump)"
+        return 158.0, 80.0, "SASS count of the loop body (cuobjdump)"
 
 
 def sg_cpu_reference(a, b, budget_s=20.0):
