@@ -191,6 +191,9 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
 // Moves each row's op string from the right edge (where the traceback left it) to the left edge.  One block per
 // row; a step reads 256 x 16 bytes into registers, synchronises, and writes them `shift` bytes lower: the
 // destination of a step never reaches the source of a later one, so an overlapping move is safe.
+// Rows of a multiple of 16 bytes move as aligned words: five 32-bit loads, four byte-permutes (the shift modulo 4)
+// and one 16-byte store per thread and step; up to three bytes past the string may be overwritten (they are
+// unspecified: the string's length is n_ops).  Other rows move byte by byte.
 __global__ void __launch_bounds__(256)
 sg_left_align_kernel(const int len, const unsigned long long n, const SgOut out)
 {
@@ -201,6 +204,23 @@ sg_left_align_kernel(const int len, const unsigned long long n, const SgOut out)
     if (n_ops == 0u || n_ops >= cap) return;
     uint8_t* const row = out.ops + p * (unsigned long long)cap;
     const uint32_t shift = cap - n_ops;
+    if ((cap & 15u) == 0u && (reinterpret_cast<uintptr_t>(out.ops) & 15u) == 0u) {
+        uint32_t* const row32 = reinterpret_cast<uint32_t*>(row);
+        const uint32_t s4 = shift >> 2, sel = 0x3210u + 0x1111u * (shift & 3u), last = cap / 4u - 1u;
+        const uint32_t n_words = (n_ops + 3u) >> 2;
+        for (uint32_t base = 0; base < n_words; base += 256u * 4u) {
+            const uint32_t k0 = base + threadIdx.x * 4u;
+            uint32_t src[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) src[q] = (k0 < n_words) ? row32[min(s4 + k0 + q, last)] : 0u;
+            __syncthreads();
+            if (k0 < n_words)
+                *reinterpret_cast<uint4*>(row32 + k0) = make_uint4(__byte_perm(src[0], src[1], sel), __byte_perm(src[1], src[2], sel),
+                                                                  __byte_perm(src[2], src[3], sel), __byte_perm(src[3], src[4], sel));
+            __syncthreads();
+        }
+        return;
+    }
     for (uint32_t base = 0; base < n_ops; base += 256u * 16u) {
         const uint32_t i0 = base + threadIdx.x * 16u;
         uint8_t b[16];
