@@ -86,6 +86,7 @@ struct Sg2State {
     int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (lane 3)
     int32_t pos_y;        // the band's upper-right cell is (pos_y, round - pos_y), source.cpp:1873-1874
     uint32_t prev_down;   // the previous round moved down
+    uint32_t dead;        // 1 once a round left every cell <= 0: the reference stops there (source.cpp:1938-1941)
     int32_t best, T, best_round, best_py;
 };
 
@@ -117,7 +118,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
         s.B[k] = SG2_PAD_B * 0x01010101u;
     }
     s.lut_lo = 0x0303030Bu - 0x02020202u; s.lut_hi = 0x03030303u - 0x02020202u;      // round 1 moves right: diag carries tag 2
-    s.pos_y = 0; s.prev_down = 0u;
+    s.pos_y = 0; s.prev_down = 0u; s.dead = 0u;
     s.best = SG2_X; s.best_round = 0; s.best_py = 0;
     // bases enter at cell 0 on a down move (lane 0: seq1p[pos_y + 31] = seq1[pos_y + 30]) and at cell 31 on a
     // right move (lane 3: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
@@ -140,8 +141,8 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
 // `rec_row` = this pair's records: lane word q of round r at rec_row[rec_stride * r + q] (rec_stride = 4 when a pair's
 // records are contiguous, 128 when 32 pairs are interleaved round by round).  Returns false when every cell is <= 0
 // (source.cpp:1938);
-// a pair in that state is inert -- further rounds change neither its best nor its cells -- so the quads of a warp
-// may keep running together until the last one is done.
+// a pair in that state is kept inert from then on (see `dead`) -- further rounds change neither its best nor its
+// cells -- so the quads of a warp may keep running together until the last one is done.
 // All communication of a round is ONE stage of seven independent shuffles issued right after the cells are
 // computed (three for the maximum, two for the next direction, two for the boundary cell and base of either
 // direction): everything that follows them is lane-local.  They carry t2, the cells BEFORE the X-drop; the
@@ -204,7 +205,10 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     m = vmax2(vmax3(m, m1, m2), m3);
     const uint32_t off = vaddmax2(m, 0xFEE1FEE1u, 0u) & 1u;        // max(m - 287, 0): 1 iff the maximum is 4 * 72
     // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
-    const uint32_t nc = 0xFFFCFFFCu - off * 0x00040004u;   // (-4c, -4c)
+    // A finished pair must stay finished while its warp runs on: the round after the last one could otherwise revive a
+    // cell through its diagonal (two rounds back).  For a dead pair the subtrahend is so large that every cell of this
+    // round drops; from then on all its inputs are F.
+    const uint32_t nc = 0xFFFCFFFCu - off * 0x00040004u - s.dead * 0x3ED03ED0u;   // (-4c, -4c); dead: a further -16080
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         const uint32_t r = vminu2(vaddmax2(t2[w], nc, SG2_FF), SG2_FF);
@@ -232,12 +236,13 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
         for (int w = 0; w < 4; ++w) s.Rb[w] = t2[w];
     }
     s.T += (int32_t)off;                                   // T = max(best - 70, 1)
+    s.dead |= amax > 0 ? 0u : 1u;
     // next round's diagonal inputs are one frame older and carry the tag of the view they come from (ver 2 on a
     // right move, hor 1 on a down move): sd = 4 (score + 1 - off) + 3 - that tag
     const uint32_t dtag = (rn ? 2u : 1u) * 0x01010101u;
     s.lut_lo = 0x0303030Bu - off * 0x03030404u - dtag;     // off = 0: 0B 03 03 03, off = 1: 07 FF FF FF, less the tag
     s.lut_hi = 0x03030303u - off * 0x03030304u - dtag;     //          03 03 03 03,          FF FF FF FF
-    return amax > 0;
+    return s.dead == 0u;
 }
 
 // After the last round: the end cell is the upper-right-most cell of the best round that holds the best

@@ -39,3 +39,29 @@ def ops_to_traceback(ops: np.ndarray) -> np.ndarray:
     tb[1:, 0] = np.cumsum(ops != 2)
     tb[1:, 1] = np.cumsum(ops != 1)
     return tb
+
+
+def xdrop_edge_cases(rng):
+    """Pairs built to sit ON the aligner's thresholds: a run of mismatches (or a gap) of exactly the length at which the
+    X-drop of 70 does or does not end the alignment, after a prefix that has or has not lifted the score above 70 (the
+    threshold T = max(best - 70, 1) is pinned at 1 until then), and again near the end of the sequences."""
+    cases = []
+    for length in (160, 400, 1025):
+        for prefix in (0, 1, 2, 35, 69, 70, 71, 72, 73, 120):
+            for run in (33, 34, 35, 36, 37, 68, 69, 70, 71, 72):
+                if prefix + run + 10 > length:
+                    continue
+                a = rng.integers(0, 4, length, dtype=np.uint8)
+                b = a.copy()
+                a[prefix:prefix + run] = 0          # a stretch that matches on NO diagonal: the alignment can only pay its way through
+                b[prefix:prefix + run] = 1
+                cases.append((a, b))
+        for prefix in (5, 80, 300):
+            for gap in (1, 15, 16, 17, 31, 32, 33, 40):
+                if prefix + gap + 40 > length:
+                    continue
+                a = rng.integers(0, 4, length, dtype=np.uint8)
+                b = np.concatenate([a[:prefix], a[prefix + gap:], rng.integers(0, 4, gap, dtype=np.uint8)])      # a deletion: the band must drift
+                cases.append((a, b))
+                cases.append((b, a))                                                                       # ... and an insertion
+    return cases

@@ -197,3 +197,18 @@ def test_sg2_emu_equals_the_oracle_at_many_lengths(sg2, oracle):
             got = sg2(a, b)
             assert got[:3] == exp[:3], (length, kind)
             assert np.array_equal(got[3], exp[3]), (length, kind)
+
+
+def test_sg2_emu_on_the_xdrop_thresholds(sg2, oracle):
+    rng = np.random.default_rng(7070)
+    from sg_common import xdrop_edge_cases
+    cases = xdrop_edge_cases(rng)
+    assert len(cases) > 300
+    ended_early = 0
+    for k, (a, b) in enumerate(cases):
+        exp = oracle.semiglobal_xdrop(a, b)
+        got = sg2(a, b)
+        assert got[:3] == exp[:3], k
+        assert np.array_equal(got[3], exp[3]), k
+        ended_early += exp[1] < a.size // 2
+    assert 20 < ended_early < len(cases) - 20      # both outcomes occur: the run ended the alignment / the alignment got past it

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-from sg_common import fnv1a64_bytes, load_cases, ops_to_traceback
+from sg_common import fnv1a64_bytes, load_cases, ops_to_traceback, xdrop_edge_cases
 
 pytestmark = pytest.mark.gpu
 NCPU = min(os.cpu_count() or 1, 16)
@@ -173,3 +173,21 @@ def test_device_resident_entry_and_errors(ctx, swb, oracle):
     assert e.value.code == swb.ERR_ARG
     score, tb = swb.SemiGlobal_AdaptiveBanded_XDrop_111_32_70_b200(cases[0]["seq1"], cases[0]["seq2"])
     assert score == cases[0]["score"] and np.array_equal(np.array(tb, np.int32), ops_to_traceback(cases[0]["ops"]))
+
+
+def test_pairs_on_the_xdrop_thresholds_beside_live_pairs(ctx, oracle):
+    # Pairs built to sit on the aligner's thresholds (sg_common.xdrop_edge_cases): many of them end early, in the same
+    # warp as pairs that run on.  A finished pair must stay finished while its warp keeps running rounds -- the round
+    # after its last one could revive a cell through the diagonal, which the reference never computes (source.cpp:1938).
+    rng = np.random.default_rng(7070)
+    by_len = {}
+    for a, b in xdrop_edge_cases(rng):
+        by_len.setdefault(a.size, []).append((a, b))
+    assert len(by_len) >= 3
+    for length, cs in by_len.items():
+        a = np.stack([c[0] for c in cs]); b = np.stack([c[1] for c in cs])
+        perm = rng.permutation(len(cs))                      # early enders and survivors side by side
+        a, b = a[perm], b[perm]
+        r = ctx.semiglobal_xdrop(a, b)
+        check_against_oracle(oracle, r, a, b)
+        assert (r["end_y"] < length // 2).sum() > 5 and (r["end_y"] > length // 2).sum() > 5

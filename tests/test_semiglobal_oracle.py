@@ -62,3 +62,35 @@ def test_short_lengths_have_the_obvious_answers(oracle):
     y = np.concatenate([np.delete(x, 50), [x[49] ^ 1]])
     score, ey, ex, ops = oracle.semiglobal_xdrop(x, y)
     assert score == 98 and (ops != 0).sum() == 1 and ey - ex == 1
+
+
+def test_on_the_xdrop_threshold_the_scalar_reference_is_the_specification(oracle):
+    """A stretch that matches on no diagonal, of exactly the length at which the X-drop decides: the restatement must
+    equal the reference's SCALAR aligner (source.cpp:1836-1976).  The reference's AVX2 forms are asserted equal to it
+    only on TestSemiGlobal's inputs (source.cpp:2774-2784); on these inputs some of them give a different answer
+    (e.g. _simd_mark4 ends at (1,1) where the scalar aligns to the end), so they cannot all be matched -- the B200
+    kernels follow the scalar, as this oracle does."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(5)
+    cases = []
+    for prefix in (0, 1, 2, 3):
+        for run in (68, 69, 70, 71, 72):
+            a = rng.integers(0, 4, 16384, dtype=np.uint8)
+            b = a.copy()
+            a[prefix:prefix + run] = 0
+            b[prefix:prefix + run] = 1
+            cases.append((a, b))
+
+    def one(c):
+        a, b = c
+        s0, tb0 = oracle.ref_semiglobal(0, a, b)
+        s, ey, ex, ops = oracle.semiglobal_xdrop(a, b)
+        same = s == s0 and np.array_equal(oracle.ops_to_traceback(ops), tb0)
+        s4, _ = oracle.ref_semiglobal(4, a, b)
+        return same, s4 == s0, s0
+    with ThreadPoolExecutor(8) as ex:
+        out = list(ex.map(one, cases))
+    assert all(o[0] for o in out)                      # restatement == scalar reference, score and traceback
+    assert any(not o[1] for o in out)                  # ... while _simd_mark4 is NOT equal to the scalar on some of them
+    assert any(o[2] > 16000 for o in out) and any(o[2] < 10 for o in out)      # both sides of the threshold occur
