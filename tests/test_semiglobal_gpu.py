@@ -191,3 +191,25 @@ def test_pairs_on_the_xdrop_thresholds_beside_live_pairs(ctx, oracle):
         r = ctx.semiglobal_xdrop(a, b)
         check_against_oracle(oracle, r, a, b)
         assert (r["end_y"] < length // 2).sum() > 5 and (r["end_y"] > length // 2).sum() > 5
+
+
+def test_adversarial_inputs_against_oracle(ctx, oracle):
+    # low-complexity alphabets, periodic repeats, runs of mismatches and indels of every length around the band width
+    # (32) and the X-drop (70) -- the generator of tools/sg_fuzz.py, cut to fixed lengths; every pair checked
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sg_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sg_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(424242)
+    for length in (37, 150, 420):
+        aa, bb = [], []
+        while len(aa) < 1500:
+            a, b = fz.make_case(rng)
+            if a.size >= length:
+                aa.append(a[:length]); bb.append(b[:length])
+            elif a.size >= 8:
+                reps = -(-length // a.size)
+                aa.append(np.tile(a, reps)[:length]); bb.append(np.tile(b, reps)[:length])
+        a = np.stack(aa); b = np.stack(bb)
+        r = ctx.semiglobal_xdrop(a, b)
+        check_against_oracle(oracle, r, a, b)
