@@ -315,3 +315,23 @@ def test_one_vs_many_equals_reference_x32(ctx, swb, oracle):
     got = ctx.score_one_vs_many(q, t, swb.MATRIX_SPEEDTEST, 15)
     assert np.array_equal(got, ctx.score_batch(q, np.repeat(t[None, :], n, axis=0), swb.MATRIX_SPEEDTEST, 15))
     assert np.array_equal(got[:3000], oracle.score_batch(q[:3000], np.repeat(t[None, :], 3000, axis=0), swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
+def test_random_matrices_and_adversarial_sequences(ctx, oracle):
+    # the generator of tools/sw_fuzz.py: score matrices and gaps drawn over the whole reference domain (both kernels get
+    # picked), low-complexity / periodic / shifted sequences; every score compared with the oracle
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sw_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sw_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(20261018)
+    fast = general = 0
+    for _ in range(250):
+        a, b, m, gap = fz.make_batch(rng, n=66)
+        got = ctx.score_batch(a, b, m, gap)
+        assert np.array_equal(got, oracle.score_batch(a, b, m, gap)), (m.tolist(), gap)
+        if ctx.kernel_info(m, gap)["fast_path"]:
+            fast += 1
+        else:
+            general += 1
+    assert fast > 20 and general > 20

@@ -1,0 +1,74 @@
+"""Differential fuzzing of the Smith-Waterman kernel's per-thread code (host emulator, tests/emu/emu_main.cpp) against
+the oracle: random score matrices and gaps over the whole reference domain, low-complexity and repetitive sequences.
+Development tool:  python tools/sw_fuzz.py [seconds] [processes]"""
+import ctypes as C
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make_batch(rng, n=64, L=128):
+    alpha = int(rng.choice([1, 2, 3, 4, 4]))
+    a = rng.integers(0, alpha, (n, L)).astype(np.uint8)
+    b = a.copy()
+    mode = int(rng.integers(0, 4))
+    if mode == 0:
+        b = rng.integers(0, alpha, (n, L)).astype(np.uint8)
+    elif mode == 1:
+        hit = rng.random((n, L)) < rng.random()
+        b[hit] = rng.integers(0, 4, int(hit.sum()))
+    elif mode == 2:
+        k = int(rng.integers(1, 64))
+        b = np.roll(a, k, axis=1)
+    else:
+        period = int(rng.integers(1, 12))
+        a = np.tile(rng.integers(0, 4, (n, period)), (1, L // period + 1))[:, :L].astype(np.uint8)
+        b = np.roll(a, int(rng.integers(0, period + 3)), axis=1)
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        m = rng.integers(-127, 128, 16)
+    elif kind == 1:
+        m = np.where(np.eye(4, dtype=bool), rng.integers(1, 128), -rng.integers(0, 128)).reshape(16)
+    elif kind == 2:
+        m = rng.integers(-5, 6, 16)
+    else:
+        m = rng.choice([-127, -1, 0, 1, 127], 16)
+    gap = int(rng.choice([0, 1, 2, 15, 63, 64, 126, 127, int(rng.integers(0, 128))]))
+    return np.ascontiguousarray(a), np.ascontiguousarray(b), m.astype(np.int8), gap
+
+
+def worker(args):
+    seed, seconds = args
+    from oracle import oracle as O
+    O.build()
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "libswemu.so"))
+    lib.swemu_score_batch_len.restype = C.c_int
+    lib.swemu_score_batch_len.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    rng = np.random.default_rng(seed)
+    t0 = time.time()
+    n = 0
+    while time.time() - t0 < seconds:
+        a, b, m, gap = make_batch(rng)
+        exp = O.score_batch(a, b, m, gap)
+        for fg in (0, 1):
+            out = np.empty(a.shape[0], np.int32)
+            rc = lib.swemu_score_batch_len(128, a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], fg)
+            if rc < 0 or not np.array_equal(out, exp):
+                np.savez(f"/tmp/swfuzz_{seed}_{n}.npz", a=a, b=b, m=m, gap=gap)
+                return ("MISMATCH", seed, n, rc, fg, m.tolist(), gap)
+        n += 1
+    return ("ok", seed, n)
+
+
+if __name__ == "__main__":
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60
+    procs = int(sys.argv[2]) if len(sys.argv) > 2 else max(1, (os.cpu_count() or 2) - 1)
+    with mp.Pool(procs) as pool:
+        for r in pool.imap_unordered(worker, [(2000 + i, seconds) for i in range(procs)]):
+            print(r, flush=True)
