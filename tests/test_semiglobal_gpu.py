@@ -213,3 +213,19 @@ def test_adversarial_inputs_against_oracle(ctx, oracle):
         a = np.stack(aa); b = np.stack(bb)
         r = ctx.semiglobal_xdrop(a, b)
         check_against_oracle(oracle, r, a, b)
+
+
+def test_all_visible_gpus_share_a_batch(swb, oracle):
+    # pairs are independent -- contiguous index ranges per GPU, every GPU writes its own slice of the
+    # caller's arrays, no collective.  (With one visible GPU this is the single-GPU path.)
+    import torch
+    g = torch.cuda.device_count()
+    rng = np.random.default_rng(31337)
+    n, length = 2501, 640
+    a = rng.integers(0, 4, (n, length), dtype=np.uint8)
+    b = np.where(rng.random((n, length)) < 0.9, a, rng.integers(0, 4, (n, length), dtype=np.uint8)).astype(np.uint8)
+    b[::11] = np.roll(a[::11], 9, axis=1)
+    with swb.Context(n_devices=g) as c:
+        assert c.n_devices == g
+        r = c.semiglobal_xdrop(a, b)
+    check_against_oracle(oracle, r, a, b, list(range(0, n, 7)) + list(range(n - 40, n)))
