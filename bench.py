@@ -479,19 +479,20 @@ def run_stream_arm(args):
 SG_LEN = 16384
 SG_ROUNDS_NOMINAL = 2 * SG_LEN       # a pair aligned end to end runs one round per anti-diagonal
 SG_TRACE_BYTES_PER_ROUND = 8.125     # 64 direction bits + 1 move bit, written once and read once by the traceback
+SG_PAIRS_PER_WARP = 16.0             # the forward kernel: two lanes per pair
 SG_RECORD_BYTES_PER_ROUND = 16       # what the kernels move: one 16-byte record per round, written by the forward kernel, read by the traceback
 
 
 def sg_instr_counts():
-    """Warp instructions per warp-round (eight pairs advance one round) of the forward kernel, from the committed ncu
+    """Warp instructions per warp-round (sixteen pairs advance one round) of the forward kernel, from the committed ncu
     capture: total and ALU-pipe.  Fallback = the SASS count of the loop body."""
-    path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v10_summary.json")
+    path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v11_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v10_summary.json"
+        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v11_summary.json"
     except (OSError, KeyError, ValueError):
-        return 158.0, 80.0, "SASS count of the loop body (cuobjdump)"
+        return 224.0, 117.0, "SASS count of the loop body (cuobjdump)"
 
 
 def sg_cpu_reference(a, b, budget_s=20.0):
@@ -522,8 +523,8 @@ def run_semiglobal_arm(args):
     insert / delete, source.cpp:2750-2771) through the adaptive-banded X-drop aligner, score + traceback.
     value = alignments/s device-resident; e2e = swb200_semiglobal_xdrop_batch with pinned host arrays."""
     import swb200
-    # default batch: 8 pairs x 4 warps per scheduler x 4 schedulers x 148 SMs = 18944 pairs -- the forward kernel runs one warp per
-    # eight pairs, and a batch that is not a multiple of 148 x 32 pairs leaves some schedulers a warp short (16384 pairs: 3.46 per scheduler)
+    # default batch: 16 pairs x 2 warps per scheduler x 4 schedulers x 148 SMs = 18944 pairs -- the forward kernel runs one warp per
+    # sixteen pairs, and a batch that is not a multiple of 148 x 64 pairs leaves some schedulers a warp short
     n = args.pairs if args.pairs != 100_000_000 else 148 * 128
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
@@ -641,13 +642,13 @@ def run_semiglobal_arm(args):
         ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
     peaks = load_peaks()
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    # roofline of the forward kernel (the dominant one): its ALU pipe.  A warp-round advances eight pairs by one round;
+    # roofline of the forward kernel (the dominant one): its ALU pipe.  A warp-round advances sixteen pairs by one round;
     # it needs `alu_wr` ALU-pipe warp instructions (ncu), and an SM retires 2 of those per clock (63.5 lanes, INT_PEAK.json).
     instr_wr, alu_wr, instr_src = sg_instr_counts()
     int_peak = json.load(open(os.path.join(ROOT, "profiles", "INT_PEAK.json")))
     lanes = float(int_peak.get("alu_lanes_per_clk_per_sm", 63.5))
     alu_peak = lanes * info["sm_count"] * sm_mhz * 1e6            # thread-level ALU-pipe instructions per second
-    warp_rounds_per_s = (n / 8.0) * SG_ROUNDS_NOMINAL / (fwd_ms * 1e-3)
+    warp_rounds_per_s = (n / SG_PAIRS_PER_WARP) * SG_ROUNDS_NOMINAL / (fwd_ms * 1e-3)
     alu_achieved = warp_rounds_per_s * alu_wr * 32.0
     rounds_per_s = n * SG_ROUNDS_NOMINAL / (ms * 1e-3)
     trace_gbs = n * SG_ROUNDS_NOMINAL * SG_RECORD_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
@@ -668,9 +669,9 @@ def run_semiglobal_arm(args):
                      "achieved": alu_achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tinstr/s (thread-level ALU-pipe instructions)",
                      "frac": alu_achieved / alu_peak, "avg_launch_ms": fwd_ms, "share_of_step": fwd_ms / ms,
                      "alu_instr_per_warp_round": alu_wr, "instr_per_warp_round": instr_wr, "instr_src": instr_src,
-                     "warp_rounds_per_launch": (n / 8.0) * SG_ROUNDS_NOMINAL,
-                     "note": "four lanes per pair: one warp instruction serves eight pairs; a round is one serial chain per pair, so the kernel is bound by "
-                             "how many ALU-pipe instructions a round needs and by how many warps there are to overlap the chains (n / 8 warps), not by HBM",
+                     "warp_rounds_per_launch": (n / SG_PAIRS_PER_WARP) * SG_ROUNDS_NOMINAL,
+                     "note": "two lanes per pair: one warp instruction serves sixteen pairs; a round is one serial chain per pair, so the kernel is bound by "
+                             "how many ALU-pipe instructions a round needs and by how many warps there are to overlap the chains (n / 16 warps), not by HBM",
                      "traffic": None,
                      "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2, "record_bytes_per_round": SG_RECORD_BYTES_PER_ROUND * 2}},

@@ -71,19 +71,25 @@ constexpr uint32_t SG2_UNTAG = 0xFFFCFFFCu;
 constexpr uint32_t SG2_PAD_A = 0xC4u;              // base bytes: code * 0x11, seq1 side has bit 7 set; the pads (4, 5)
 constexpr uint32_t SG2_PAD_B = 0x55u;              //   differ from every base and from each other (source.cpp:1913-1915)
 
+// NW = packed words per lane: 4 (eight cells per lane, four lanes per pair, eight pairs per warp) or 8 (sixteen cells
+// per lane, two lanes per pair, sixteen pairs per warp).  The per-round overhead that does not depend on the cells
+// (direction, boundary exchange, threshold, loop) is paid once per lane, so the wider lane spends fewer instructions
+// per pair; the narrower one has twice the warps for the same batch.
+template <int NW>
 struct Sg2State {
-    uint32_t R1[4], R2[4];  // this round's cells 8q..8q+7 (word k = cells 2k | 2k+1 << 16): 4 (value - T), dropped = F,
+    static constexpr int kWords = NW, kCells = 2 * NW, kLanes = 32 / (2 * NW), kLast = kLanes - 1;
+    uint32_t R1[NW], R2[NW];  // this round's cells kCells q .. (word k = cells 2k | 2k+1 << 16): 4 (value - T), dropped = F,
                           //   tagged 1 (as a left neighbour) and 2 (as an upper neighbour)
-    uint32_t H[4], V[4];  // the previous round's left / upper neighbours (views of the round before it), tagged 1 / 2
-    uint32_t A[2], B[2];  // bases under the band: seq1 (byte c = cell c) and seq2
-    uint32_t Rb[4];       // t2 of the best round (to find the end cell)
+    uint32_t H[NW], V[NW];  // the previous round's left / upper neighbours (views of the round before it), tagged 1 / 2
+    uint32_t A[NW / 2], B[NW / 2];  // bases under the band: seq1 (byte c = cell c) and seq2
+    uint32_t Rb[NW];      // t2 of the best round (to find the end cell)
     uint32_t lut_lo, lut_hi;   // sd table: index 0 = match
     uint32_t right;       // the next round moves right (else down)
     uint32_t got;         // what enters this lane from its neighbour in the next round: bits 0-15 cell, 16-23 base
-    uint32_t next_raw;    // lanes 0 and 3: the next base to enter the band (code, or 4 / 5 = pad) ...
+    uint32_t next_raw;    // first and last lane: the next base to enter the band (code, or 4 / 5 = pad) ...
     uint32_t next2_raw;   // ... and the one after it: a base is loaded two entries before it is used
     uint32_t role_base;   // F | (0x80 << 16 in lane 0)
-    int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (lane 3)
+    int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (last lane)
     int32_t pos_y;        // the band's upper-right cell is (pos_y, round - pos_y), source.cpp:1873-1874
     uint32_t prev_down;   // the previous round moved down
     uint32_t dead;        // 1 once a round left every cell <= 0: the reference stops there (source.cpp:1938-1941)
@@ -92,25 +98,36 @@ struct Sg2State {
 
 SWB_HD int32_t sg2_half(uint32_t w, int hi) { return (int32_t)(int16_t)(hi ? (w >> 16) : (w & 0xffffu)); }
 
+template <int NW>
+SWB_HD uint32_t sg2_max_words(const uint32_t* t)
+{
+    uint32_t m = vmax3(t[0], t[1], t[2]);
+    if (NW == 4) return vmax2(m, t[3]);
+    m = vmax3(m, t[3], t[4]);
+    m = vmax3(m, t[5 % NW], t[6 % NW]);
+    return vmax2(m, t[7 % NW]);
+}
+
 // Round 0 (source.cpp:1876-1884): cell 31 = X_THRESHOLD, everything else unreached; band at (0, 31).  Round 1
 // always moves right (result[0] = 0 < result[31] = 70).
-template <class Env>
-SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uint8_t* seq2, int len)
+template <int NW, class Env>
+SWB_HD void sg2_init(Sg2State<NW>& s, const Env& env, const uint8_t* seq1, const uint8_t* seq2, int len)
 {
+    constexpr int LAST = Sg2State<NW>::kLast, CELLS = Sg2State<NW>::kCells;
     const int q = env.q();
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { s.Rb[w] = SG2_FF; s.H[w] = SG2_FF + 0x00010001u; s.V[w] = SG2_FF + 0x00020002u; }
+    for (int w = 0; w < NW; ++w) { s.Rb[w] = SG2_FF; s.H[w] = SG2_FF + 0x00010001u; s.V[w] = SG2_FF + 0x00020002u; }
     s.T = 1;                                         // max(70 - 70, 1)
-    if (q == 3) s.Rb[3] = ((uint32_t)(4 * (SG2_X - 1)) << 16) | SG2_F;
+    if (q == LAST) s.Rb[NW - 1] = ((uint32_t)(4 * (SG2_X - 1)) << 16) | SG2_F;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) { s.R1[w] = s.Rb[w] + 0x00010001u; s.R2[w] = s.Rb[w] + 0x00020002u; }
+    for (int w = 0; w < NW; ++w) { s.R1[w] = s.Rb[w] + 0x00010001u; s.R2[w] = s.Rb[w] + 0x00020002u; }
     // cell i holds seq1p[31 - i] = seq1[30 - i] (i = 31: pad) and seq2p[i] = pad
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NW / 2; ++k) {
         uint32_t a = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int idx = 30 - (8 * q + 4 * k + c);
+            const int idx = 30 - (CELLS * q + 4 * k + c);
             const uint32_t e = ((unsigned)idx < (unsigned)len) ? ((uint32_t)seq1[idx] * 0x11u | 0x80u) : SG2_PAD_A;
             a |= e << (8 * c);
         }
@@ -121,7 +138,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
     s.pos_y = 0; s.prev_down = 0u; s.dead = 0u;
     s.best = SG2_X; s.best_round = 0; s.best_py = 0;
     // bases enter at cell 0 on a down move (lane 0: seq1p[pos_y + 31] = seq1[pos_y + 30]) and at cell 31 on a
-    // right move (lane 3: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
+    // right move (last lane: seq2p[pos_x] = seq2[pos_x - 32]); round 1 takes seq2[0]
     s.role_base = SG2_F | (q == 0 ? 0x800000u : 0u);
     s.right = 1u;
     s.got = SG2_F | (SG2_PAD_B << 16);
@@ -129,7 +146,7 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
     s.next_raw = s.next2_raw = 4u;
     if (q == 0 && 31 < len) s.next_raw = seq1[31];
     if (q == 0 && 32 < len) s.next2_raw = seq1[32];
-    if (q == 3) {
+    if (q == LAST) {
         s.got = SG2_F | ((0 < len ? (uint32_t)seq2[0] : 5u) * 0x110000u);
         s.cidx = 2;
         s.next_raw = (1 < len) ? (uint32_t)seq2[1] : 5u;
@@ -137,72 +154,86 @@ SWB_HD void sg2_init(Sg2State& s, const Env& env, const uint8_t* seq1, const uin
     }
 }
 
-// One round (source.cpp:1886-1942).  `role_seq` = seq1 in lane 0, seq2 in lane 3 (unused elsewhere);
-// `rec_row` = this pair's records: lane word q of round r at rec_row[rec_stride * r + q] (rec_stride = 4 when a pair's
-// records are contiguous, 128 when 32 pairs are interleaved round by round).  Returns false when every cell is <= 0
-// (source.cpp:1938);
-// a pair in that state is kept inert from then on (see `dead`) -- further rounds change neither its best nor its
-// cells -- so the quads of a warp may keep running together until the last one is done.
-// All communication of a round is ONE stage of seven independent shuffles issued right after the cells are
-// computed (three for the maximum, two for the next direction, two for the boundary cell and base of either
-// direction): everything that follows them is lane-local.  They carry t2, the cells BEFORE the X-drop; the
-// receiver applies the drop itself, and the direction test is restated on t2:
+// One round (source.cpp:1886-1942).  `role_seq` = seq1 in lane 0, seq2 in the last lane (unused elsewhere);
+// `rec_row` = this pair's records, 16 bytes per round: round r starts at rec_row[rec_stride * r] (rec_stride = 4 when a
+// pair's records are contiguous, 128 when 32 pairs are interleaved round by round).  NW = 4: one word per lane (tags in
+// bytes 0 and 2, moves in byte 1).  NW = 8: two words per lane (32 tag bits; moves).  Returns false when every cell is
+// <= 0 (source.cpp:1938); a pair in that state is kept inert from then on (see `dead`) -- further rounds change neither
+// its best nor its cells -- so the pairs of a warp may keep running together until the last one is done.
+// All communication of a round is ONE stage of independent shuffles issued right after the cells are computed (the
+// maximum, two for the next direction, two for the boundary cell and base of either direction): everything that
+// follows them is lane-local.  They carry t2, the cells BEFORE the X-drop; the receiver applies the drop itself, and the
+// direction test is restated on t2:
 //     result[0] < result[31]   <=>   t2[0] < t2[31]  and  t2[31] - c >= 0
 // (with c the amount subtracted this round; dropped cells compare as the smallest value).
-template <bool RECORD, class Env>
-SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride)
+template <bool RECORD, int NW, class Env>
+SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride)
 {
+    constexpr int LAST = Sg2State<NW>::kLast, NA = NW / 2;
     const int q = env.q();
     const bool right = s.right != 0u;                      // source.cpp:1889
     const uint32_t got = s.got;
-    uint32_t D[4];
+    uint32_t D[NW];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) D[w] = right ? s.V[w] : s.H[w];       // source.cpp:1892,1903
+    for (int w = 0; w < NW; ++w) D[w] = right ? s.V[w] : s.H[w];       // source.cpp:1892,1903
     const uint32_t one = env.one();                        // a 1 the compiler cannot see: it keeps bookkeeping adds and shifts multiply-adds
     const uint32_t gh = got * (one << 16) + 0x00010000u, ga = got << 8, gb = got >> 16, gv = got * one + 2u;
     const uint32_t down = s.right * (0u - one) + one;      // 1 - right, as a multiply-add
     const uint32_t sR = s.right * (one << 4), sD = down * (one << 4), cR = s.right * (one << 3), cD = down * (one << 3);      // shift amounts: 16 / 8 or 0
-    s.H[3] = fsl(s.R1[2], s.R1[3], sD); s.H[2] = fsl(s.R1[1], s.R1[2], sD); s.H[1] = fsl(s.R1[0], s.R1[1], sD); s.H[0] = fsl(gh, s.R1[0], sD);
-    s.V[0] = fsr(s.R2[0], s.R2[1], sR); s.V[1] = fsr(s.R2[1], s.R2[2], sR); s.V[2] = fsr(s.R2[2], s.R2[3], sR); s.V[3] = fsr(s.R2[3], gv, sR);
-    s.A[1] = fsl(s.A[0], s.A[1], cD); s.A[0] = fsl(ga, s.A[0], cD);
-    s.B[0] = fsr(s.B[0], s.B[1], cR); s.B[1] = fsr(s.B[1], gb, cR);
+#pragma unroll
+    for (int w = NW - 1; w >= 0; --w) s.H[w] = fsl(w ? s.R1[w - 1] : gh, s.R1[w], sD);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s.V[w] = fsr(s.R2[w], w < NW - 1 ? s.R2[w + 1] : gv, sR);
+#pragma unroll
+    for (int k = NA - 1; k >= 0; --k) s.A[k] = fsl(k ? s.A[k - 1] : ga, s.A[k], cD);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) s.B[k] = fsr(s.B[k], k < NA - 1 ? s.B[k + 1] : gb, cR);
     s.pos_y += (int32_t)down;
-    const uint32_t moves = (down + s.prev_down * (one << 1)) * (one << 8);      // byte 1: bit 0 = this round moved down, bit 1 = the one before
+    const uint32_t moves = down + s.prev_down * (one << 1);      // bit 0 = this round moved down, bit 1 = the one before
     s.prev_down = down;
     // ---- scores: selector byte of a cell = (a ^ b) in the low nibble, 8 | (a ^ b) in the high one (sign replication)
-    const uint32_t x0 = s.A[0] ^ s.B[0], x1 = s.A[1] ^ s.B[1];
-    uint32_t sd[4];
-    sd[0] = prmt(s.lut_lo, s.lut_hi, x0); sd[1] = prmt(s.lut_lo, s.lut_hi, x0 >> 16);
-    sd[2] = prmt(s.lut_lo, s.lut_hi, x1); sd[3] = prmt(s.lut_lo, s.lut_hi, x1 >> 16);
-    // ---- the cells (source.cpp:1916-1926); the tag of the winner is what the traceback will find (source.cpp:1960-1969)
-    uint32_t t[4], t2[4];
+    uint32_t sd[NW];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int k = 0; k < NA; ++k) {
+        const uint32_t x = s.A[k] ^ s.B[k];
+        sd[2 * k] = prmt(s.lut_lo, s.lut_hi, x);
+        sd[2 * k + 1] = prmt(s.lut_lo, s.lut_hi, x >> 16);
+    }
+    // ---- the cells (source.cpp:1916-1926); the tag of the winner is what the traceback will find (source.cpp:1960-1969)
+    uint32_t t[NW], t2[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
         t[w] = vmax3(vadd2(D[w], sd[w]), s.H[w], s.V[w]);
         t2[w] = t[w] & SG2_UNTAG;
     }
     // ---- the shuffle stage
-    uint32_t m = vmax2(vmax3(t2[0], t2[1], t2[2]), t2[3]);
-    m = vmax2(m, prmt(m, m, 0x1032u));                     // both halves: the maximum of this lane's eight cells
-    const uint32_t xr = prmt(t2[0], s.B[0], 0x0410u), xd = prmt(t2[3], s.A[1], 0x0732u);
-    const uint32_t m1 = env.shfl_xor(m, 1), m2 = env.shfl_xor(m, 2), m3 = env.shfl_xor(m, 3);
-    const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[3], 3);
+    uint32_t m = sg2_max_words<NW>(t2);
+    m = vmax2(m, prmt(m, m, 0x1032u));                     // both halves: the maximum of this lane's cells
+    const uint32_t xr = prmt(t2[0], s.B[0], 0x0410u), xd = prmt(t2[NW - 1], s.A[NA - 1], 0x0732u);
+    const uint32_t m1 = env.shfl_xor(m, 1);
+    uint32_t m2 = m1, m3 = m1;
+    if (NW == 4) { m2 = env.shfl_xor(m, 2); m3 = env.shfl_xor(m, 3); }
+    const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[NW - 1], LAST);
     const uint32_t gn = env.shfl(xr, q + 1), gp = env.shfl(xd, q - 1);
-    // ---- the record (independent of the shuffles): tags of cells 0,2,4,6 in byte 0, of 1,3,5,7 in byte 2, the two moves in byte 1
-    // (tag = t - t2, no borrow between the halves: clearing bits never raises a half; summed as multiply-adds)
+    // ---- the record (independent of the shuffles).  tag = t - t2 (no borrow between the halves: clearing bits never
+    // raises a half), gathered as multiply-adds: word w's tags land at bits 2w (cell 2w) and 16 + 2w (cell 2w + 1)
     if (RECORD) {
-        const uint32_t c4 = one << 2, c16 = one << 4, c64 = one << 6, mone = 0u - one;
-        uint32_t neg = t2[0] * one + t2[1] * c4;
-        uint32_t acc = t[0] * one + moves;
-        neg = t2[2] * c16 + neg; acc = t[1] * c4 + acc;
-        neg = t2[3] * c64 + neg; acc = t[2] * c16 + acc;
-        acc = t[3] * c64 + acc;
-        rec_row[rec_stride * round + q] = neg * mone + acc;
+        const uint32_t mone = 0u - one;
+        uint32_t neg = t2[0] * one, acc = t[0] * one;
+#pragma unroll
+        for (int w = 1; w < NW; ++w) { neg = t2[w] * (one << (2 * w)) + neg; acc = t[w] * (one << (2 * w)) + acc; }
+        if (NW == 4) {
+            rec_row[rec_stride * round + q] = neg * mone + acc + moves * (one << 8);       // tags in bytes 0 and 2, moves in byte 1
+        } else {
+            uint32_t* const at = rec_row + rec_stride * round + 2 * q;                     // {32 tag bits, moves}
+            at[0] = neg * mone + acc;
+            at[1] = moves;
+        }
     }
     // ---- round maximum (source.cpp:1925).  In the X-drop frame the best so far sits at 69 or 70, a cell is at most
     // two above it, and the threshold moves exactly when a cell reaches 72 -- so the amount subtracted this round,
     // c = 1 + off, comes from one packed compare; the bookkeeping of the best (below) is off the critical path.
-    m = vmax2(vmax3(m, m1, m2), m3);
+    m = (NW == 4) ? vmax2(vmax3(m, m1, m2), m3) : vmax2(m, m1);
     const uint32_t off = vaddmax2(m, 0xFEE1FEE1u, 0u) & 1u;        // max(m - 287, 0): 1 iff the maximum is 4 * 72
     // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
     // A finished pair must stay finished while its warp runs on: the round after the last one could otherwise revive a
@@ -210,7 +241,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     // round drops; from then on all its inputs are F.
     const uint32_t nc = 0xFFFCFFFCu - off * 0x00040004u - s.dead * 0x3ED03ED0u;   // (-4c, -4c); dead: a further -16080
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < NW; ++w) {
         const uint32_t r = vminu2(vaddmax2(t2[w], nc, SG2_FF), SG2_FF);
         s.R1[w] = vadd2(r, 0x00010001u);
         s.R2[w] = vadd2(r, 0x00020002u);
@@ -218,7 +249,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     // ---- the next round's direction and what enters this lane then
     const int32_t t31 = sg2_half(e31, 1);
     const bool rn = sg2_half(e0, 0) < t31 && t31 > (int32_t)(4u * off);   // t31 - 4c >= 0 (multiples of 4)
-    const bool edge = rn ? (q == 3) : (q == 0);            // the band's end: a dropped cell and a new base come in
+    const bool edge = rn ? (q == LAST) : (q == 0);         // the band's end: a dropped cell and a new base come in
     uint32_t cand = rn ? gn : gp;
     if (edge) cand = s.next_raw * 0x110000u + s.role_base;
     s.got = vminu2(vaddmax2(cand, nc & 0xffffu, 0x80000000u | SG2_F), 0xFFFF0000u | SG2_F);   // drop the cell; the upper half (base, stray byte) passes
@@ -233,7 +264,7 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     if (amax > s.best) {
         s.best = amax; s.best_round = round; s.best_py = s.pos_y;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) s.Rb[w] = t2[w];
+        for (int w = 0; w < NW; ++w) s.Rb[w] = t2[w];
     }
     s.T += (int32_t)off;                                   // T = max(best - 70, 1)
     s.dead |= amax > 0 ? 0u : 1u;
@@ -245,39 +276,50 @@ SWB_HD bool sg2_round(Sg2State& s, Env& env, const uint8_t* role_seq, int len, i
     return s.dead == 0u;
 }
 
-// After the last round: the end cell is the upper-right-most cell of the best round that holds the best
-// score (source.cpp:1953-1954).  Returns this lane's word of record 0 = {best round, band element of the end cell, end_y, end_x}.
-template <class Env>
-SWB_HD uint32_t sg2_finish(const Sg2State& s, Env& env, int32_t& score, int32_t& end_y, int32_t& end_x)
+// After the last round: the end cell is the upper-right-most cell of the best round that holds the best score
+// (source.cpp:1953-1954); the traceback starts on band element `loc` of `best_round`.
+template <int NW, class Env>
+SWB_HD void sg2_finish(const Sg2State<NW>& s, Env& env, int32_t& score, int32_t& end_y, int32_t& end_x, int32_t& best_round, int32_t& loc)
 {
+    constexpr int CELLS = Sg2State<NW>::kCells;
     const int q = env.q();
-    uint32_t m = vmax2(vmax3(s.Rb[0], s.Rb[1], s.Rb[2]), s.Rb[3]);        // the best round's maximum, once more
+    uint32_t m = sg2_max_words<NW>(s.Rb);                  // the best round's maximum, once more
     m = vmax2(m, prmt(m, m, 0x1032u));
     m = vmax2(m, env.shfl_xor(m, 1));
-    m = vmax2(m, env.shfl_xor(m, 2));
+    if (NW == 4) m = vmax2(m, env.shfl_xor(m, 2));
     const int32_t best_m = sg2_half(m, 0);
-    int32_t loc = -1;
+    loc = -1;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        if (sg2_half(s.Rb[c >> 1], c & 1) == best_m) loc = 8 * q + c;
+    for (int c = 0; c < CELLS; ++c)
+        if (sg2_half(s.Rb[c >> 1], c & 1) == best_m) loc = CELLS * q + c;
     int32_t o = (int32_t)env.shfl_xor((uint32_t)loc, 1); loc = loc > o ? loc : o;
-    o = (int32_t)env.shfl_xor((uint32_t)loc, 2); loc = loc > o ? loc : o;
+    if (NW == 4) { o = (int32_t)env.shfl_xor((uint32_t)loc, 2); loc = loc > o ? loc : o; }
     score = s.best - SG2_X;
     end_y = s.best_py + 31 - loc;
     end_x = (s.best_round - s.best_py) - 31 + loc;         // pos_x = 31 + (number of right moves)
-    return (uint32_t)(q == 0 ? s.best_round : q == 1 ? loc : q == 2 ? end_y : end_x);
+    best_round = s.best_round;
 }
 
-// One traceback step (source.cpp:1958-1971): the walker stands on band element o of round r; w = word o >> 3 of that
-// round's record.  The tag says where the cell came from (3 diagonal, 2 up, 1 left -- the reference's preference order
-// was applied by the forward pass); the move bits say how the band had shifted, which gives the element index of the
+// One traceback step (source.cpp:1958-1971): the walker stands on band element o of round r; rec = that round's record
+// (four words).  The tag says where the cell came from (3 diagonal, 2 up, 1 left -- the reference's preference order was
+// applied by the forward pass); the move bits say how the band had shifted, which gives the element index of the
 // predecessor in ITS round:  up: o + 1 - down(r),  left: o - down(r),  diagonal (two rounds back): o + 1 - down(r) - down(r-1).
 // Round 0 is the cell (0,0): the walk ends at r == 0.  Returns the op: 0 = diagonal, 1 = down (y+1), 2 = right (x+1).
-SWB_HD uint32_t sg2_tb_step(uint32_t w, int& o, int& r)
+template <int NW>
+SWB_HD uint32_t sg2_tb_step(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, int& o, int& r)
 {
-    const uint32_t code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;
+    uint32_t code, mv;
+    if (NW == 4) {                                          // lane word o >> 3: tags in bytes 0 and 2, moves in byte 1
+        const uint32_t w = (o & 16) ? ((o & 8) ? r3 : r2) : ((o & 8) ? r1 : r0);
+        code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;
+        mv = w >> 8;
+    } else {                                                // lane o >> 4: {32 tag bits, moves}
+        const uint32_t w = (o & 16) ? r2 : r0;
+        code = (w >> (((o & 1) << 4) | (o & 14))) & 3u;
+        mv = r1;
+    }
     const uint32_t diag = code == 3u ? 1u : 0u;
-    o += (int)(code >> 1) - (int)((w >> 8) & 1u) - (int)((w >> 9) & diag);
+    o += (int)(code >> 1) - (int)(mv & 1u) - (int)((mv >> 1) & diag);
     r -= 1 + (int)diag;
     return 3u - code;
 }

@@ -58,53 +58,59 @@ struct SgOut {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Forward kernel, four lanes per pair (sg2_core.cuh): a warp advances eight pairs per round.  Quads of a warp
-// run their pairs side by side and pick up the next eight together (pairs of similar length finish together;
-// the bench's and the reference's pairs all run the full 2*len rounds).
+// Forward kernel (sg2_core.cuh): four lanes per pair and eight pairs per warp (NW = 4), or two lanes per pair and
+// sixteen pairs per warp (NW = 8).  The lane groups of a warp run their pairs side by side and pick up the next ones
+// together (pairs of similar length finish together; the bench's and the reference's pairs all run the full 2*len rounds).
 constexpr int SG2_THREADS = 32;
+// Words per lane of the shipped forward kernel.  8 (two lanes per pair, sixteen pairs per warp) needs 224 instructions per
+// warp-round = 14 per pair; 4 (four lanes, eight pairs) needs 158 = 19.8 per pair and measured 12 % slower at 18944 pairs
+// (1.06 M vs 1.21 M alignments/s), 3 % slower at 8192.
+constexpr int kSgWords = 8;
 
+template <int LANES>
 struct Sg2DevEnv {
-    int lane4; uint32_t one_;
-    __device__ __forceinline__ int q() const { return lane4; }
+    int lane_; uint32_t one_;
+    __device__ __forceinline__ int q() const { return lane_; }
     __device__ __forceinline__ uint32_t one() const { return one_; }
-    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
-    __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) const { return __shfl_sync(0xffffffffu, v, src, LANES); }
+    __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, LANES); }
 };
 
-template <bool RECORD>         // false: score and end cell only, no round records are written
+template <bool RECORD, int NW>         // RECORD false: score and end cell only, no round records are written; NW: words per lane
 __global__ void __launch_bounds__(SG2_THREADS)
 sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ seq2, const int len, const unsigned long long n,
                  uint4* __restrict__ traces, const SgOut out, const uint32_t one)
 {
+    constexpr int LANES = Sg2State<NW>::kLanes, PPW = 32 / LANES;      // lanes per pair, pairs per warp
     const unsigned lane = threadIdx.x & 31u;
-    Sg2DevEnv env{(int)(lane & 3u), one};
+    Sg2DevEnv<LANES> env{(int)(lane & (LANES - 1)), one};
     const unsigned long long warp = ((unsigned long long)blockIdx.x * SG2_THREADS + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * SG2_THREADS) >> 5;
     const uint32_t rounds_cap = sg_rounds_cap(len);
     const int max_round = 2 * len + 1;          // rounds run while round < MAX_ROUND (source.cpp:1872,1886)
-    // The warp stays converged (full-mask shuffles): its eight quads take eight consecutive pairs, run their rounds
-    // together until the last of them is done, then take the next eight.  A quad beyond the batch shadows the last
+    // The warp stays converged (full-mask shuffles): its lane groups take PPW consecutive pairs, run their rounds
+    // together until the last of them is done, then take the next PPW.  A group beyond the batch shadows the last
     // pair and writes its records to the spare group of the scratch.
-    for (unsigned long long base = warp * 8ull; base < n; base += n_warps * 8ull) {
-        const unsigned long long want = base + (lane >> 2);
+    for (unsigned long long base = warp * PPW; base < n; base += n_warps * PPW) {
+        const unsigned long long want = base + lane / LANES;
         const bool live = want < n;
         const unsigned long long p = live ? want : n - 1ull;
         const uint8_t* const s1 = seq1 + p * (unsigned long long)len;
         const uint8_t* const s2 = seq2 + p * (unsigned long long)len;
         const unsigned long long slot = live ? want : ((n + SG_GROUP - 1) / SG_GROUP) * SG_GROUP + (want & (SG_GROUP - 1));
         uint32_t* const rec_row = reinterpret_cast<uint32_t*>(traces + (slot / SG_GROUP) * rounds_cap * SG_GROUP + (slot & (SG_GROUP - 1)));
-        Sg2State s;
+        Sg2State<NW> s;
         sg2_init(s, env, s1, s2, len);
         const uint8_t* const role = env.q() == 0 ? s1 : s2;
         for (int round = 1; round < max_round; ++round) {
             const bool go = sg2_round<RECORD>(s, env, role, len, round, rec_row, 4 * SG_GROUP);
             if ((round & 3) == 0 && !__any_sync(0xffffffffu, go)) break;      // a finished pair stays finished: asking every fourth round is enough
         }
-        int32_t score, end_y, end_x;
-        const uint32_t rec0 = sg2_finish(s, env, score, end_y, end_x);
-        if (live) {
-            if (RECORD) rec_row[env.q()] = rec0;
-            if (env.q() == 0) { out.score[p] = score; out.end_y[p] = end_y; out.end_x[p] = end_x; }
+        int32_t score, end_y, end_x, best_round, loc;
+        sg2_finish(s, env, score, end_y, end_x, best_round, loc);
+        if (live && env.q() == 0) {
+            if (RECORD) *reinterpret_cast<uint4*>(rec_row) = make_uint4((uint32_t)best_round, (uint32_t)loc, (uint32_t)end_y, (uint32_t)end_x);   // record 0: where the traceback starts
+            out.score[p] = score; out.end_y[p] = end_y; out.end_x[p] = end_x;
         }
     }
 }
@@ -128,6 +134,7 @@ __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
+template <int NW>               // the forward kernel's words per lane: the record layout
 __global__ void __launch_bounds__(SG_TB_THREADS)
 sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
 {
@@ -169,9 +176,8 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
         for (int q = 0; q < 8; ++q) {           // ... then the dependent chain: element -> lane word -> tag -> next element,
             const int r = rb - q;               //     branch-free (selects and one predicated store)
             const bool act = rw == r && r >= 1 && n_ops < cap;
-            const uint32_t w = (o & 16) ? ((o & 8) ? rec[q].w : rec[q].z) : ((o & 8) ? rec[q].y : rec[q].x);
             int o2 = o, r2 = rw;
-            const uint32_t op = sg2_tb_step(w, o2, r2);                                 // 0 = diagonal, 1 = down, 2 = right
+            const uint32_t op = sg2_tb_step<NW>(rec[q].x, rec[q].y, rec[q].z, rec[q].w, o2, r2);                                 // 0 = diagonal, 1 = down, 2 = right
             if (act) row[cap - 1u - n_ops] = (uint8_t)op;
             o = act ? o2 : o;
             rw = act ? r2 : rw;

@@ -275,7 +275,7 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<kSgWords>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -527,7 +527,7 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
 // ---------------------------------------------------------------------------------------------
 // Semi-global X-drop aligner (sg_kernel.cuh)
 constexpr int kSgMaxLen = 1 << 15;                // pos_y <= len + 1 must fit the 16 bits it has in a round record
-constexpr int kSgBlocksPerSm = 24;                // resident warps per SM of the forward kernel (one warp = eight pairs)
+constexpr int kSgBlocksPerSm = 24;                // resident warps per SM of the forward kernel
 
 constexpr size_t kSgTraceBudget = 40ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 81 800 pairs)
 
@@ -566,15 +566,17 @@ int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* 
         const uint64_t m = (n - c0 < per) ? n - c0 : per;
         SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
         const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);      // a warp per group of 32 pairs
-        const uint64_t need = (m * 4 + SG2_THREADS - 1) / SG2_THREADS;
+        const uint64_t ppw = 32 / Sg2State<kSgWords>::kLanes;      // pairs per warp
+        const uint64_t need = ((m + ppw - 1) / ppw * 32 + SG2_THREADS - 1) / SG2_THREADS;
         const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
         const unsigned fgrid = (unsigned)(need < cap ? need : cap);
-        if (d_ops) sg2_xdrop_kernel<true><<<fgrid, SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m, sc.traces, out, 1u);
-        else sg2_xdrop_kernel<false><<<fgrid, SG2_THREADS, 0, st>>>(d1 + c0 * (uint64_t)len, d2 + c0 * (uint64_t)len, len, m, sc.traces, out, 1u);
+        const uint8_t* const a1 = d1 + c0 * (uint64_t)len; const uint8_t* const a2 = d2 + c0 * (uint64_t)len;
+        if (d_ops) sg2_xdrop_kernel<true, kSgWords><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+        else sg2_xdrop_kernel<false, kSgWords><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
         SWB_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (d_ops) {
-            sg_traceback_kernel<<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            sg_traceback_kernel<kSgWords><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
             sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
@@ -1073,8 +1075,8 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     cudaFuncAttributes fa{};
     int blocks = 0;
-    SWB_CUDA(ctx, cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true>));
-    SWB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true>, SG2_THREADS, 0));
+    SWB_CUDA(ctx, (cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true, kSgWords>)));
+    SWB_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true, kSgWords>, SG2_THREADS, 0)));
     info->threads_per_block = SG2_THREADS;
     info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
     info->fast_path = 0;

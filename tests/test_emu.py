@@ -149,22 +149,26 @@ SG2_LIB = os.path.join(ROOT, "tests", "emu", "libsg2emu.so")
 
 @pytest.fixture(scope="module")
 def sg2():
-    """The four-lanes-per-pair round of the semi-global kernel, run on the host as four coroutines in lock step."""
+    """The per-lane round of the semi-global kernel, run on the host: the lanes of a pair are coroutines in lock step."""
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-I{CSRC}", "-o", SG2_LIB, SG2_SRC], check=True)
     lib = C.CDLL(SG2_LIB)
     lib.swemu_sg2.restype = C.c_int
-    lib.swemu_sg2.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.swemu_sg2.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
 
     def run(a, b):
         a = np.ascontiguousarray(a, dtype=np.uint8)
         b = np.ascontiguousarray(b, dtype=np.uint8)
         n = a.size
-        meta = np.zeros(4, np.int32)
-        ops = np.zeros(2 * n, np.uint8)
-        rc = lib.swemu_sg2(a.ctypes.data, b.ctypes.data, n, meta[0:].ctypes.data, meta[1:].ctypes.data, meta[2:].ctypes.data,
-                           ops.ctypes.data, meta[3:].ctypes.data)
-        assert rc == 0, rc
-        return int(meta[0]), int(meta[1]), int(meta[2]), ops[:meta[3]].copy()
+        out = []
+        for words in (8, 4):            # the shipped width (two lanes per pair) and the four-lane one: the same templated code
+            meta = np.zeros(4, np.int32)
+            ops = np.zeros(2 * n, np.uint8)
+            rc = lib.swemu_sg2(a.ctypes.data, b.ctypes.data, n, meta[0:].ctypes.data, meta[1:].ctypes.data, meta[2:].ctypes.data,
+                               ops.ctypes.data, meta[3:].ctypes.data, words)
+            assert rc == 0, (rc, words)
+            out.append((int(meta[0]), int(meta[1]), int(meta[2]), ops[:meta[3]].copy()))
+        assert out[0][:3] == out[1][:3] and np.array_equal(out[0][3], out[1][3])
+        return out[0]
     return run
 
 
