@@ -479,20 +479,28 @@ def run_stream_arm(args):
 SG_LEN = 16384
 SG_ROUNDS_NOMINAL = 2 * SG_LEN       # a pair aligned end to end runs one round per anti-diagonal
 SG_TRACE_BYTES_PER_ROUND = 8.125     # 64 direction bits + 1 move bit, written once and read once by the traceback
-SG_PAIRS_PER_WARP = 16.0             # the forward kernel: two lanes per pair
 SG_RECORD_BYTES_PER_ROUND = 16       # what the kernels move: one 16-byte record per round, written by the forward kernel, read by the traceback
 
 
-def sg_instr_counts():
-    """Warp instructions per warp-round (sixteen pairs advance one round) of the forward kernel, from the committed ncu
-    capture: total and ALU-pipe.  Fallback = the SASS count of the loop body."""
+SG_KERNEL_SHAPES = {16: {"pairs_per_warp": 32, "instr": 360.0, "alu": 222.0}, 8: {"pairs_per_warp": 16, "instr": 224.0, "alu": 127.0}}
+
+
+def sg_kernel_shape(n, sm_count):
+    """The forward kernel the library launches for a batch of n pairs (csrc/sg_kernel.cuh, sg_words_for): words per lane,
+    pairs per warp, and warp instructions per warp-round (all pairs of the warp advance one round) in total and on the ALU
+    pipe -- from the committed ncu capture when it is of this width, else the SASS count of the loop body."""
+    words = 16 if n >= sm_count * 128 else 8
+    shape = dict(SG_KERNEL_SHAPES[words], words_per_lane=words, src="SASS count of the loop body (cuobjdump)")
     path = os.path.join(ROOT, "profiles", "r01", "ncu_full_semiglobal_v11_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return float(d["warp_instr_per_warp_round"]), float(d["alu_pipe_instr_per_warp_round"]), "profiles/r01/ncu_full_semiglobal_v11_summary.json"
+        if int(d.get("words_per_lane", 0)) == words:
+            shape.update(instr=float(d["warp_instr_per_warp_round"]), alu=float(d["alu_pipe_instr_per_warp_round"]),
+                         src="profiles/r01/ncu_full_semiglobal_v11_summary.json")
     except (OSError, KeyError, ValueError):
-        return 224.0, 117.0, "SASS count of the loop body (cuobjdump)"
+        pass
+    return shape
 
 
 def sg_cpu_reference(a, b, budget_s=20.0):
@@ -523,9 +531,9 @@ def run_semiglobal_arm(args):
     insert / delete, source.cpp:2750-2771) through the adaptive-banded X-drop aligner, score + traceback.
     value = alignments/s device-resident; e2e = swb200_semiglobal_xdrop_batch with pinned host arrays."""
     import swb200
-    # default batch: 16 pairs x 2 warps per scheduler x 4 schedulers x 148 SMs = 18944 pairs -- the forward kernel runs one warp per
-    # sixteen pairs, and a batch that is not a multiple of 148 x 64 pairs leaves some schedulers a warp short
-    n = args.pairs if args.pairs != 100_000_000 else 148 * 128
+    # default batch: 32 pairs x 2 warps per scheduler x 4 schedulers x 148 SMs = 37888 pairs -- the forward kernel runs one warp per
+    # 32 pairs, and a batch that is not a multiple of 148 x 128 pairs leaves some schedulers a warp short
+    n = args.pairs if args.pairs != 100_000_000 else 148 * 256
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
@@ -644,11 +652,12 @@ def run_semiglobal_arm(args):
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     # roofline of the forward kernel (the dominant one): its ALU pipe.  A warp-round advances sixteen pairs by one round;
     # it needs `alu_wr` ALU-pipe warp instructions (ncu), and an SM retires 2 of those per clock (63.5 lanes, INT_PEAK.json).
-    instr_wr, alu_wr, instr_src = sg_instr_counts()
+    shape = sg_kernel_shape(n, info["sm_count"])
+    instr_wr, alu_wr, instr_src, ppw = shape["instr"], shape["alu"], shape["src"], float(shape["pairs_per_warp"])
     int_peak = json.load(open(os.path.join(ROOT, "profiles", "INT_PEAK.json")))
     lanes = float(int_peak.get("alu_lanes_per_clk_per_sm", 63.5))
     alu_peak = lanes * info["sm_count"] * sm_mhz * 1e6            # thread-level ALU-pipe instructions per second
-    warp_rounds_per_s = (n / SG_PAIRS_PER_WARP) * SG_ROUNDS_NOMINAL / (fwd_ms * 1e-3)
+    warp_rounds_per_s = (n / ppw) * SG_ROUNDS_NOMINAL / (fwd_ms * 1e-3)
     alu_achieved = warp_rounds_per_s * alu_wr * 32.0
     rounds_per_s = n * SG_ROUNDS_NOMINAL / (ms * 1e-3)
     trace_gbs = n * SG_ROUNDS_NOMINAL * SG_RECORD_BYTES_PER_ROUND * 2 / (ms * 1e-3) / 1e9
@@ -669,9 +678,9 @@ def run_semiglobal_arm(args):
                      "achieved": alu_achieved / 1e12, "peak": alu_peak / 1e12, "unit": "Tinstr/s (thread-level ALU-pipe instructions)",
                      "frac": alu_achieved / alu_peak, "avg_launch_ms": fwd_ms, "share_of_step": fwd_ms / ms,
                      "alu_instr_per_warp_round": alu_wr, "instr_per_warp_round": instr_wr, "instr_src": instr_src,
-                     "warp_rounds_per_launch": (n / SG_PAIRS_PER_WARP) * SG_ROUNDS_NOMINAL,
-                     "note": "two lanes per pair: one warp instruction serves sixteen pairs; a round is one serial chain per pair, so the kernel is bound by "
-                             "how many ALU-pipe instructions a round needs and by how many warps there are to overlap the chains (n / 16 warps), not by HBM",
+                     "warp_rounds_per_launch": (n / ppw) * SG_ROUNDS_NOMINAL, "words_per_lane": shape["words_per_lane"], "pairs_per_warp": ppw,
+                     "note": "one lane per pair (two below 18944 pairs): one warp instruction serves 32 (16) pairs; a round is one serial chain per pair, so the kernel "
+                             "is bound by how many ALU-pipe instructions a round needs and by how many warps there are to overlap the chains, not by HBM",
                      "traffic": None,
                      "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2, "record_bytes_per_round": SG_RECORD_BYTES_PER_ROUND * 2}},

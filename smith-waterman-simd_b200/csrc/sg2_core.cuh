@@ -71,8 +71,8 @@ constexpr uint32_t SG2_UNTAG = 0xFFFCFFFCu;
 constexpr uint32_t SG2_PAD_A = 0xC4u;              // base bytes: code * 0x11, seq1 side has bit 7 set; the pads (4, 5)
 constexpr uint32_t SG2_PAD_B = 0x55u;              //   differ from every base and from each other (source.cpp:1913-1915)
 
-// NW = packed words per lane: 4 (eight cells per lane, four lanes per pair, eight pairs per warp) or 8 (sixteen cells
-// per lane, two lanes per pair, sixteen pairs per warp).  The per-round overhead that does not depend on the cells
+// NW = packed words per lane: 4 (eight cells per lane, four lanes per pair, eight pairs per warp), 8 (sixteen cells
+// per lane, two lanes per pair, sixteen pairs per warp) or 16 (the whole band in one lane, 32 pairs per warp, no shuffles).  The per-round overhead that does not depend on the cells
 // (direction, boundary exchange, threshold, loop) is paid once per lane, so the wider lane spends fewer instructions
 // per pair; the narrower one has twice the warps for the same batch.
 template <int NW>
@@ -90,6 +90,7 @@ struct Sg2State {
     uint32_t next2_raw;   // ... and the one after it: a base is loaded two entries before it is used
     uint32_t role_base;   // F | (0x80 << 16 in lane 0)
     int32_t cidx;         // index of next2_raw in seq1 (lane 0) / seq2 (last lane)
+    uint32_t nextb_raw, nextb2_raw; int32_t cidxb;      // one lane per pair: the lane feeds both ends; these are the seq2 side
     int32_t pos_y;        // the band's upper-right cell is (pos_y, round - pos_y), source.cpp:1873-1874
     uint32_t prev_down;   // the previous round moved down
     uint32_t dead;        // 1 once a round left every cell <= 0: the reference stops there (source.cpp:1938-1941)
@@ -102,10 +103,9 @@ template <int NW>
 SWB_HD uint32_t sg2_max_words(const uint32_t* t)
 {
     uint32_t m = vmax3(t[0], t[1], t[2]);
-    if (NW == 4) return vmax2(m, t[3]);
-    m = vmax3(m, t[3], t[4]);
-    m = vmax3(m, t[5 % NW], t[6 % NW]);
-    return vmax2(m, t[7 % NW]);
+#pragma unroll
+    for (int w = 3; w + 1 < NW; w += 2) m = vmax3(m, t[w], t[w + 1]);
+    return vmax2(m, t[NW - 1]);
 }
 
 // Round 0 (source.cpp:1876-1884): cell 31 = X_THRESHOLD, everything else unreached; band at (0, 31).  Round 1
@@ -146,7 +146,12 @@ SWB_HD void sg2_init(Sg2State<NW>& s, const Env& env, const uint8_t* seq1, const
     s.next_raw = s.next2_raw = 4u;
     if (q == 0 && 31 < len) s.next_raw = seq1[31];
     if (q == 0 && 32 < len) s.next2_raw = seq1[32];
-    if (q == LAST) {
+    s.nextb_raw = s.nextb2_raw = 5u; s.cidxb = 2;
+    if (LAST == 0) {                                 // one lane per pair: it keeps the seq1 side above and the seq2 side here
+        s.got = SG2_F | ((0 < len ? (uint32_t)seq2[0] : 5u) * 0x110000u);
+        if (1 < len) s.nextb_raw = seq2[1];
+        if (2 < len) s.nextb2_raw = seq2[2];
+    } else if (q == LAST) {
         s.got = SG2_F | ((0 < len ? (uint32_t)seq2[0] : 5u) * 0x110000u);
         s.cidx = 2;
         s.next_raw = (1 < len) ? (uint32_t)seq2[1] : 5u;
@@ -157,7 +162,8 @@ SWB_HD void sg2_init(Sg2State<NW>& s, const Env& env, const uint8_t* seq1, const
 // One round (source.cpp:1886-1942).  `role_seq` = seq1 in lane 0, seq2 in the last lane (unused elsewhere);
 // `rec_row` = this pair's records, 16 bytes per round: round r starts at rec_row[rec_stride * r] (rec_stride = 4 when a
 // pair's records are contiguous, 128 when 32 pairs are interleaved round by round).  NW = 4: one word per lane (tags in
-// bytes 0 and 2, moves in byte 1).  NW = 8: two words per lane (32 tag bits; moves).  Returns false when every cell is
+// bytes 0 and 2, moves in byte 1).  NW = 8: two words per lane (32 tag bits; moves).  NW = 16: the lane's four words
+// (64 tag bits; moves; 0).  With one lane per pair `role_seq` is seq1 and `role_seq2` seq2.  Returns false when every cell is
 // <= 0 (source.cpp:1938); a pair in that state is kept inert from then on (see `dead`) -- further rounds change neither
 // its best nor its cells -- so the pairs of a warp may keep running together until the last one is done.
 // All communication of a round is ONE stage of independent shuffles issued right after the cells are computed (the
@@ -167,7 +173,8 @@ SWB_HD void sg2_init(Sg2State<NW>& s, const Env& env, const uint8_t* seq1, const
 //     result[0] < result[31]   <=>   t2[0] < t2[31]  and  t2[31] - c >= 0
 // (with c the amount subtracted this round; dropped cells compare as the smallest value).
 template <bool RECORD, int NW, class Env>
-SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride)
+SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int len, int round, uint32_t* rec_row, int rec_stride,
+                      const uint8_t* role_seq2 = nullptr)
 {
     constexpr int LAST = Sg2State<NW>::kLast, NA = NW / 2;
     const int q = env.q();
@@ -210,19 +217,31 @@ SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int le
     uint32_t m = sg2_max_words<NW>(t2);
     m = vmax2(m, prmt(m, m, 0x1032u));                     // both halves: the maximum of this lane's cells
     const uint32_t xr = prmt(t2[0], s.B[0], 0x0410u), xd = prmt(t2[NW - 1], s.A[NA - 1], 0x0732u);
-    const uint32_t m1 = env.shfl_xor(m, 1);
-    uint32_t m2 = m1, m3 = m1;
-    if (NW == 4) { m2 = env.shfl_xor(m, 2); m3 = env.shfl_xor(m, 3); }
-    const uint32_t e0 = env.shfl(t2[0], 0), e31 = env.shfl(t2[NW - 1], LAST);
-    const uint32_t gn = env.shfl(xr, q + 1), gp = env.shfl(xd, q - 1);
+    uint32_t m1 = m, m2 = m, m3 = m, e0 = t2[0], e31 = t2[NW - 1], gn = xr, gp = xd;      // one lane per pair: nothing to exchange
+    if (LAST > 0) {
+        m1 = env.shfl_xor(m, 1);
+        if (NW == 4) { m2 = env.shfl_xor(m, 2); m3 = env.shfl_xor(m, 3); }
+        e0 = env.shfl(t2[0], 0); e31 = env.shfl(t2[NW - 1], LAST);
+        gn = env.shfl(xr, q + 1); gp = env.shfl(xd, q - 1);
+    }
     // ---- the record (independent of the shuffles).  tag = t - t2 (no borrow between the halves: clearing bits never
     // raises a half), gathered as multiply-adds: word w's tags land at bits 2w (cell 2w) and 16 + 2w (cell 2w + 1)
     if (RECORD) {
         const uint32_t mone = 0u - one;
         uint32_t neg = t2[0] * one, acc = t[0] * one;
 #pragma unroll
-        for (int w = 1; w < NW; ++w) { neg = t2[w] * (one << (2 * w)) + neg; acc = t[w] * (one << (2 * w)) + acc; }
-        if (NW == 4) {
+        for (int w = 1; w < (NW < 8 ? NW : 8); ++w) { neg = t2[w] * (one << (2 * w)) + neg; acc = t[w] * (one << (2 * w)) + acc; }
+        if (NW == 16) {                                     // the sums above cover words 0-7; words 8-15 fill a second word
+            uint32_t neg2 = t2[8 % NW] * one, acc2 = t[8 % NW] * one;
+#pragma unroll
+            for (int w = 9; w < NW; ++w) { neg2 = t2[w % NW] * (one << (2 * (w - 8))) + neg2; acc2 = t[w % NW] * (one << (2 * (w - 8))) + acc2; }
+            uint32_t* const at = rec_row + rec_stride * round;                             // {tags of cells 0-15, of cells 16-31, moves, 0}
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint4*>(at) = make_uint4(neg * mone + acc, neg2 * mone + acc2, moves, 0u);       // one 16-byte store
+#else
+            at[0] = neg * mone + acc; at[1] = neg2 * mone + acc2; at[2] = moves; at[3] = 0u;
+#endif
+        } else if (NW == 4) {
             rec_row[rec_stride * round + q] = neg * mone + acc + moves * (one << 8);       // tags in bytes 0 and 2, moves in byte 1
         } else {
             uint32_t* const at = rec_row + rec_stride * round + 2 * q;                     // {32 tag bits, moves}
@@ -233,7 +252,7 @@ SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int le
     // ---- round maximum (source.cpp:1925).  In the X-drop frame the best so far sits at 69 or 70, a cell is at most
     // two above it, and the threshold moves exactly when a cell reaches 72 -- so the amount subtracted this round,
     // c = 1 + off, comes from one packed compare; the bookkeeping of the best (below) is off the critical path.
-    m = (NW == 4) ? vmax2(vmax3(m, m1, m2), m3) : vmax2(m, m1);
+    if (LAST > 0) m = (NW == 4) ? vmax2(vmax3(m, m1, m2), m3) : vmax2(m, m1);
     const uint32_t off = vaddmax2(m, 0xFEE1FEE1u, 0u) & 1u;        // max(m - 287, 0): 1 iff the maximum is 4 * 72
     // ---- X-drop and "<= 0 is dropped" (source.cpp:1918,1933-1936) in the new frame
     // A finished pair must stay finished while its warp runs on: the round after the last one could otherwise revive a
@@ -251,13 +270,27 @@ SWB_HD bool sg2_round(Sg2State<NW>& s, Env& env, const uint8_t* role_seq, int le
     const bool rn = sg2_half(e0, 0) < t31 && t31 > (int32_t)(4u * off);   // t31 - 4c >= 0 (multiples of 4)
     const bool edge = rn ? (q == LAST) : (q == 0);         // the band's end: a dropped cell and a new base come in
     uint32_t cand = rn ? gn : gp;
-    if (edge) cand = s.next_raw * 0x110000u + s.role_base;
+    if (LAST == 0) {                                        // one lane per pair: always the end; the seq2 side on a right move
+        cand = (rn ? s.nextb_raw : s.next_raw) * 0x110000u + (rn ? SG2_F : s.role_base);
+    } else if (edge) {
+        cand = s.next_raw * 0x110000u + s.role_base;
+    }
     s.got = vminu2(vaddmax2(cand, nc & 0xffffu, 0x80000000u | SG2_F), 0xFFFF0000u | SG2_F);   // drop the cell; the upper half (base, stray byte) passes
     s.right = rn ? 1u : 0u;
     // the base after next, branch-free: shift the two staged bases, load the new one under a predicate
-    s.cidx += edge ? 1 : 0;
-    s.next_raw = edge ? s.next2_raw : s.next_raw;
-    s.next2_raw = ld_u8_if(role_seq + s.cidx, edge && (uint32_t)s.cidx < (uint32_t)len, edge ? (q == 0 ? 4u : 5u) : s.next2_raw);
+    if (LAST == 0) {
+        const bool ea = !rn, eb = rn;
+        s.cidx += ea ? 1 : 0;
+        s.next_raw = ea ? s.next2_raw : s.next_raw;
+        s.next2_raw = ld_u8_if(role_seq + s.cidx, ea && (uint32_t)s.cidx < (uint32_t)len, ea ? 4u : s.next2_raw);
+        s.cidxb += eb ? 1 : 0;
+        s.nextb_raw = eb ? s.nextb2_raw : s.nextb_raw;
+        s.nextb2_raw = ld_u8_if(role_seq2 + s.cidxb, eb && (uint32_t)s.cidxb < (uint32_t)len, eb ? 5u : s.nextb2_raw);
+    } else {
+        s.cidx += edge ? 1 : 0;
+        s.next_raw = edge ? s.next2_raw : s.next_raw;
+        s.next2_raw = ld_u8_if(role_seq + s.cidx, edge && (uint32_t)s.cidx < (uint32_t)len, edge ? (q == 0 ? 4u : 5u) : s.next2_raw);
+    }
     // ---- the best so far (source.cpp:1928-1931: strict, the FIRST round that reaches it)
     const int32_t rmax = sg2_half(m, 0);
     const int32_t amax = (rmax >> 2) - 1 + s.T;            // with the reference's +70 offset
@@ -285,15 +318,15 @@ SWB_HD void sg2_finish(const Sg2State<NW>& s, Env& env, int32_t& score, int32_t&
     const int q = env.q();
     uint32_t m = sg2_max_words<NW>(s.Rb);                  // the best round's maximum, once more
     m = vmax2(m, prmt(m, m, 0x1032u));
-    m = vmax2(m, env.shfl_xor(m, 1));
+    if (NW <= 8) m = vmax2(m, env.shfl_xor(m, 1));
     if (NW == 4) m = vmax2(m, env.shfl_xor(m, 2));
     const int32_t best_m = sg2_half(m, 0);
     loc = -1;
 #pragma unroll
     for (int c = 0; c < CELLS; ++c)
         if (sg2_half(s.Rb[c >> 1], c & 1) == best_m) loc = CELLS * q + c;
-    int32_t o = (int32_t)env.shfl_xor((uint32_t)loc, 1); loc = loc > o ? loc : o;
-    if (NW == 4) { o = (int32_t)env.shfl_xor((uint32_t)loc, 2); loc = loc > o ? loc : o; }
+    if (NW <= 8) { const int32_t o = (int32_t)env.shfl_xor((uint32_t)loc, 1); loc = loc > o ? loc : o; }
+    if (NW == 4) { const int32_t o = (int32_t)env.shfl_xor((uint32_t)loc, 2); loc = loc > o ? loc : o; }
     score = s.best - SG2_X;
     end_y = s.best_py + 31 - loc;
     end_x = (s.best_round - s.best_py) - 31 + loc;         // pos_x = 31 + (number of right moves)
@@ -313,10 +346,14 @@ SWB_HD uint32_t sg2_tb_step(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, 
         const uint32_t w = (o & 16) ? ((o & 8) ? r3 : r2) : ((o & 8) ? r1 : r0);
         code = (w >> (((o & 1) << 4) | (o & 6))) & 3u;
         mv = w >> 8;
-    } else {                                                // lane o >> 4: {32 tag bits, moves}
+    } else if (NW == 8) {                                   // lane o >> 4: {32 tag bits, moves}
         const uint32_t w = (o & 16) ? r2 : r0;
         code = (w >> (((o & 1) << 4) | (o & 14))) & 3u;
         mv = r1;
+    } else {                                                // {tags of cells 0-15, tags of cells 16-31, moves, -}
+        const uint32_t w = (o & 16) ? r1 : r0;
+        code = (w >> (((o & 1) << 4) | (o & 14))) & 3u;
+        mv = r2;
     }
     const uint32_t diag = code == 3u ? 1u : 0u;
     o += (int)(code >> 1) - (int)(mv & 1u) - (int)((mv >> 1) & diag);

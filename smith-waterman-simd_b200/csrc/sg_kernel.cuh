@@ -62,10 +62,12 @@ struct SgOut {
 // sixteen pairs per warp (NW = 8).  The lane groups of a warp run their pairs side by side and pick up the next ones
 // together (pairs of similar length finish together; the bench's and the reference's pairs all run the full 2*len rounds).
 constexpr int SG2_THREADS = 32;
-// Words per lane of the shipped forward kernel.  8 (two lanes per pair, sixteen pairs per warp) needs 224 instructions per
-// warp-round = 14 per pair; 4 (four lanes, eight pairs) needs 158 = 19.8 per pair and measured 12 % slower at 18944 pairs
-// (1.06 M vs 1.21 M alignments/s), 3 % slower at 8192.
-constexpr int kSgWords = 8;
+// Words per lane of the forward kernel, chosen per launch by the batch size (sg_words_for): 16 -- the whole band in one lane,
+// 32 pairs per warp, no shuffles, 360 instructions per warp-round = 11.3 per pair -- once the batch gives every scheduler
+// a warp of 32 pairs; below that 8 -- two lanes per pair, sixteen pairs per warp, 224 = 14 per pair -- which has twice
+// the warps.  Measured (alignments/s, 16384-mers): 8192 pairs 599 k / 784 k (16 / 8 words); 18 944 pairs 1.24 M / 1.21 M;
+// 37 888 pairs 1.42 M with 16 words.  Four lanes per pair (4 words, 158 = 19.8 per pair) never won: 759 k and 1.06 M.
+__host__ __device__ inline int sg_words_for(unsigned long long pairs, int sm_count) { return pairs >= (unsigned long long)sm_count * 128ull ? 16 : 8; }
 
 template <int LANES>
 struct Sg2DevEnv {
@@ -103,7 +105,7 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
         sg2_init(s, env, s1, s2, len);
         const uint8_t* const role = env.q() == 0 ? s1 : s2;
         for (int round = 1; round < max_round; ++round) {
-            const bool go = sg2_round<RECORD>(s, env, role, len, round, rec_row, 4 * SG_GROUP);
+            const bool go = sg2_round<RECORD>(s, env, role, len, round, rec_row, 4 * SG_GROUP, s2);
             if ((round & 3) == 0 && !__any_sync(0xffffffffu, go)) break;      // a finished pair stays finished: asking every fourth round is enough
         }
         int32_t score, end_y, end_x, best_round, loc;

@@ -275,7 +275,8 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<kSgWords>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -566,17 +567,24 @@ int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* 
         const uint64_t m = (n - c0 < per) ? n - c0 : per;
         SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
         const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);      // a warp per group of 32 pairs
-        const uint64_t ppw = 32 / Sg2State<kSgWords>::kLanes;      // pairs per warp
+        const int nw = sg_words_for(m, d->prop.multiProcessorCount);
+        const uint64_t ppw = nw == 16 ? 32 : 16;                  // pairs per warp
         const uint64_t need = ((m + ppw - 1) / ppw * 32 + SG2_THREADS - 1) / SG2_THREADS;
         const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
         const unsigned fgrid = (unsigned)(need < cap ? need : cap);
         const uint8_t* const a1 = d1 + c0 * (uint64_t)len; const uint8_t* const a2 = d2 + c0 * (uint64_t)len;
-        if (d_ops) sg2_xdrop_kernel<true, kSgWords><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
-        else sg2_xdrop_kernel<false, kSgWords><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+        if (nw == 16) {
+            if (d_ops) sg2_xdrop_kernel<true, 16><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+            else sg2_xdrop_kernel<false, 16><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+        } else {
+            if (d_ops) sg2_xdrop_kernel<true, 8><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+            else sg2_xdrop_kernel<false, 8><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
+        }
         SWB_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         if (d_ops) {
-            sg_traceback_kernel<kSgWords><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            if (nw == 16) sg_traceback_kernel<16><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
+            else sg_traceback_kernel<8><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
             sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
             SWB_CUDA(ctx, cudaGetLastError());
@@ -1075,8 +1083,8 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     cudaFuncAttributes fa{};
     int blocks = 0;
-    SWB_CUDA(ctx, (cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true, kSgWords>)));
-    SWB_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true, kSgWords>, SG2_THREADS, 0)));
+    SWB_CUDA(ctx, (cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true, 16>)));       // the large-batch kernel (sg_words_for)
+    SWB_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true, 16>, SG2_THREADS, 0)));
     info->threads_per_block = SG2_THREADS;
     info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
     info->fast_path = 0;

@@ -53,7 +53,8 @@ void lane_main(int lane)
     const int max_round = 2 * Q.len + 1;
     // On the device a finished pair keeps running rounds beside the live pairs of its warp: run EVERY round here, so
     // that a finished pair that is not inert (a best, a threshold or a record that still moves) shows up as a mismatch.
-    for (int round = 1; round < max_round; ++round) sg2_round<true>(s, env, role, Q.len, round, Q.rec.data(), 4);
+    if (Sg2State<NW>::kLanes == 1) role = Q.seq1;
+    for (int round = 1; round < max_round; ++round) sg2_round<true>(s, env, role, Q.len, round, Q.rec.data(), 4, Q.seq2);
     int32_t sc, ey, ex, br, loc;
     sg2_finish(s, env, sc, ey, ex, br, loc);
     if (lane == 0) { Q.score = sc; Q.end_y = ey; Q.end_x = ex; Q.best_round = br; Q.loc = loc; }
@@ -104,10 +105,11 @@ int run(const uint8_t* seq1, const uint8_t* seq2, int len, int32_t* score, int32
 
 } // namespace
 
-// words_per_lane: 4 (four lanes per pair) or 8 (two lanes per pair)
+// words_per_lane: 4 (four lanes per pair), 8 (two lanes per pair) or 16 (one lane per pair)
 extern "C" int swemu_sg2(const uint8_t* seq1, const uint8_t* seq2, int len, int32_t* score, int32_t* end_y, int32_t* end_x,
                          uint8_t* ops, int32_t* n_ops, int words_per_lane)
 {
+    if (words_per_lane == 16) return run<16>(seq1, seq2, len, score, end_y, end_x, ops, n_ops);
     if (words_per_lane == 8) return run<8>(seq1, seq2, len, score, end_y, end_x, ops, n_ops);
     return run<4>(seq1, seq2, len, score, end_y, end_x, ops, n_ops);
 }

@@ -93,11 +93,11 @@ def test_lengths_against_oracle(ctx, oracle, length):
 
 
 def test_more_pairs_than_resident_warps(ctx, oracle):
-    # the forward grid is persistent (SMs x resident blocks of one warp, sixteen pairs per warp): with more than sixteen
-    # pairs per resident warp every warp takes a second batch; 777 is not a multiple of 16 or 32, so the last warp has
-    # lane groups beyond the batch (they shadow the last pair into the spare group) and the last traceback warp is partial
+    # the forward grid is persistent (SMs x resident blocks of one warp; a batch this large runs 32 pairs per warp): with
+    # more pairs than that every warp takes a second batch; 777 is not a multiple of 32, so the last warp has lanes beyond
+    # the batch (they shadow the last pair into the spare group) and the last traceback warp is partial
     info = ctx.semiglobal_kernel_info()
-    resident = 16 * info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
+    resident = 32 * info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] // 32
     n = resident + 777
     rng = np.random.default_rng(9)
     length = 96

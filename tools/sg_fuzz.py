@@ -56,7 +56,7 @@ def worker(args):
         meta = np.zeros(4, np.int32)
         ops = np.zeros(2 * L, np.uint8)
         rc = lib.swemu_sg2(a.ctypes.data, b.ctypes.data, L, meta[0:].ctypes.data, meta[1:].ctypes.data, meta[2:].ctypes.data,
-                           ops.ctypes.data, meta[3:].ctypes.data, 8 if n % 2 == 0 else 4)
+                           ops.ctypes.data, meta[3:].ctypes.data, (16, 8, 4)[n % 3])
         exp = O.semiglobal_xdrop(a, b)
         if rc != 0 or (int(meta[0]), int(meta[1]), int(meta[2])) != exp[:3] or not np.array_equal(ops[:meta[3]], exp[3]):
             np.save(f"/tmp/sgfuzz_{seed}_{n}_a.npy", a); np.save(f"/tmp/sgfuzz_{seed}_{n}_b.npy", b)
