@@ -127,8 +127,8 @@ sg2_xdrop_kernel(const uint8_t* __restrict__ seq1, const uint8_t* __restrict__ s
 // Step k (k = 0 is the LAST move) is written to row[2*len - 1 - k], so the row ends up holding the forward-ordered op
 // string right-aligned; sg_left_align_kernel then moves it to the left edge.
 constexpr int SG_TB_THREADS = 64;
-constexpr int SG_TB_DEPTH = 64;
-constexpr size_t SG_TB_SMEM = (size_t)SG_TB_DEPTH * SG_TB_THREADS * sizeof(uint4);    // 64 KiB
+constexpr int SG_TB_DEPTH = 32;
+constexpr size_t SG_TB_SMEM = (size_t)SG_TB_DEPTH * SG_TB_THREADS * sizeof(uint4);    // 32 KiB: seven blocks per SM (64 KiB allowed three, and a batch of 37888 pairs ran in two waves)
 
 __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem_src)
 {
