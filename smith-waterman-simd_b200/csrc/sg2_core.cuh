@@ -1,13 +1,13 @@
-// sg2_core.cuh -- one round of the adaptive-banded X-drop semi-global aligner, FOUR LANES PER PAIR,
-// eight band cells per lane in packed int16x2 registers.
+// sg2_core.cuh -- one round of the adaptive-banded X-drop semi-global aligner with the band in packed int16x2
+// registers: all 32 cells in one lane (32 pairs per warp) or 16 cells in each of two lanes.
 //
 // What it computes: exactly SemiGlobal_AdaptiveBanded_XDrop_111_32_70 (/root/reference/source.cpp:1836-1976)
 // and hence its AVX2 forms (source.cpp:1978-2725): see sg_kernel.cuh for the statement of the algorithm.
 //
 // Why this shape.  A round is one serial chain (direction -> shift -> 32 cells -> maximum -> X-drop), so the
 // bound is instructions per round.  With a warp per pair every instruction serves ONE cell per lane; here a
-// lane owns cells 8q..8q+7 of the band as four int16x2 words, so the cell arithmetic, the shifts and the
-// traceback masks are packed two cells per instruction and a warp advances EIGHT pairs per round.
+// lane owns 16 or 32 cells of the band as int16x2 words, so the cell arithmetic, the shifts and the traceback
+// evidence are packed two cells per instruction, and a warp advances 16 or 32 pairs per round.
 //   * Values live in the X-drop frame: u = value - T with T = max(best - 70, 1) (the reference's own
 //     trick for its 8-bit AVX2 forms, offset_diff at source.cpp:2661-2665), so every live cell is in 0..70
 //     and int16 never overflows at any length.  Registers hold 4u; a dropped cell is the sentinel
@@ -23,14 +23,14 @@
 //     value (unsigned >= 0xC000; none is below F) to F and keeps 0..288: the X-drop and the reference's "0 = dropped" in
 //     one instruction, with no compare/select.
 //   * The band shift of the reference (alignr/permute2x128, source.cpp:2622,2632) is a funnel shift by
-//     16 or 0 bits per word (the amount is the direction, so the pairs of a warp do not diverge) plus ONE
-//     shuffle between neighbouring lanes that carries the boundary cell and the boundary base together.
-//   * The 32 bases of either sequence under the band are two registers per lane (a byte per cell); they
+//     16 or 0 bits per word (the amount is the direction, so the pairs of a warp do not diverge) plus, with two
+//     lanes per pair, ONE shuffle between the lanes that carries the boundary cell and the boundary base together.
+//   * The 32 bases of either sequence under the band are bytes in registers (a byte per cell); they
 //     shift by 8 or 0 bits; the match score of two cells is one PRMT through an 8-byte table indexed by
 //     a XOR b (the reference's pshufb table, source.cpp:2640-2641).
-//   * Traceback evidence, not band values, is stored: the 2-bit tag of every cell, gathered with four
-//     multiply-adds on the FMA pipe: 4 bytes per lane per round (16 per pair); a spare byte says which way the
-//     band moved in this round and the one before, which is all the traceback needs to follow a cell.
+//   * Traceback evidence, not band values, is stored: the 2-bit tag of every cell, gathered with multiply-adds:
+//     16 bytes per pair per round, two bits of which say which way the band moved in this round and the one
+//     before -- all the traceback needs to follow a cell.
 //
 // Every function is SWB_HD and templated on an Env that supplies the lane index and the two shuffles, so
 // the same text runs on the device (real shuffles) and in tests/emu (four coroutines in lock step).

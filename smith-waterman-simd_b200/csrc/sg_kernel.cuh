@@ -11,17 +11,18 @@
 // (source.cpp:1928-1931, 1953-1954), traceback preferring diagonal > up > left (source.cpp:1958-1971).
 //
 // This is not a translation of the AVX2 code.  The mapping is the one the band suggests on a GPU:
-//   * FOUR LANES PER PAIR, eight band cells per lane in packed int16x2 registers (sg2_core.cuh): a warp advances
-//     eight pairs per round.  The reference's byte shifts across a 256-bit register (alignr/permute2x128,
-//     source.cpp:2622,2632) are funnel shifts inside a lane plus one shuffle between neighbouring lanes; its
-//     five-step horizontal max (source.cpp:2656-2660) is three shuffles and two packed max.
+//   * THE BAND IN ONE LANE (or two), as packed int16x2 registers (sg2_core.cuh): a warp advances 32 (16) pairs per
+//     round.  The reference's byte shifts across a 256-bit register (alignr/permute2x128, source.cpp:2622,2632)
+//     are funnel shifts inside a lane; its five-step horizontal max (source.cpp:2656-2660) is a chain of packed
+//     three-input max.
 //   * Values live in the X-drop frame (value - max(best - 70, 1)), as in the reference's 8-bit AVX2 forms
 //     (offset_diff, source.cpp:2661-2665), so int16 holds at any length; a dropped cell is a sentinel that one
 //     unsigned minimum produces.
 //   * The reference keeps the whole band history (1 MB of uint8 per pair, source.cpp:2591) and re-derives each
 //     traceback step by comparing scores.  Here the forward pass records, per round and cell, the OUTCOME of those
 //     comparisons -- "this cell's value came from the diagonal" / "... from above", evaluated with the reference's
-//     own comparisons and preference order -- plus the band's pos_y: 16 bytes per round (4 per lane).
+//     own comparisons and preference order (a 2-bit tag per cell) -- plus two bits that say which way the band moved:
+//     16 bytes per round.
 //   * The traceback is a second kernel, ONE THREAD PER PAIR: the walk is serial (as in the reference), so a warp
 //     spent on it would execute every instruction for one live lane.  The records of 32 pairs are interleaved
 //     round by round, and the 32 walkers of a warp march down the ROUNDS together (a walker acts in the rounds its
