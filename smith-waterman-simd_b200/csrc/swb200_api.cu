@@ -627,16 +627,19 @@ int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t*
     if (hi <= lo) return SWB200_OK;
     std::lock_guard<std::mutex> lock(d->mu);
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    // chunk: 32 pairs per SM (one forward warp per scheduler), at least 32 MiB of sequence per array; the range is cut
-    // in equal chunks.  The forward kernels of the four slots run side by side (a chunk alone leaves most issue slots
-    // idle), and the short chunks keep the exposed head (first H2D) and tail (last traceback + D2H) of the pipeline small.
-    // Measured with SWB200_SG_TIMELINE on 16384 pairs (31.4 ms): the four forward kernels share the issue slots evenly and
-    // finish together at ~23.8 ms, so three result copies (2.4 ms each) are exposed.  Two alternatives made no difference:
-    // stream priorities (every block is resident anyway), and letting only two chunks' forward kernels run at a time (the
-    // chunks then finish in order, but each traceback runs beside forward warps and slows down: 31.3 ms).
-    const uint64_t wave = (uint64_t)d->prop.multiProcessorCount * 64;      // pairs that give every scheduler two warps of the forward kernel
+    // The range is cut in equal chunks that go round the four slots; the kernels of different slots run side by side and
+    // the copies overlap them.  Measured with SWB200_SG_TIMELINE on 16384 pairs in four chunks (31.4 ms): the four forward
+    // kernels share the issue slots evenly and finish together at ~23.8 ms, so three result copies (2.4 ms each) are
+    // exposed.  Two alternatives made no difference: stream priorities (every block is resident anyway), and letting only
+    // two chunks' forward kernels run at a time (the chunks then finish in order, but each traceback runs beside forward
+    // warps and slows down: 31.3 ms).  What does help is fewer, larger chunks for large batches (each kernel then runs at
+    // the efficient lane width): 37888 pairs in two chunks 63.6 ms, in eight chunks 74.4 ms.
+    // Chunk size: the forward kernel wants 128 pairs per SM (a warp of 32 pairs on every scheduler); a batch that has
+    // at least two such chunks is cut that way, a smaller one into halves of that, down to 32 pairs per SM.
+    const uint64_t sms = (uint64_t)d->prop.multiProcessorCount;
     uint64_t chunk = (32ull << 20) / (uint64_t)len;
-    if (chunk < wave / 2) chunk = wave / 2;
+    for (uint64_t per_sm = 128; per_sm >= 32; per_sm >>= 1)
+        if (hi - lo >= 2 * sms * per_sm || per_sm == 32) { if (chunk < sms * per_sm) chunk = sms * per_sm; break; }
     if (chunk > sg_pairs_per_launch(len)) chunk = sg_pairs_per_launch(len);
     const uint64_t parts = (hi - lo + chunk - 1) / chunk;
     chunk = (hi - lo + parts - 1) / parts;

@@ -120,16 +120,17 @@ def test_more_pairs_than_resident_warps(ctx, oracle):
 
 
 def test_staging_slots_are_reused(ctx, oracle):
-    # len = 2048: the host path cuts the batch into chunks of 16384 pairs (32 MiB per array) over four independent
-    # slots; a fifth chunk reuses slot 0 after its first chunk is back on the host
-    n = 4 * 16384 + 5003
+    # len = 2048: the host path cuts a batch of more than four times 128 pairs per SM into five chunks over four
+    # independent slots; the fifth chunk reuses slot 0 after its first chunk is back on the host
+    n = 4 * 128 * ctx.semiglobal_kernel_info()["sm_count"] + 5003
     length = 2048
     rng = np.random.default_rng(78)
     a = rng.integers(0, 4, (n, length), dtype=np.uint8)
     b = np.where(rng.random((n, length)) < 0.88, a, rng.integers(0, 4, (n, length), dtype=np.uint8)).astype(np.uint8)
     b[::9] = np.roll(a[::9], -7, axis=1)
     r = ctx.semiglobal_xdrop(a, b)
-    idx = np.r_[0:40, 16384 - 20:16384 + 20, 3 * 16384 - 20:3 * 16384 + 20, 4 * 16384 - 20:4 * 16384 + 60, n - 40:n].tolist()
+    c = -(-n // 5)                                   # the chunk size the library arrives at: five equal parts
+    idx = np.r_[0:40, c - 20:c + 20, 3 * c - 20:3 * c + 20, 4 * c - 20:4 * c + 60, n - 40:n].tolist()
     check_against_oracle(oracle, r, a, b, idx)
     ops, n_ops = r["ops"], r["n_ops"]
     valid = np.arange(ops.shape[1])[None, :] < n_ops[:, None]
