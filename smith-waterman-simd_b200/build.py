@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libswb200.so")
 SOURCES = [os.path.join(CSRC, "swb200_api.cu"), os.path.join(CSRC, "pairgen.cpp"), os.path.join(CSRC, "hostpack.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("sw_core.cuh", "sw_kernel.cuh", "sg_kernel.cuh", "sw_params.h")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("sw_core.cuh", "sw_kernel.cuh", "sg_kernel.cuh", "sg2_core.cuh", "sg_host.inc", "sg_abi.inc", "sw_params.h")] + [
     os.path.join(ROOT, "include", "swb200.h"), os.path.abspath(__file__)]
 
 NVCC_FLAGS = [

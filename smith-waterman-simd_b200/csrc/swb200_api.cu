@@ -525,180 +525,8 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
     return job.rc.load();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Semi-global X-drop aligner (sg_kernel.cuh)
-constexpr int kSgMaxLen = 1 << 15;                // pos_y <= len + 1 must fit the 16 bits it has in a round record
-constexpr int kSgBlocksPerSm = 24;                // resident warps per SM of the forward kernel
-
-constexpr size_t kSgTraceBudget = 40ull << 30;    // round records kept per launch (524 800 B per pair at len 16384: 81 800 pairs)
-
-uint64_t sg_pairs_per_launch(int len)
-{
-    const uint64_t groups = kSgTraceBudget / sg_group_bytes(len);
-    return groups > 1 ? (groups - 1) * SG_GROUP : SG_GROUP;
-}
-
-int sg_ensure_scratch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, int len, uint64_t n)
-{
-    const uint64_t pairs = n < sg_pairs_per_launch(len) ? n : sg_pairs_per_launch(len);
-    const size_t need_trace = sg_groups_for(pairs) * sg_group_bytes(len);      // groups of 32 pairs + the spare group of sg2_xdrop_kernel
-    const bool grow_trace = need_trace > sc.trace_bytes;
-    if (!grow_trace) return SWB200_OK;
-    SWB_CUDA(ctx, cudaDeviceSynchronize());
-    {
-        cudaFree(sc.traces);
-        sc.traces = nullptr; sc.trace_bytes = 0;
-        SWB_CUDA(ctx, cudaMalloc(&sc.traces, need_trace));
-        sc.trace_bytes = need_trace;
-    }
-    return SWB200_OK;
-}
-
-// The launches alone, on device arrays: the forward kernel (four lanes per pair) and, when ops are wanted, the
-// traceback and left-align kernels (one thread / one block per pair), in equal sub-batches that fit the record
-// scratch.  All launches on one scratch must be stream-ordered with each other.
-int sg_launch(swb200_ctx* ctx, Device* d, Device::SgScratch& sc, const uint8_t* d1, const uint8_t* d2, int len, uint64_t n,
-              int32_t* d_score, int32_t* d_ey, int32_t* d_ex, int32_t* d_nops, uint8_t* d_ops, cudaStream_t st)
-{
-    const uint64_t cap_pairs = (sc.trace_bytes / sg_group_bytes(len) - 1) * SG_GROUP;
-    const uint64_t parts = (n + cap_pairs - 1) / cap_pairs;
-    const uint64_t per = (n + parts - 1) / parts;                 // equal parts: no small remainder launch that leaves the GPU mostly idle
-    for (uint64_t c0 = 0; c0 < n; c0 += per) {
-        const uint64_t m = (n - c0 < per) ? n - c0 : per;
-        SgOut out{d_score + c0, d_ey + c0, d_ex + c0, d_nops ? d_nops + c0 : nullptr, d_ops ? d_ops + c0 * 2ull * (uint64_t)len : nullptr};
-        const unsigned tb_grid = (unsigned)((m + SG_TB_THREADS - 1) / SG_TB_THREADS);      // a warp per group of 32 pairs
-        const int nw = sg_words_for(m, d->prop.multiProcessorCount);
-        const uint64_t ppw = nw == 16 ? 32 : 16;                  // pairs per warp
-        const uint64_t need = ((m + ppw - 1) / ppw * 32 + SG2_THREADS - 1) / SG2_THREADS;
-        const uint64_t cap = (uint64_t)d->prop.multiProcessorCount * kSgBlocksPerSm;
-        const unsigned fgrid = (unsigned)(need < cap ? need : cap);
-        const uint8_t* const a1 = d1 + c0 * (uint64_t)len; const uint8_t* const a2 = d2 + c0 * (uint64_t)len;
-        if (nw == 16) {
-            if (d_ops) sg2_xdrop_kernel<true, 16><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
-            else sg2_xdrop_kernel<false, 16><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
-        } else {
-            if (d_ops) sg2_xdrop_kernel<true, 8><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
-            else sg2_xdrop_kernel<false, 8><<<fgrid, SG2_THREADS, 0, st>>>(a1, a2, len, m, sc.traces, out, 1u);
-        }
-        SWB_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 1;
-        if (d_ops) {
-            if (nw == 16) sg_traceback_kernel<16><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
-            else sg_traceback_kernel<8><<<tb_grid, SG_TB_THREADS, SG_TB_SMEM, st>>>(sc.traces, len, m, out);
-            SWB_CUDA(ctx, cudaGetLastError());
-            sg_left_align_kernel<<<(unsigned)m, 256, 0, st>>>(len, m, out);
-            SWB_CUDA(ctx, cudaGetLastError());
-            ctx->launches += 2;
-        }
-    }
-    return SWB200_OK;
-}
-
-int sg_check(swb200_ctx* ctx, const void* a, const void* b, int len, uint64_t n, const void* score, const void* ey, const void* ex,
-             const void* nops, const void* ops)
-{
-    if (!ctx) return SWB200_ERR_ARG;
-    if (len < 1 || len > kSgMaxLen) return fail(ctx, SWB200_ERR_ARG, "seq_len must be in [1, 32768]");
-    if (n && (!a || !b || !score || !ey || !ex)) return fail(ctx, SWB200_ERR_ARG, "NULL array with n > 0");
-    if (n && ((ops == nullptr) != (nops == nullptr))) return fail(ctx, SWB200_ERR_ARG, "ops and n_ops must both be given or both be NULL");
-    return SWB200_OK;
-}
-
-int sg_ensure_slot(swb200_ctx* ctx, Device::SgSlot& s, size_t cap, int len, bool with_ops)
-{
-    if (!s.stream) SWB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    if (s.cap_pairs >= cap && s.len >= len && (s.with_ops || !with_ops)) return SWB200_OK;
-    SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));
-    cudaFree(s.d_seq1); cudaFree(s.d_seq2); cudaFree(s.d_ops); cudaFree(s.d_meta);
-    s.d_seq1 = s.d_seq2 = s.d_ops = nullptr; s.d_meta = nullptr; s.cap_pairs = 0;
-    SWB_CUDA(ctx, cudaMalloc(&s.d_seq1, cap * (size_t)len));
-    SWB_CUDA(ctx, cudaMalloc(&s.d_seq2, cap * (size_t)len));
-    SWB_CUDA(ctx, cudaMalloc(&s.d_meta, 4 * cap * sizeof(int32_t)));
-    if (with_ops) SWB_CUDA(ctx, cudaMalloc(&s.d_ops, cap * 2 * (size_t)len));
-    s.cap_pairs = cap; s.len = len; s.with_ops = with_ops;
-    return SWB200_OK;
-}
-
-// One GPU's share [lo, hi) of a host batch: chunks go round four slots, each an independent stream with its own
-// staging buffers and record scratch, so copies overlap kernels.
-int sg_run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, int len, uint64_t lo, uint64_t hi,
-                 int32_t* score, int32_t* ey, int32_t* ex, int32_t* nops, uint8_t* ops)
-{
-    if (hi <= lo) return SWB200_OK;
-    std::lock_guard<std::mutex> lock(d->mu);
-    SWB_CUDA(ctx, cudaSetDevice(d->id));
-    // The range is cut in equal chunks that go round the four slots; the kernels of different slots run side by side and
-    // the copies overlap them.  Measured with SWB200_SG_TIMELINE on 16384 pairs in four chunks (31.4 ms): the four forward
-    // kernels share the issue slots evenly and finish together at ~23.8 ms, so three result copies (2.4 ms each) are
-    // exposed.  Two alternatives made no difference: stream priorities (every block is resident anyway), and letting only
-    // two chunks' forward kernels run at a time (the chunks then finish in order, but each traceback runs beside forward
-    // warps and slows down: 31.3 ms).  What does help is fewer, larger chunks for large batches (each kernel then runs at
-    // the efficient lane width): 37888 pairs in two chunks 63.6 ms, in eight chunks 74.4 ms.
-    // Chunk size: the forward kernel wants 128 pairs per SM (a warp of 32 pairs on every scheduler); a batch that has
-    // at least two such chunks is cut that way, a smaller one into halves of that, down to 32 pairs per SM.
-    const uint64_t sms = (uint64_t)d->prop.multiProcessorCount;
-    uint64_t chunk = (32ull << 20) / (uint64_t)len;
-    for (uint64_t per_sm = 128; per_sm >= 32; per_sm >>= 1)
-        if (hi - lo >= 2 * sms * per_sm || per_sm == 32) { if (chunk < sms * per_sm) chunk = sms * per_sm; break; }
-    if (chunk > sg_pairs_per_launch(len)) chunk = sg_pairs_per_launch(len);
-    const uint64_t parts = (hi - lo + chunk - 1) / chunk;
-    chunk = (hi - lo + parts - 1) / parts;
-    int rc;
-    for (auto& s : d->sg_slots) {
-        rc = sg_ensure_slot(ctx, s, chunk, len, ops != nullptr);
-        if (rc == SWB200_OK) rc = sg_ensure_scratch(ctx, d, s.scratch, len, chunk);
-        if (rc != SWB200_OK) return rc;
-    }
-    // The slots are independent streams with their own scratch, so copies overlap kernels and the forward kernels of
-    // neighbouring chunks share the machine.  (Measured with SWB200_SG_TIMELINE: ordering the forward kernels so that a
-    // chunk's traceback runs beside the NEXT chunk's forward kernel does not pay -- the traceback is one dependent
-    // chain per thread, and beside eight forward warps per scheduler each of its steps waits its turn: 2.4 ms alone
-    // became 12 ms.)
-    // SWB200_SG_TIMELINE=1: print, per chunk, when its H2D, kernels and D2H finished (ms after the first enqueue)
-    static const bool timeline = getenv("SWB200_SG_TIMELINE") != nullptr;
-    std::vector<cudaEvent_t> marks;
-    size_t n_marked = 0;
-    if (timeline) {
-        marks.resize(4 * (size_t)((hi - lo + chunk - 1) / chunk));
-        for (auto& e : marks) SWB_CUDA(ctx, cudaEventCreate(&e));
-    }
-    auto mark = [&](cudaStream_t st, int which) {
-        if (!timeline) return;
-        cudaEventRecord(marks[4 * n_marked + which], st);
-        if (which == 3) ++n_marked;
-    };
-    int si = 0;
-    for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si = (si + 1) & 3) {
-        Device::SgSlot& s = d->sg_slots[si];
-        const uint64_t m = (hi - c0 < chunk) ? hi - c0 : chunk;
-        SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));                       // this slot's previous chunk is fully back on the host
-        mark(s.stream, 0);
-        SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq1, seq1 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
-        SWB_CUDA(ctx, cudaMemcpyAsync(s.d_seq2, seq2 + c0 * (uint64_t)len, m * (uint64_t)len, cudaMemcpyHostToDevice, s.stream));
-        mark(s.stream, 1);
-        int32_t* meta = s.d_meta;
-        rc = sg_launch(ctx, d, s.scratch, s.d_seq1, s.d_seq2, len, m, meta, meta + s.cap_pairs, meta + 2 * s.cap_pairs,
-                       ops ? meta + 3 * s.cap_pairs : nullptr, ops ? s.d_ops : nullptr, s.stream);
-        if (rc != SWB200_OK) return rc;
-        mark(s.stream, 2);
-        SWB_CUDA(ctx, cudaMemcpyAsync(score + c0, meta, m * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWB_CUDA(ctx, cudaMemcpyAsync(ey + c0, meta + s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
-        SWB_CUDA(ctx, cudaMemcpyAsync(ex + c0, meta + 2 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
-        if (ops) {
-            SWB_CUDA(ctx, cudaMemcpyAsync(nops + c0, meta + 3 * s.cap_pairs, m * 4, cudaMemcpyDeviceToHost, s.stream));
-            SWB_CUDA(ctx, cudaMemcpyAsync(ops + c0 * 2ull * (uint64_t)len, s.d_ops, m * 2ull * (uint64_t)len, cudaMemcpyDeviceToHost, s.stream));
-        }
-        mark(s.stream, 3);
-    }
-    for (auto& s : d->sg_slots) SWB_CUDA(ctx, cudaStreamSynchronize(s.stream));
-    for (size_t k = 0; k < n_marked; ++k) {
-        float t[4] = {0, 0, 0, 0};
-        for (int w = 0; w < 4; ++w) cudaEventElapsedTime(&t[w], marks[0], marks[4 * k + w]);
-        fprintf(stderr, "[swb200 sg timeline] chunk %zu: enqueue %.2f  h2d done %.2f  kernels done %.2f  d2h done %.2f ms\n", k, t[0], t[1], t[2], t[3]);
-    }
-    for (auto& e : marks) cudaEventDestroy(e);
-    return SWB200_OK;
-}
+// Semi-global X-drop aligner: scratch, launches and the host pipeline (a textual part of this translation unit)
+#include "sg_host.inc"
 
 int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, int gap, const void* out, uint64_t n)
 {
@@ -1045,60 +873,8 @@ int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, 
     return swb200_kernel_info_len(ctx, device_index, SWB200_SEQ_LEN, sm, gap, info);
 }
 
-int swb200_semiglobal_xdrop_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t seq_len, uint64_t n,
-                                  int32_t* scores, int32_t* end_y, int32_t* end_x, int32_t* n_ops, uint8_t* ops)
-{
-    int rc = sg_check(ctx, seq1, seq2, seq_len, n, scores, end_y, end_x, n_ops, ops);
-    if (rc != SWB200_OK || n == 0) return rc;
-    const size_t G = ctx->devs.size();
-    if (G == 1 || n < 2 * G) return sg_run_range(ctx, ctx->devs[0], seq1, seq2, seq_len, 0, n, scores, end_y, end_x, n_ops, ops);
-    std::vector<std::thread> pool;
-    std::vector<int> rcs(G, SWB200_OK);
-    for (size_t k = 0; k < G; ++k) {
-        const uint64_t lo = n * k / G, hi = n * (k + 1) / G;       // contiguous index ranges, as for the scoring batch
-        pool.emplace_back([=, &rcs] { rcs[k] = sg_run_range(ctx, ctx->devs[k], seq1, seq2, seq_len, lo, hi, scores, end_y, end_x, n_ops, ops); });
-    }
-    for (auto& t : pool) t.join();
-    for (int r : rcs) if (r != SWB200_OK) return r;
-    return SWB200_OK;
-}
-
-int swb200_semiglobal_xdrop_batch_device(swb200_ctx* ctx, int device_index, const uint8_t* d_seq1, const uint8_t* d_seq2, int32_t seq_len,
-                                         uint64_t n, int32_t* d_scores, int32_t* d_end_y, int32_t* d_end_x, int32_t* d_n_ops, uint8_t* d_ops,
-                                         void* cuda_stream)
-{
-    int rc = sg_check(ctx, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops);
-    if (rc != SWB200_OK || n == 0) return rc;
-    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
-    Device* d = ctx->devs[device_index];
-    std::lock_guard<std::mutex> lock(d->mu);
-    SWB_CUDA(ctx, cudaSetDevice(d->id));
-    rc = sg_ensure_scratch(ctx, d, d->sg_dev, seq_len, n);
-    if (rc != SWB200_OK) return rc;
-    return sg_launch(ctx, d, d->sg_dev, d_seq1, d_seq2, seq_len, n, d_scores, d_end_y, d_end_x, d_n_ops, d_ops, (cudaStream_t)cuda_stream);
-}
-
-int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kernel_info* info)
-{
-    if (!ctx || !info) return SWB200_ERR_ARG;
-    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
-    Device* d = ctx->devs[device_index];
-    SWB_CUDA(ctx, cudaSetDevice(d->id));
-    cudaFuncAttributes fa{};
-    int blocks = 0;
-    SWB_CUDA(ctx, (cudaFuncGetAttributes(&fa, sg2_xdrop_kernel<true, 16>)));       // the large-batch kernel (sg_words_for)
-    SWB_CUDA(ctx, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, sg2_xdrop_kernel<true, 16>, SG2_THREADS, 0)));
-    info->threads_per_block = SG2_THREADS;
-    info->blocks_per_sm = blocks < kSgBlocksPerSm ? blocks : kSgBlocksPerSm;
-    info->fast_path = 0;
-    info->regs_per_thread = fa.numRegs;
-    info->smem_bytes_per_block = (int)fa.sharedSizeBytes;
-    info->sm_count = d->prop.multiProcessorCount;
-    int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->id);
-    info->sm_clock_khz = khz;
-    return SWB200_OK;
-}
+// Semi-global X-drop aligner: the C-ABI entry points (a textual part of this translation unit)
+#include "sg_abi.inc"
 
 uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
