@@ -1,5 +1,6 @@
 """Differential fuzzing of the Smith-Waterman kernel's per-thread code (host emulator, tests/emu/emu_main.cpp) against
-the oracle: random score matrices and gaps over the whole reference domain, low-complexity and repetitive sequences.
+the oracle: random score matrices and gaps over the whole reference domain, low-complexity and repetitive sequences,
+at 128 / 256 / 512 bases, both tuning variants and every FIFO read-ahead distance.
 Development tool:  python tools/sw_fuzz.py [seconds] [processes]"""
 import ctypes as C
 import multiprocessing as mp
@@ -54,14 +55,21 @@ def worker(args):
     t0 = time.time()
     n = 0
     while time.time() - t0 < seconds:
-        a, b, m, gap = make_batch(rng)
+        # every fourth batch at 256 or 512 bases (the length sweep), with the tuning variant and the FIFO read-ahead
+        # distance of the global-memory FIFO kernel drawn at random; the rest at the reference's 128
+        L = int(rng.choice([256, 512])) if n % 4 == 3 else 128
+        a, b, m, gap = make_batch(rng, n=64 if L == 128 else 12, L=L)
+        m = np.clip(m, -127, 32767 // L).astype(np.int8)            # int16 stays exact while L * max(S) <= 32767
         exp = O.score_batch(a, b, m, gap)
+        variant, ahead = (0, 0) if L == 128 and n % 2 == 0 else (int(rng.integers(0, 2)), int(rng.integers(0, 3)))
+        lib.swemu_set_variant(variant)
+        lib.swemu_set_prefetch(ahead)
         for fg in (0, 1):
             out = np.empty(a.shape[0], np.int32)
-            rc = lib.swemu_score_batch_len(128, a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], fg)
+            rc = lib.swemu_score_batch_len(L, a.ctypes.data, b.ctypes.data, m.ctypes.data, gap, out.ctypes.data, a.shape[0], fg)
             if rc < 0 or not np.array_equal(out, exp):
                 np.savez(f"/tmp/swfuzz_{seed}_{n}.npz", a=a, b=b, m=m, gap=gap)
-                return ("MISMATCH", seed, n, rc, fg, m.tolist(), gap)
+                return ("MISMATCH", seed, n, rc, fg, L, variant, ahead, m.tolist(), gap)
         n += 1
     return ("ok", seed, n)
 
