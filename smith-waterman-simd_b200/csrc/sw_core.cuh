@@ -172,6 +172,14 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 //   * substitution words of 4-10 rows of the strip from a lane-replicated shared-memory table
 //     (IMAD address add + LDS on the FMA/LSU pipes instead of PRMT on the ALU pipe): bit-exact,
 //     0.8-3.5 % slower than the all-PRMT kernel in the same block shape.
+//   * n of the 16 rows computing t = max(diag + s'', up) on the FMA pipe as c + relu((a + b) - c) in fp16x2
+//     (HADD2, HFMA2.RELU with a negated operand, HADD2): on bit patterns 0..2047 fp16 is one linear ramp
+//     (subnormals + first binade, value = pattern * 2^-24), so these ARE the integer operations as long as every
+//     value stays below 2048 -- the frame renormalised every 16 steps, both benchmark settings qualify.
+//     Bit-exact on the B200 (reference checksum), SASS as intended (57 - n ALU-pipe, 7 + 3n FMA-pipe
+//     instructions per step, 168 registers), but SLOWER by about 1 % per row (n = 2..12: 1.87 .. 2.07 ms against
+//     1.79): three issue slots for one ALU-pipe slot is a bad trade even with the FMA pipe at 6 %
+//     (profiles/r01/kbench_v6_fp16_rows_on_fma_pipe.jsonl; the patch is kept beside it).
 constexpr int SW_V_BEST_FMA = 1;
 
 template <bool FAST, bool WRAP, int L, int V, class Fifo, class Table>
