@@ -135,6 +135,8 @@ int swb200_score_batch_device(swb200_ctx* ctx, int device_index,
                               const uint8_t* d_seq1, const uint8_t* d_seq2,
                               const int8_t* score_matrix, int8_t gap_penalty,
                               int32_t* d_scores, uint64_t n, void* cuda_stream);
+/* The packed form expands chunk by chunk into the context's own byte staging (stream-ordered with the
+ * other users of that staging: a later host batch or a call on another stream waits for this one). */
 int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index,
                                      const uint8_t* d_seq1_packed, const uint8_t* d_seq2_packed,
                                      const int8_t* score_matrix, int8_t gap_penalty,

@@ -116,6 +116,7 @@ struct Device {
 struct swb200_ctx {
     std::vector<Device*> devs;
     std::string err;
+    std::mutex err_mu;               // per-GPU threads, lanes and submit threads can all fail at once
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};   // host batches: pairs sent 2-bit packed / as bytes
     int force_general = 0;
@@ -132,7 +133,8 @@ int fail(swb200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSucces
     char buf[512];
     if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
     else snprintf(buf, sizeof buf, "%s", what);
-    if (ctx) ctx->err = buf; else g_init_error = buf;
+    if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); ctx->err = buf; }
+    else g_init_error = buf;
     return code;
 }
 
@@ -633,6 +635,7 @@ void swb200_shutdown(swb200_ctx* ctx)
         stop_lanes(d);
         for (Slot& s : d->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.busy && s.done) cudaEventSynchronize(s.done);   // a packed-device call on the caller's stream may still read the staging
             cudaFree(s.d_seq1); cudaFree(s.d_seq2); cudaFree(s.d_pk1); cudaFree(s.d_pk2); cudaFree(s.d_scores);
             if (s.done) cudaEventDestroy(s.done);
             if (s.stream) cudaStreamDestroy(s.stream);
@@ -805,7 +808,10 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const ui
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     // Stream-ordered: unpack a chunk into slot 0's byte staging, score it, next chunk.
+    // The staging is shared with the host-batch pipeline and with calls on other streams, and this call returns
+    // before its kernels have run: whoever uses slot 0 next waits on `done` (run_range does so through `busy`).
     Slot& s = d->slots[0];
+    if (s.busy) SWB_CUDA(ctx, cudaStreamWaitEvent(st, s.done, 0));
     for (uint64_t c0 = 0; c0 < n; c0 += kChunkPairs) {
         const uint64_t m = (n - c0 < kChunkPairs) ? n - c0 : kChunkPairs;
         SWB_CUDA(ctx, launch_unpack(d_pk1 + c0 * 32, s.d_seq1, m, st));
@@ -813,6 +819,8 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const ui
         SWB_CUDA(ctx, launch_for(prm, SWB200_SEQ_LEN, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
         ctx->launches += 3;
     }
+    SWB_CUDA(ctx, cudaEventRecord(s.done, st));
+    s.busy = true;
     return SWB200_OK;
 }
 
