@@ -1,0 +1,57 @@
+"""The bench line's contract (bench.py docstring): the committed round-1 lines under profiles/ carry every
+key the driver and the judge read, with consistent values.  CPU-only: this checks the recorded lines, not the GPU."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R01 = os.path.join(ROOT, "profiles", "r01")
+
+
+def _line(name):
+    with open(os.path.join(R01, name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("name", ["bench_v7_default.json", "bench_v7_n2.json"])
+def test_b200_arm_line_has_the_contract_keys(name):
+    d = _line(name)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert k in d, k
+    assert d["unit"] == "GCUPS" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"] > 0
+    # value is what the timing says: pairs * cells / time
+    cells = d["config"]["pairs_per_gpu"] * d["n_gpus"] * d["config"]["cells_per_pair"]
+    assert d["value"] == pytest.approx(cells / (d["ms_per_step"] * 1e-3) / 1e9, rel=1e-6)
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < d["value"]            # copies inside the timed region: never faster than the resident run
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and 0 < r["frac"] < 1.05
+    assert r["hbm"]["bound"] == "hbm" and r["hbm"]["frac"] < 0.1   # the sequence stream is nowhere near the HBM roofline
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["verified"]["e2e_equals_device"] is True
+    if d["n_gpus"] == 1:
+        c = d["cpu_baseline"]
+        assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == d["unit"] and "sample" in c
+        assert d["verified"]["fnv1a64_ae56a1e6a1d57492_and_sum_75478815"] is True
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    d = _line("bench_v7_reference_arm.json")
+    assert d["impl"] == "reference" and d["unit"] == "GCUPS" and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["value"] == d["value"] and c["cores"] >= 1 and "sample" in c
+
+
+def test_bench_source_emits_what_the_recorded_lines_carry():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for key in ('"roofline"', '"cpu_baseline"', '"e2e"', '"clocks"', '"gpu_launches"', '"h2d_bytes_per_step"',
+                '"d2h_bytes_per_step"', '"traffic"', '"impl": "reference"'):
+        assert key in src, key
