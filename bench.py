@@ -344,6 +344,31 @@ def run_b200_arm(args):
 
     clocks = sampler.summary(t_wall0, t_wall1)
 
+    # ---- the same host call fed with the reference's 2-bit wire format (`unpack`, source.cpp:1580-1583):
+    #      64 B per pair over PCIe instead of 256.  Reported beside `e2e`, never instead of it; one rank only
+    #      (no barrier inside, so a failure here cannot hang or lose the line).
+    e2e_packed = None
+    if world == 1:
+        try:
+            pka, pkb = swb200.PinnedArray((n, 32), np.uint8), swb200.PinnedArray((n, 32), np.uint8)
+            psp = swb200.PinnedArray((n,), np.int32)
+            pka.array[...] = swb200.pack2bit(pa.array)
+            pkb.array[...] = swb200.pack2bit(pb.array)
+            for _ in range(3):
+                ctx.score_batch(pka.array, pkb.array, matrix, gap, out=psp.array, packed=True)
+            torch.cuda.synchronize()
+            tq0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                ctx.score_batch(pka.array, pkb.array, matrix, gap, out=psp.array, packed=True)
+            torch.cuda.synchronize()
+            pk_ms = 1e3 * (time.perf_counter() - tq0) / e2e_steps
+            e2e_packed = {"value": n * CELLS_PER_PAIR / (pk_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": pk_ms,
+                          "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": 4 * n,
+                          "api": "swb200_score_batch_packed (pinned host arrays [n][32], 2 bits per base; expanded on the device)",
+                          "scores_equal_device_leg": bool(np.array_equal(psp.array, scores))}
+        except Exception as ex:   # an extra, never the headline: report and carry on
+            e2e_packed = {"error": f"{type(ex).__name__}: {ex}"}
+
     # ---- roofline of the dominant kernel, from this rank's live CUDA-event launch times
     peaks = load_peaks()
     avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
@@ -395,7 +420,7 @@ def run_b200_arm(args):
                     "host_pack": {"threads_per_gpu": pack1["pack_threads_per_gpu"], "fraction_of_pairs_sent_packed": packed_frac,
                                   "plain_pipeline_ms_per_step": plain_ms,
                                   "note": "rank 0's split; wire compression only, no scoring on the host"},
-                    "scores_equal_device_leg": all_ok},
+                    "scores_equal_device_leg": all_ok, "packed_input": e2e_packed},
             "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,
             "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok},
