@@ -180,7 +180,13 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 //     instructions per step, 168 registers), but SLOWER by about 1 % per row (n = 2..12: 1.87 .. 2.07 ms against
 //     1.79): three issue slots for one ALU-pipe slot is a bad trade even with the FMA pipe at 6 %
 //     (profiles/r01/kbench_v6_fp16_rows_on_fma_pipe.jsonl; the patch is kept beside it).
+//   bit 1 (SW_V_FIFO_PREOFF, fast path only, EXPERIMENTAL -- built by tools/kbench.cu and tests/emu only, not measured
+//          yet): the FIFO holds each value already in the frame it will be popped in, so the pop needs no add.  Column c
+//          is popped at step T = c of its epoch, where Z_{T-1} = g(c+1); a value pushed at step T (frame g(T+2)) for
+//          column T-15 therefore goes in as H~ - 16g, and one pushed inside a wrap iteration at sub-step u < 15
+//          (column L-15+u, popped later in the SAME epoch) as H~ + (L-16)g.  One IMAD less per step.
 constexpr int SW_V_BEST_FMA = 1;
+constexpr int SW_V_FIFO_PREOFF = 2;
 
 template <bool FAST, bool WRAP, int L, int V, class Fifo, class Table>
 SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
@@ -244,7 +250,8 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         // --- row 0's upper neighbours come from the previous strip's bottom row (frame-free in the FIFO)
         const uint32_t popped = Fifo::kPrefetch ? pv[u] : fifo.pop(WRAP ? u : col0 + u);
         st.dg0 = st.up0;
-        st.up0 = FAST ? fadd(popped, st.Zp, prm) : popped;   // plain add: both halves >= 0, no carry across
+        if (FAST && (V & SW_V_FIFO_PREOFF)) st.up0 = popped;   // pushed in this step's frame already
+        else st.up0 = FAST ? fadd(popped, st.Zp, prm) : popped;   // plain add: both halves >= 0, no carry across
         const uint32_t Zm2 = (FAST && WRAP) ? fsub(st.Zp, prm.G, prm) : 0u;   // true zero two steps ago
 
         uint32_t hn[SW_R];
@@ -269,6 +276,13 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         // --- bottom row to the FIFO (column of row 15 at this step), as a true H value.
         //     (a WRAP iteration always starts at column 0; elsewhere col0 >= 16 and nothing wraps,
         //     so every FIFO address is `per-iteration base + compile-time offset`)
+        if (FAST && (V & SW_V_FIFO_PREOFF)) {
+            // hn >= Z_T >= 17g wherever 16g is taken off (T >= 15 there), and hn + (L-16)g stays inside the
+            // int16 bound of sw_make_params (L*smax + (L+2)g): plain 32-bit arithmetic, no carry or borrow across
+            const uint32_t w = (WRAP && u < SW_R - 1) ? fadd(hn[SW_R - 1], prm.G * (uint32_t)(L - 16), prm)
+                                                      : fsub(hn[SW_R - 1], prm.G * 16u, prm);
+            fifo.push(WRAP ? ((u - (SW_R - 1)) & (L - 1)) : (col0 + u - (SW_R - 1)), w);
+        } else
         fifo.push(WRAP ? ((u - (SW_R - 1)) & (L - 1)) : (col0 + u - (SW_R - 1)),
                   FAST ? fsub(hn[SW_R - 1], st.Z, prm) : hn[SW_R - 1]);   // plain subtract: hn >= Z in both halves
         // --- running best
@@ -308,7 +322,11 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
     // Top boundary H[0][*] = 0 (source.cpp:44)
     constexpr int STRIPS = L / SW_R;
     static_assert(L >= 64 && (L & (L - 1)) == 0, "L must be a power of two >= 64");
-    for (int c = 0; c < L; ++c) fifo.push(c, 0u);
+    if (FAST && (V & SW_V_FIFO_PREOFF)) {
+        for (int c = 0; c < L; ++c) fifo.push(c, prm.G * (uint32_t)(c + 1));   // a true zero in the frame of its pop: g(c+1)
+    } else {
+        for (int c = 0; c < L; ++c) fifo.push(c, 0u);
+    }
     if (Fifo::kPrefetch) {
 #pragma unroll
         for (int q = 0; q < (Fifo::kPrefetch == 2 ? 16 : 8); ++q) st.pq[q] = fifo.pop(q);

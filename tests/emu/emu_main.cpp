@@ -72,6 +72,8 @@ static int run_len(const uint8_t* seq1, const uint8_t* seq2, const int8_t* sm, i
         switch (g_variant) {
         case 0: two_pairs<L, 0>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
         case 1: two_pairs<L, 1>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
+        case 2: two_pairs<L, 2>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;   // SW_V_FIFO_PREOFF
+        case 3: two_pairs<L, 3>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
         default: two_pairs<L, 1>(prm.fast, seq1 + p * L, seq2 + p * stride2, dq, dqb, fifo, t4, prm, lo, hi); break;
         }
         scores[p] = lo;

@@ -33,7 +33,7 @@ def emu():
     return run
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])   # bit 0: best on the FMA pipe; bit 1: FIFO pre-offset (experimental)
 def test_emu_structured_all_param_sets(emu, golden, variant):
     z = golden["structured_npz"]
     fast_seen = general_seen = 0
@@ -89,13 +89,15 @@ def _related_pairs(rng, n, L):
     return a, b
 
 
+@pytest.mark.parametrize("variant", [1, 3])
 @pytest.mark.parametrize("prefetch", [0, 1, 2])
 @pytest.mark.parametrize("L", [256, 512])
-def test_emu_length_sweep(emu, oracle, L, prefetch):
+def test_emu_length_sweep(emu, oracle, L, prefetch, variant):
     # BASELINE.json configs[3]: 2x and 4x the built-in shape; oracle = source.cpp:35-60 restated for any length
     rng = np.random.default_rng(L)
     a, b = _related_pairs(rng, 41, L)
     C.CDLL(EMU_LIB).swemu_set_prefetch(prefetch)   # 1 = the read-ahead FIFO path of the global-memory FIFO kernels
+    C.CDLL(EMU_LIB).swemu_set_variant(variant)     # 1 = shipped; 3 = with the FIFO pre-offset (experimental)
 
     def mm(m, x):
         return [m if i == j else x for i in range(4) for j in range(4)]
@@ -109,6 +111,7 @@ def test_emu_length_sweep(emu, oracle, L, prefetch):
     rc, _ = emu(a, b, mm(127, -127), 127, allow_refusal=True)
     assert rc == (-2 if L == 512 else 0)
     C.CDLL(EMU_LIB).swemu_set_prefetch(0)
+    C.CDLL(EMU_LIB).swemu_set_variant(0)
 
 
 def test_emu_prefetching_fifo_at_128(emu, golden):

@@ -63,6 +63,8 @@ int main(int argc, char** argv)
     g_quick = argc > 1;
     run<true, 128, 3>("fast nt128 x3", fast, F, S);
     if (g_quick) { run<false, 128, 3>("general nt128 x3", gen, F, S); return 0; }
+    run<true, 64, 6, SW_V_BEST_FMA | SW_V_FIFO_PREOFF>("fast nt64 x6 V=3 (FIFO pre-offset, experimental)", fast, F, S);
+    run<true, 32, 12, SW_V_BEST_FMA | SW_V_FIFO_PREOFF>("fast nt32 x12 V=3 (FIFO pre-offset, experimental)", fast, F, S);
     run<true, 128, 3, 0>("fast nt128 x3 V=0", fast, F, S);
     run<true, 64, 6, 1>("fast nt64 x6 V=1", fast, F, S);
     run<true, 64, 5, 1>("fast nt64 x5 V=1 (204 regs)", fast, F, S);

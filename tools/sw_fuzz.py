@@ -1,6 +1,6 @@
 """Differential fuzzing of the Smith-Waterman kernel's per-thread code (host emulator, tests/emu/emu_main.cpp) against
 the oracle: random score matrices and gaps over the whole reference domain, low-complexity and repetitive sequences,
-at 128 / 256 / 512 bases, both tuning variants and every FIFO read-ahead distance.
+at 128 / 256 / 512 bases, all four tuning variants (bit 0 best on the FMA pipe, bit 1 FIFO pre-offset) and every FIFO read-ahead distance.
 Development tool:  python tools/sw_fuzz.py [seconds] [processes]"""
 import ctypes as C
 import multiprocessing as mp
@@ -61,7 +61,9 @@ def worker(args):
         a, b, m, gap = make_batch(rng, n=64 if L == 128 else 12, L=L)
         m = np.clip(m, -127, 32767 // L).astype(np.int8)            # int16 stays exact while L * max(S) <= 32767
         exp = O.score_batch(a, b, m, gap)
-        variant, ahead = (0, 0) if L == 128 and n % 2 == 0 else (int(rng.integers(0, 2)), int(rng.integers(0, 3)))
+        variant, ahead = (0, 0) if L == 128 and n % 2 == 0 else (int(rng.integers(0, 4)), int(rng.integers(0, 3)))
+        if os.environ.get("SWFUZZ_VARIANTS"):       # e.g. SWFUZZ_VARIANTS=2,3: a campaign on chosen variant bits only
+            variant = int(rng.choice([int(x) for x in os.environ["SWFUZZ_VARIANTS"].split(",")]))
         lib.swemu_set_variant(variant)
         lib.swemu_set_prefetch(ahead)
         for fg in (0, 1):
