@@ -436,6 +436,17 @@ def run_b200_arm(args):
 
 
 # --------------------------------------------------------------------------- streaming / 100M-pair mode
+def stream_sum_check(pairs: int, score_sum: int):
+    """The sum of all scores of counter-stream pairs [0, pairs) against the committed value computed with the
+    reference (tests/golden/make_counter_sums.py); independent of batch size, wire format and sharding."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "counter_stream_sums.json")) as f:
+            want = json.load(f)["sum_of_scores_over_prefix"]["speedtest_10_-30_15"].get(str(pairs))
+    except (OSError, KeyError, ValueError):
+        return None
+    return None if want is None else bool(int(want) == int(score_sum))
+
+
 def run_stream_arm(args):
     """BASELINE.json configs[2]/[4]: `--workload stream --pairs 100000000` -- the pair-index space
     [0, pairs) is split in contiguous ranges over the ranks (STRONG scaling: total work fixed);
@@ -491,6 +502,8 @@ def run_stream_arm(args):
             "breakdown": {"wall_s": wall, "host_generation_s_max_rank": gen_s, "blocked_on_gpu_pipeline_s_max_rank": wait_s,
                           "bottleneck": "host generation" if gen_s > 0.8 * wall else "PCIe/kernel pipeline"},
             "gpu_launches": int(launches), "score_sum": int(score_sum), "mean_score": score_sum / total,
+            "verified": {"score_sum_equals_reference": stream_sum_check(args.pairs, int(score_sum)),
+                         "golden": "tests/golden/counter_stream_sums.json (sums of the unmodified reference's simd9 scores over prefixes of the counter stream; null = no entry for this --pairs)"},
         }
         print(json.dumps(line), flush=True)
     runner.close()

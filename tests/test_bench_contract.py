@@ -55,3 +55,24 @@ def test_bench_source_emits_what_the_recorded_lines_carry():
     for key in ('"roofline"', '"cpu_baseline"', '"e2e"', '"clocks"', '"gpu_launches"', '"h2d_bytes_per_step"',
                 '"d2h_bytes_per_step"', '"traffic"', '"impl": "reference"'):
         assert key in src, key
+
+
+@pytest.mark.parametrize("name", ["stream_100m_bytes_1gpu.json", "stream_100m_packed_1gpu.json"])
+def test_recorded_100m_pair_streams_equal_the_reference_sum(name):
+    # BASELINE.json configs[2] at full size: the B200 runs recorded in round 1 summed 100 000 000 scores; the same sum
+    # computed later with the unmodified reference (tests/golden/make_counter_sums.py) must be the same number.
+    d = _line(name)
+    with open(os.path.join(ROOT, "tests", "golden", "counter_stream_sums.json")) as f:
+        want = json.load(f)["sum_of_scores_over_prefix"]["speedtest_10_-30_15"]
+    assert d["config"]["pairs"] == 100_000_000
+    assert d["score_sum"] == want["100000000"] == 7_546_733_630
+
+
+def test_stream_sum_check_helper():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.stream_sum_check(100_000_000, 7_546_733_630) is True
+    assert bench.stream_sum_check(100_000_000, 7_546_733_631) is False
+    assert bench.stream_sum_check(123, 1) is None
