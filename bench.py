@@ -301,6 +301,19 @@ def run_b200_arm(args):
     verified = None
     if rank == 0:
         verified = (f"{swb200.fnv1a64(scores):016x}" == "ae56a1e6a1d57492") and int(scores.sum()) == 75_478_815
+    # ranks >= 1 score counter-stream pairs [rank*1M, (rank+1)*1M): their score sum against the value computed with the
+    # unmodified reference (tests/golden/counter_stream_sums.json).  The two reductions run on EVERY rank.
+    block_state = 0.0        # 1.0 = checked and equal, -1.0 = checked and different, 0.0 = no golden entry / rank 0
+    if rank > 0:
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "counter_stream_sums.json")) as f:
+                want = json.load(f)["sum_of_scores_block_1M"]["speedtest_10_-30_15"].get(str(rank))
+            if want is not None and n == 1_000_000:
+                block_state = 1.0 if int(scores.sum(dtype=np.int64)) == int(want) else -1.0
+        except (OSError, KeyError, ValueError):
+            pass
+    blocks_equal = sum_over_ranks(1.0 if block_state > 0 else 0.0, ddist)
+    blocks_differ = sum_over_ranks(1.0 if block_state < 0 else 0.0, ddist)
 
     # ================= leg 2: end to end through the C-ABI host call (pinned host in/out)
     # Host cores per GPU that compress sub-chunks to 2 bits before PCIe (include/swb200.h, "host-side
@@ -423,7 +436,9 @@ def run_b200_arm(args):
                     "scores_equal_device_leg": all_ok, "packed_input": e2e_packed},
             "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,
-            "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok},
+            "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok,
+                         "other_ranks_score_sums_equal_reference": (None if world == 1 else bool(blocks_differ == 0 and blocks_equal > 0)),
+                         "other_ranks_checked": int(blocks_equal + blocks_differ)},
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

@@ -32,6 +32,7 @@ def main():
     a = np.empty((chunk, 128), np.uint8)
     b = np.empty((chunk, 128), np.uint8)
     sums = {k: {} for k in SETTINGS}
+    blocks = {k: {} for k in SETTINGS}      # pairs [r*1M, (r+1)*1M), r = 0..7: what rank r of `bench.py --gpus N` scores (r >= 1)
     run = {k: 0 for k in SETTINGS}
     t0 = time.time()
     for first in range(0, CHECKPOINTS[-1], chunk):
@@ -48,16 +49,18 @@ def main():
                 assert np.array_equal(s[:n], O.ref_score_batch(0, a[:n], b[:n], m, g, threads=threads))
                 assert np.array_equal(s[:n], O.ref_score_batch(4, a[:n], b[:n], m, g, threads=threads))
             run[key] += int(s.sum(dtype=np.int64))
+            if first < 8 * chunk:
+                blocks[key][str(first // chunk)] = int(s.sum(dtype=np.int64))
             if first + chunk in CHECKPOINTS:
                 sums[key][str(first + chunk)] = run[key]
         if (first // chunk) % 10 == 9:
             print(f"{first + chunk} pairs, {time.time() - t0:.0f} s", flush=True)
     out = {"stream": "swb200.counter_pairs(first=0, seed=10000): pair k from splitmix64 of (seed, 8k..8k+7), 32 bases per draw",
            "scored_by": "SmithWaterman_simd9 of the unmodified reference (oracle/_ref), first 200000 pairs also scalar and simd4",
-           "sum_of_scores_over_prefix": sums}
+           "sum_of_scores_over_prefix": sums, "sum_of_scores_block_1M": blocks}
     with open(os.path.join(HERE, "counter_stream_sums.json"), "w") as f:
         json.dump(out, f, indent=1)
-    print(json.dumps(sums))
+    print(json.dumps(sums), json.dumps(blocks))
 
 
 if __name__ == "__main__":

@@ -120,3 +120,22 @@ def test_fixed_111_functions_of_the_reference_equal_the_general_scalar(oracle, s
     for i in range(300):
         assert oracle.ref_111(a[i], b[i]) == exp[i]
         assert oracle.ref_8bit111(a[i], b[i]) == exp[i]
+
+
+def test_counter_stream_golden_sums_against_the_port(oracle):
+    # tests/golden/counter_stream_sums.json was written from the unmodified reference's simd9 (make_counter_sums.py);
+    # the plain-C restatement must reproduce its 1 M-pair block sums (what ranks >= 1 of a multi-GPU bench score).
+    import json
+    import swb200
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "counter_stream_sums.json")) as f:
+        g = json.load(f)
+    want = g["sum_of_scores_block_1M"]
+    a, b = swb200.counter_pairs(3_000_000, 1_000_000)
+    s = oracle.score_batch(a, b, oracle.MATRIX_SPEEDTEST, 15, threads=os.cpu_count() or 1)
+    assert int(s.sum(dtype=np.int64)) == want["speedtest_10_-30_15"]["3"]
+    s = oracle.score_batch(a, b, oracle.MATRIX_111, 1, threads=os.cpu_count() or 1)
+    assert int(s.sum(dtype=np.int64)) == want["x32_1_-1_1"]["3"]
+    pre = g["sum_of_scores_over_prefix"]["speedtest_10_-30_15"]
+    assert pre["1000000"] == want["speedtest_10_-30_15"]["0"]
+    assert pre["2000000"] == want["speedtest_10_-30_15"]["0"] + want["speedtest_10_-30_15"]["1"]
+    assert pre["8000000"] == sum(want["speedtest_10_-30_15"][str(r)] for r in range(8))
