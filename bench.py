@@ -556,6 +556,17 @@ def sg_kernel_shape(n, sm_count):
     return shape
 
 
+def sg_weighted_ops_sum(ops: np.ndarray, n_ops: np.ndarray, rows_per_block: int = 512) -> int:
+    """sum over pairs p and k < n_ops[p] of (k+1) * ops[p][k] -- moves when any op of any alignment moves."""
+    total = 0
+    w = np.arange(1, ops.shape[1] + 1, dtype=np.uint64)
+    for r0 in range(0, ops.shape[0], rows_per_block):
+        blk = ops[r0:r0 + rows_per_block].astype(np.uint64)
+        blk *= (np.arange(ops.shape[1])[None, :] < n_ops[r0:r0 + rows_per_block, None])
+        total += int((blk * w[None, :]).sum(dtype=np.uint64))
+    return total
+
+
 def sg_cpu_reference(a, b, budget_s=20.0):
     """The reference's aligner on all host threads (the fastest of its four AVX2 forms on this box)."""
     from oracle import oracle as O   # allowed: cpu_baseline / --impl reference legs only
@@ -701,6 +712,18 @@ def run_semiglobal_arm(args):
     cpu = None if args.no_cpu_baseline else sg_cpu_reference(pa.array, pb.array, budget_s=20.0)
     if cpu is not None:
         ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
+    # the WHOLE batch against sums computed with the oracle restatement (tests/golden/make_semiglobal_batch_sums.py):
+    # scores, end cells, op counts and a position-weighted sum of every op string.  None = no entry for this batch size.
+    full_ok = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "semiglobal_batch_sums.json")) as f:
+            want = json.load(f)["prefix"].get(str(n))
+        if want is not None:
+            got = {k: int(h_meta[j].array.sum(dtype=np.int64)) for j, k in enumerate(("score", "end_y", "end_x", "n_ops"))}
+            got["ops_weighted"] = sg_weighted_ops_sum(h_ops.array, h_meta[3].array)
+            full_ok = bool(got == {k: int(v) for k, v in want.items()})
+    except Exception as ex:       # a check, not the measurement: report and carry on
+        full_ok = f"{type(ex).__name__}: {ex}"
     peaks = load_peaks()
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     # roofline of the forward kernel (the dominant one): its ALU pipe.  A warp-round advances sixteen pairs by one round;
@@ -737,7 +760,8 @@ def run_semiglobal_arm(args):
                      "traffic": None,
                      "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2, "record_bytes_per_round": SG_RECORD_BYTES_PER_ROUND * 2}},
-        "verified": {"sample_equals_oracle_score_and_traceback": bool(ok), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n)},
+        "verified": {"sample_equals_oracle_score_and_traceback": bool(ok), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n),
+                     "whole_batch_sums_equal_oracle": full_ok},
     }
     if cpu is not None:
         line["cpu_baseline"] = {"value": cpu["alignments_per_s"], "unit": "alignments/s", "cores": cpu["cores"], "kind": "reference", "variant": cpu["variant"],

@@ -76,3 +76,21 @@ def test_stream_sum_check_helper():
     assert bench.stream_sum_check(100_000_000, 7_546_733_630) is True
     assert bench.stream_sum_check(100_000_000, 7_546_733_631) is False
     assert bench.stream_sum_check(123, 1) is None
+
+
+def test_semiglobal_weighted_ops_sum_matches_the_golden_definition():
+    # bench.sg_weighted_ops_sum (vectorised, masks the unused tail of each row) == the per-pair definition used by
+    # tests/golden/make_semiglobal_batch_sums.py
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(3)
+    ops = rng.integers(0, 3, (1030, 96), dtype=np.uint8)
+    n_ops = rng.integers(0, 97, 1030).astype(np.int32)
+    want = sum(int((ops[p, :n_ops[p]].astype(np.uint64) * np.arange(1, n_ops[p] + 1, dtype=np.uint64)).sum()) for p in range(1030))
+    assert bench.sg_weighted_ops_sum(ops, n_ops) == want
+    with open(os.path.join(ROOT, "tests", "golden", "semiglobal_batch_sums.json")) as f:
+        g = json.load(f)["prefix"]
+    assert set(g) == {"2048", "37888"} and g["37888"]["score"] > g["2048"]["score"] > 0
