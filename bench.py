@@ -788,9 +788,12 @@ def run_sweep_arm(args):
     rows = []
     for L in swb200.SWEEP_LENGTHS:
         n = max((1 << 34) // (L * L), 262144)
-        g = torch.Generator(device="cuda").manual_seed(1234 + L)
-        d_a = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
-        d_b = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
+        # the counter stream re-cut to length L (sequence i = rows i*L/128 .. of counter_pairs(0, n*L/128)): reproducible on
+        # the host, so the whole batch has a committed score sum from the oracle (tests/golden/make_sweep_sums.py)
+        h_a, h_b = swb200.counter_pairs(0, n * (L // 128))
+        d_a = torch.from_numpy(h_a.reshape(n, L)).cuda()
+        d_b = torch.from_numpy(h_b.reshape(n, L)).cuda()
+        del h_a, h_b
         d_s = torch.empty(n, dtype=torch.int32, device="cuda")
         for _ in range(max(3, args.warmup)):
             ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
@@ -805,12 +808,22 @@ def run_sweep_arm(args):
         info = ctx.kernel_info(matrix, gap, seq_len=L)
         gcups = n * L * L / (ms * 1e-3) / 1e9
         peak_t = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        score_sum = int(d_s.sum(dtype=torch.int64).item())
+        sum_ok = None
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
+                want = json.load(f)["by_length"].get(str(L))
+            if want is not None and int(want["pairs"]) == n:
+                sum_ok = bool(int(want["sum_of_scores"]) == score_sum)
+        except (OSError, KeyError, ValueError):
+            pass
         rows.append({"seq_len": L, "pairs": n, "ms_per_launch": ms, "gcups": gcups, "alignments_per_s": n / (ms * 1e-3),
-                     "roofline_frac": gcups * 1e9 * ALGO_INSTR_PER_CELL / 1e12 / peak_t, "mean_score": float(d_s.float().mean().item()), "kernel": info})
+                     "roofline_frac": gcups * 1e9 * ALGO_INSTR_PER_CELL / 1e12 / peak_t, "mean_score": score_sum / n,
+                     "score_sum": score_sum, "score_sum_equals_oracle": sum_ok, "kernel": info})
         del d_a, d_b, d_s
     line = {"metric": "GCUPS", "unit": "GCUPS", "value": rows[0]["gcups"], "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": rows[0]["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
-            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), max(2^34 cells, 262144 pairs) per launch, iid pairs, matrix +10/-30, gap 15",
+            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), max(2^34 cells, 262144 pairs) per launch, iid pairs (counter stream re-cut to length L), matrix +10/-30, gap 15",
                        "roofline_peak": f"{peaks['alu_src']}, at sm_max clock"},
             "sweep": rows}
     print(json.dumps(line), flush=True)

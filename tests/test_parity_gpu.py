@@ -335,3 +335,16 @@ def test_random_matrices_and_adversarial_sequences(ctx, oracle):
         else:
             general += 1
     assert fast > 20 and general > 20
+
+
+@pytest.mark.parametrize("L", [128, 256, 512])
+def test_sweep_batch_head_equals_the_golden(ctx, swb, L):
+    # tests/golden/sweep_sums.json (make_sweep_sums.py): the batches of `bench.py --workload sweep` -- the counter stream
+    # re-cut to length L -- scored by the oracle; the bench compares the whole batch's score sum, this test its head.
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sweep_sums.json")) as f:
+        want = json.load(f)["by_length"][str(L)]
+    n = 4096
+    a, b = swb.counter_pairs(0, n * (L // 128))
+    got = ctx.score_batch(a.reshape(n, L), b.reshape(n, L), swb.MATRIX_SPEEDTEST, 15)
+    assert [int(x) for x in got[:8]] == want["first_8_scores"]
