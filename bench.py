@@ -773,6 +773,11 @@ def run_semiglobal_arm(args):
 
 
 # --------------------------------------------------------------------------- length sweep
+def sweep_pairs(L: int) -> int:
+    """Pairs per launch of the length sweep: 2^34 cells, never fewer than 262144 pairs."""
+    return max((1 << 34) // (L * L), 262144)
+
+
 def run_sweep_arm(args):
     """BASELINE.json configs[3]: `--workload sweep` -- square pairs of 128, 256 and 512 bases on one
     GPU, device-resident, 2^34 cells per launch and never fewer than 262144 pairs (the L = 512 kernel keeps
@@ -787,7 +792,7 @@ def run_sweep_arm(args):
     peaks = load_peaks()
     rows = []
     for L in swb200.SWEEP_LENGTHS:
-        n = max((1 << 34) // (L * L), 262144)
+        n = sweep_pairs(L)
         # the counter stream re-cut to length L (sequence i = rows i*L/128 .. of counter_pairs(0, n*L/128)): reproducible on
         # the host, so the whole batch has a committed score sum from the oracle (tests/golden/make_sweep_sums.py)
         h_a, h_b = swb200.counter_pairs(0, n * (L // 128))
