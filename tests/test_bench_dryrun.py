@@ -208,3 +208,56 @@ def test_semiglobal_arm_assembles_its_line(bench, monkeypatch):
     v = line["verified"]
     assert v["sample_equals_oracle_score_and_traceback"] is True and v["e2e_equals_device"] is True
     assert v["whole_batch_sums_equal_oracle"] is None       # 12 pairs: no golden entry
+
+
+def _two_rank_worker(rank, world, port, out_path):
+    """One rank of a 2-process dry run: the same stand-ins as the `bench` fixture, applied by hand (no pytest here),
+    and the process group on gloo instead of nccl."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "smith-waterman-simd_b200"))
+    import swb200
+    from oracle import oracle as O
+    os.environ.update(WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    spec = importlib.util.spec_from_file_location("bench_dry2", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.cuda.is_available = lambda: True
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
+    torch.cuda.Event = _Event
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    real_empty = torch.empty
+    torch.empty = lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"})
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: real_init("gloo", rank=rank, world_size=world)
+    swb200.Context = _fake_context_class(O, swb200)
+    swb200.PinnedArray = _FakePinned
+    swb200.bind_to_gpu_numa_node = lambda *a, **k: None
+    mod.PAIRS_PER_GPU = 1500
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        mod.run_b200_arm(_args())
+    if rank == 0:
+        with open(out_path, "w") as f:
+            f.write(buf.getvalue())
+    else:
+        assert buf.getvalue().strip() == ""          # only rank 0 prints
+
+
+def test_b200_arm_two_ranks_on_gloo(tmp_path, oracle):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out_path = str(tmp_path / "line.json")
+    mp.spawn(_two_rank_worker, args=(2, port, out_path), nprocs=2, join=True)
+    line = json.loads(open(out_path).read().strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["config"]["pairs_per_gpu"] == 1500
+    assert line["value"] == pytest.approx(2 * 1500 * 16384 / (line["ms_per_step"] * 1e-3) / 1e9)
+    assert line["verified"]["e2e_equals_device"] is True
+    assert line["verified"]["other_ranks_checked"] == 0 and line["verified"]["other_ranks_score_sums_equal_reference"] is None   # 1500-pair blocks have no golden
+    assert "cpu_baseline" not in line and line["e2e"]["packed_input"] is None      # both are N = 1 only
