@@ -773,15 +773,20 @@ def run_semiglobal_arm(args):
 
 
 # --------------------------------------------------------------------------- length sweep
-def sweep_pairs(L: int) -> int:
-    """Pairs per launch of the length sweep: 2^34 cells, never fewer than 262144 pairs."""
-    return max((1 << 34) // (L * L), 262144)
+def sweep_pairs(L: int, info: dict) -> int:
+    """Pairs per launch of the length sweep: 2^34 cells, never fewer than 262144 pairs, rounded UP to whole waves of the
+    kernel on this GPU (resident pairs = SMs x blocks per SM x threads x 2).  A pair is one indivisible work item of
+    L^2 cells, so a launch that ends in a partly filled wave times the tail, not the kernel: at L = 512 the plain
+    262144 pairs are 2.31 waves of 113664 and cannot read above 0.89 of the kernel's steady rate."""
+    base = max((1 << 34) // (L * L), 262144)
+    wave = info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] * 2
+    return -(-base // wave) * wave if wave > 0 else base
 
 
 def run_sweep_arm(args):
     """BASELINE.json configs[3]: `--workload sweep` -- square pairs of 128, 256 and 512 bases on one
-    GPU, device-resident, 2^34 cells per launch and never fewer than 262144 pairs (the L = 512 kernel keeps
-    75 776 pairs resident at once; a batch below a few such waves would time latency, not throughput)."""
+    GPU, device-resident, 2^34 cells per launch and never fewer than 262144 pairs, rounded up to whole waves of the
+    kernel (sweep_pairs)."""
     import torch
     import swb200
     if not torch.cuda.is_available():
@@ -792,7 +797,8 @@ def run_sweep_arm(args):
     peaks = load_peaks()
     rows = []
     for L in swb200.SWEEP_LENGTHS:
-        n = sweep_pairs(L)
+        info = ctx.kernel_info(matrix, gap, seq_len=L)
+        n = sweep_pairs(L, info)
         # the counter stream re-cut to length L (sequence i = rows i*L/128 .. of counter_pairs(0, n*L/128)): reproducible on
         # the host, so the whole batch has a committed score sum from the oracle (tests/golden/make_sweep_sums.py)
         h_a, h_b = swb200.counter_pairs(0, n * (L // 128))
@@ -810,16 +816,15 @@ def run_sweep_arm(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
-        info = ctx.kernel_info(matrix, gap, seq_len=L)
         gcups = n * L * L / (ms * 1e-3) / 1e9
         peak_t = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         score_sum = int(d_s.sum(dtype=torch.int64).item())
         sum_ok = None
         try:
             with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
-                want = json.load(f)["by_length"].get(str(L))
-            if want is not None and int(want["pairs"]) == n:
-                sum_ok = bool(int(want["sum_of_scores"]) == score_sum)
+                want = json.load(f)["by_length"][str(L)]["sum_of_scores_by_pairs"].get(str(n))
+            if want is not None:
+                sum_ok = bool(int(want) == score_sum)
         except (OSError, KeyError, ValueError):
             pass
         rows.append({"seq_len": L, "pairs": n, "ms_per_launch": ms, "gcups": gcups, "alignments_per_s": n / (ms * 1e-3),
@@ -828,7 +833,7 @@ def run_sweep_arm(args):
         del d_a, d_b, d_s
     line = {"metric": "GCUPS", "unit": "GCUPS", "value": rows[0]["gcups"], "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": rows[0]["ms_per_launch"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
-            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), max(2^34 cells, 262144 pairs) per launch, iid pairs (counter stream re-cut to length L), matrix +10/-30, gap 15",
+            "config": {"workload": "configs[3]: sequence-length sweep 128/256/512 (templated kernels), max(2^34 cells, 262144 pairs) per launch rounded up to whole waves of resident pairs, iid pairs (counter stream re-cut to length L), matrix +10/-30, gap 15",
                        "roofline_peak": f"{peaks['alu_src']}, at sm_max clock"},
             "sweep": rows}
     print(json.dumps(line), flush=True)

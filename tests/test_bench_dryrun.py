@@ -181,15 +181,16 @@ def _run(fn, args):
 
 
 def test_sweep_arm_assembles_its_line(bench, monkeypatch):
-    monkeypatch.setattr(bench, "sweep_pairs", lambda L: 96)
+    info = {"sm_count": 148, "blocks_per_sm": 6, "threads_per_block": 64}
+    assert [bench.sweep_pairs(L, dict(info, blocks_per_sm=b)) for L, b in ((128, 6), (256, 3), (512, 6))] == [1136640, 284160, 340992]
+    with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
+        g = json.load(f)["by_length"]
+    assert all(str(n) in g[L]["sum_of_scores_by_pairs"] for L, n in (("128", 1136640), ("256", 284160), ("512", 340992)))   # the B200's batches are pinned
+    monkeypatch.setattr(bench, "sweep_pairs", lambda L, info: 96)
     line = _run(bench.run_sweep_arm, _args(workload="sweep"))
     assert [r["seq_len"] for r in line["sweep"]] == [128, 256, 512]
     for r in line["sweep"]:
         assert r["pairs"] == 96 and r["score_sum"] > 0 and r["score_sum_equals_oracle"] is None   # not the golden's batch size
-    # the head of each dry-run batch is the head of the real one: the committed first scores must show up
-    with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
-        g = json.load(f)["by_length"]
-    assert bench.sweep_pairs(128) == 96 and g["128"]["pairs"] == 1048576
 
 
 @pytest.mark.parametrize("packed", [False, True])
