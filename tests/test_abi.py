@@ -137,3 +137,26 @@ def test_host_packer_is_the_inverse_of_the_reference_unpack(swb, oracle):
     assert np.array_equal(swb.pack2bit(dirty.astype(np.uint8)), oracle.pack2bit(codes))
     with pytest.raises(ValueError):
         swb.pack2bit(np.zeros(12, np.uint8))
+
+
+def test_host_packer_alignments_tails_and_the_streaming_store_path(swb):
+    # hostpack.cpp takes non-temporal stores when the destination is 32-byte aligned and the buffer is large, plain
+    # stores otherwise, 128 codes per iteration with a SWAR tail: every combination must give the same bytes and must
+    # not write outside its output.
+    import ctypes as C
+    lib = swb.load_library()
+    rng = np.random.default_rng(12)
+    for n_codes in (8, 120, 128, 136, 65536, 65536 + 8, 65536 + 128 + 40, 1 << 19):
+        src_buf = rng.integers(0, 256, n_codes + 64, dtype=np.uint8)          # any byte: the packer masks to two bits
+        for off_in in (0, 1, 13):
+            for off_out in (0, 1, 32):
+                out_buf = np.full(n_codes // 4 + 128, 0xAA, np.uint8)
+                base = out_buf.ctypes.data
+                j = (-base) % 32 + off_out
+                codes = src_buf[off_in:off_in + n_codes]
+                rc = lib.swb200_pack2bit_host(C.c_void_p(codes.ctypes.data), C.c_void_p(base + j), C.c_uint64(n_codes))
+                assert rc == 0
+                c = (codes & 3).reshape(-1, 4).astype(np.uint8)
+                want = c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)
+                assert np.array_equal(out_buf[j:j + n_codes // 4], want), (n_codes, off_in, off_out)
+                assert (out_buf[:j] == 0xAA).all() and (out_buf[j + n_codes // 4:] == 0xAA).all(), (n_codes, off_in, off_out)
