@@ -18,6 +18,9 @@
 #include "../../include/swb200.h"
 
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <random>
 #include <thread>
 #include <vector>
@@ -38,6 +41,24 @@ inline uint64_t pair_word(uint64_t seed, uint64_t k, unsigned w)
     return splitmix64(k * 8ull + w + seed * 0x9E3779B97F4A7C15ull);
 }
 
+// 64 bits = 32 bases of 2 bits -> 32 byte codes, base i from bits 2i (the reference's `unpack`, source.cpp:1580-1583).
+// The byte-coded stream was bound by this loop (profiles/r01/stream_100m_bytes_1gpu.json: 1.32 of 1.34 s in host
+// generation), so on x86-64 it is done in registers: the four 2-bit planes of the eight source bytes (x, x>>2, x>>4,
+// x>>6) interleaved byte-wise and then word-wise put plane k of byte i at output 4i+k; one mask at the end.
+inline void expand32(uint64_t x, uint8_t* d)
+{
+#if defined(__SSE2__)
+    const __m128i v0 = _mm_cvtsi64_si128((long long)x);
+    const __m128i p01 = _mm_unpacklo_epi8(v0, _mm_srli_epi64(v0, 2));                         // b0>>0, b0>>2, b1>>0, b1>>2, ...
+    const __m128i p23 = _mm_unpacklo_epi8(_mm_srli_epi64(v0, 4), _mm_srli_epi64(v0, 6));      // b0>>4, b0>>6, b1>>4, ...
+    const __m128i m3 = _mm_set1_epi8(3);
+    _mm_storeu_si128((__m128i*)d, _mm_and_si128(_mm_unpacklo_epi16(p01, p23), m3));           // source bytes 0..3 -> codes 0..15
+    _mm_storeu_si128((__m128i*)(d + 16), _mm_and_si128(_mm_unpackhi_epi16(p01, p23), m3));    // source bytes 4..7 -> codes 16..31
+#else
+    for (int i = 0; i < 32; ++i) d[i] = (uint8_t)((x >> (2 * i)) & 3);
+#endif
+}
+
 void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t* seq1, uint8_t* seq2, bool packed)
 {
     for (uint64_t p = lo; p < hi; ++p) {
@@ -48,8 +69,7 @@ void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t*
                 // 32 bases = 8 packed bytes; byte i holds bases 4i..4i+3, base j at bits 2j (source.cpp:1580-1583)
                 std::memcpy(dst + p * 32 + (w & 3) * 8, &x, 8);
             } else {
-                uint8_t* d = dst + p * 128 + (w & 3) * 32;
-                for (int i = 0; i < 32; ++i) d[i] = (uint8_t)((x >> (2 * i)) & 3);
+                expand32(x, dst + p * 128 + (w & 3) * 32);
             }
         }
     }
