@@ -18,8 +18,8 @@
 #include "../../include/swb200.h"
 
 #include <cstring>
-#if defined(__SSE2__)
-#include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
 #endif
 #include <random>
 #include <thread>
@@ -59,8 +59,36 @@ inline void expand32(uint64_t x, uint8_t* d)
 #endif
 }
 
+#if defined(__x86_64__)
+// The packed stream is 64 raw bytes per pair -- its eight splitmix64 draws -- so with AVX-512 (64-bit lane multiply,
+// vpmullq) one vector computes a whole pair: lanes 0..3 are seq1's 32 packed bytes, lanes 4..7 seq2's.  Eight GPUs
+// consume about 3.4 G packed pairs/s; the scalar loop gives 46 M pairs/s per thread.
+__attribute__((target("avx512f,avx512dq")))
+void gen_range_packed_avx512(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t* seq1, uint8_t* seq2)
+{
+    const __m512i lane = _mm512_setr_epi64(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m512i g = _mm512_set1_epi64((long long)0x9E3779B97F4A7C15ull);
+    const __m512i m1 = _mm512_set1_epi64((long long)0xBF58476D1CE4E5B9ull);
+    const __m512i m2 = _mm512_set1_epi64((long long)0x94D049BB133111EBull);
+    const __m512i base = _mm512_add_epi64(lane, _mm512_set1_epi64((long long)(seed * 0x9E3779B97F4A7C15ull)));
+    for (uint64_t p = lo; p < hi; ++p) {
+        __m512i x = _mm512_add_epi64(base, _mm512_set1_epi64((long long)((first + p) * 8ull)));   // pair_word's argument, 8 lanes
+        x = _mm512_add_epi64(x, g);                                                               // splitmix64
+        x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 30)), m1);
+        x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 27)), m2);
+        x = _mm512_xor_si512(x, _mm512_srli_epi64(x, 31));
+        _mm256_storeu_si256((__m256i*)(seq1 + p * 32), _mm512_castsi512_si256(x));
+        _mm256_storeu_si256((__m256i*)(seq2 + p * 32), _mm512_extracti64x4_epi64(x, 1));
+    }
+}
+#endif
+
 void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t* seq1, uint8_t* seq2, bool packed)
 {
+#if defined(__x86_64__)
+    static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
+    if (packed && have_avx512) { gen_range_packed_avx512(seed, first, lo, hi, seq1, seq2); return; }
+#endif
     for (uint64_t p = lo; p < hi; ++p) {
         for (unsigned w = 0; w < 8; ++w) {
             const uint64_t x = pair_word(seed, first + p, w);
