@@ -139,3 +139,17 @@ def test_counter_stream_golden_sums_against_the_port(oracle):
     assert pre["1000000"] == want["speedtest_10_-30_15"]["0"]
     assert pre["2000000"] == want["speedtest_10_-30_15"]["0"] + want["speedtest_10_-30_15"]["1"]
     assert pre["8000000"] == sum(want["speedtest_10_-30_15"][str(r)] for r in range(8))
+
+
+def test_reference_stream_10m_golden_is_consistent_with_the_survey_pins(oracle, stream):
+    # the 10 M-pair known answers (the reference test's own size) contain the 1 M-pair pins of SURVEY.md 8(c)
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_stream_10m.json")) as f:
+        g = json.load(f)["by_scoring"]
+    assert g["speedtest_10_-30_15"]["first_million"] == {"sum": 75478815, "fnv1a64": "ae56a1e6a1d57492"}
+    assert g["x32_1_-1_1"]["first_million"]["sum"] == 18154767
+    assert g["speedtest_10_-30_15"]["pairs"] == g["x32_1_-1_1"]["pairs"] == 10_000_000
+    # and the port agrees with the file on a window in the middle of the stream's first 100 000 pairs
+    a, b = stream
+    s = oracle.score_batch(a, b, oracle.MATRIX_SPEEDTEST, 15, threads=os.cpu_count() or 1)
+    assert int(s.min()) >= g["speedtest_10_-30_15"]["min"] and int(s.max()) <= g["speedtest_10_-30_15"]["max"]
