@@ -25,7 +25,10 @@ static int n_sm;
 static uint64_t splitmix(uint64_t& s) { uint64_t z = (s += 0x9e3779b97f4a7c15ull); z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); }
 
 template <int L>
-static uint64_t n_pairs() { return 262144; }   // 3.5 resident waves of the 8-warp persistent grid at L = 512 (a batch below one wave measures latency, not throughput)
+static uint64_t n_pairs() { return 454656; }   // = 148 SMs x 3072: WHOLE waves of every shape compared here -- 16 of the 3-warp, 8 of the 6-warp, 6 of the
+                                               // 8-warp and 4 of the 12-warp configurations (resident pairs = SMs x warps x 32 x 2).  A pair is one indivisible item, so
+                                               // a partly filled last wave would be charged to the shape, not the batch: the first comparison (262144 pairs,
+                                               // profiles/r01/kbench_len_*.jsonl) gave the shapes 9.2 / 4.6 / 3.5 / 2.3 waves and so under-read the 12-warp one most.
 
 static bool same(uint64_t n)
 {
