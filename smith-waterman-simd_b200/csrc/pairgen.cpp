@@ -18,6 +18,7 @@
 #include "../../include/swb200.h"
 
 #include <cstring>
+#include <exception>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -103,17 +104,33 @@ void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t*
     }
 }
 
+// [0, n) in `threads` contiguous parts, one host thread each.  If a thread cannot be started, the parts that have no
+// thread are done by the caller's: a generator has no reason to fail, and the C ABI lets no exception out.
+template <class Body>
+int run_split(int threads, uint64_t n, Body body)
+{
+    std::vector<std::thread> pool;
+    int started = 0;
+    try {
+        pool.reserve((size_t)threads);
+        for (; started < threads; ++started) {
+            const uint64_t lo = n * (uint64_t)started / threads, hi = n * (uint64_t)(started + 1) / threads;
+            pool.emplace_back([&body, lo, hi] { body(lo, hi); });
+        }
+    } catch (const std::exception&) {
+    }
+    if (started < threads) body(n * (uint64_t)started / threads, n);
+    for (auto& th : pool) th.join();
+    return SWB200_OK;
+}
+
 int gen_counter(uint64_t seed, uint64_t first, uint64_t n, uint8_t* seq1, uint8_t* seq2, int threads, bool packed)
 {
     if (n && (!seq1 || !seq2)) return SWB200_ERR_ARG;
     if (threads < 1) threads = 1;
     if ((uint64_t)threads > n) threads = n ? (int)n : 1;
     if (threads == 1) { gen_range(seed, first, 0, n, seq1, seq2, packed); return SWB200_OK; }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back(gen_range, seed, first, n * (uint64_t)t / threads, n * (uint64_t)(t + 1) / threads, seq1, seq2, packed);
-    for (auto& th : pool) th.join();
-    return SWB200_OK;
+    return run_split(threads, n, [&](uint64_t lo, uint64_t hi) { gen_range(seed, first, lo, hi, seq1, seq2, packed); });
 }
 
 // TestSemiGlobal's construction (source.cpp:2750-2771) with a per-pair splitmix64 stream instead of
@@ -156,12 +173,9 @@ int swb200_gen_related_pairs(uint64_t seed, uint64_t first, uint64_t n, int32_t 
     if (seq_len < 1 || sub_pct < 0 || ins_pct < 0 || del_pct < 0 || sub_pct + ins_pct + del_pct > 100) return SWB200_ERR_ARG;
     if (threads < 1) threads = 1;
     if ((uint64_t)threads > n) threads = n ? (int)n : 1;
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back(gen_related_range, seed, first, n * (uint64_t)t / threads, n * (uint64_t)(t + 1) / threads, (int)seq_len,
-                          sub_pct, ins_pct, del_pct, seq1, seq2);
-    for (auto& th : pool) th.join();
-    return SWB200_OK;
+    return run_split(threads, n, [&](uint64_t lo, uint64_t hi) {
+        gen_related_range(seed, first, lo, hi, (int)seq_len, sub_pct, ins_pct, del_pct, seq1, seq2);
+    });
 }
 
 

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <mutex>
 #include <string>
@@ -483,23 +484,29 @@ void stop_lanes(Device* d)
 int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
 {
     if (!d->lanes.empty()) return SWB200_OK;
-    for (int k = 0; k <= n_pack; ++k) {
-        Lane* ln = new Lane;
-        ln->pack = (k > 0);
-        d->lanes.push_back(ln);
-        const int rc = lane_alloc(ctx, ln);
-        if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
-            stop_lanes(d);
-            d->pool_stop = false;
-            return rc;
+    try {
+        for (int k = 0; k <= n_pack; ++k) {
+            Lane* ln = new Lane;
+            ln->pack = (k > 0);
+            d->lanes.push_back(ln);
+            const int rc = lane_alloc(ctx, ln);
+            if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
+                stop_lanes(d);
+                d->pool_stop = false;
+                return rc;
+            }
         }
+        uint64_t gen;
+        {
+            std::lock_guard<std::mutex> lk(d->pool_mu);
+            gen = d->pool_gen;
+        }
+        for (Lane* ln : d->lanes) ln->th = std::thread(lane_main, ctx, d, ln, gen);
+    } catch (const std::exception& e) {      // a lane or its thread could not be made: take the pool down again (joins what started)
+        stop_lanes(d);
+        d->pool_stop = false;
+        return fail(ctx, SWB200_ERR_NOMEM, e.what());
     }
-    uint64_t gen;
-    {
-        std::lock_guard<std::mutex> lk(d->pool_mu);
-        gen = d->pool_gen;
-    }
-    for (Lane* ln : d->lanes) ln->th = std::thread(lane_main, ctx, d, ln, gen);
     return SWB200_OK;
 }
 
@@ -529,6 +536,28 @@ int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8
 
 // Semi-global X-drop aligner: scratch, launches and the host pipeline (a textual part of this translation unit)
 #include "sg_host.inc"
+
+// One host thread per GPU of the context; body(k) returns that GPU's code.  A thread that cannot be created (or an
+// allocation that fails on the way) becomes SWB200_ERR_NOMEM after the threads that did start have been joined:
+// the C ABI never lets an exception out and never leaves a joinable thread behind.
+template <class Body>
+int run_per_device(swb200_ctx* ctx, size_t G, Body body)
+{
+    std::vector<int> rcs;
+    std::vector<std::thread> pool;
+    int spawn_rc = SWB200_OK;
+    try {
+        rcs.assign(G, SWB200_OK);
+        pool.reserve(G);
+        for (size_t k = 0; k < G; ++k) pool.emplace_back([&rcs, &body, k] { rcs[k] = body(k); });
+    } catch (const std::exception& e) {
+        spawn_rc = fail(ctx, SWB200_ERR_NOMEM, e.what());
+    }
+    for (auto& t : pool) t.join();
+    if (spawn_rc != SWB200_OK) return spawn_rc;
+    for (int r : rcs) if (r != SWB200_OK) return r;
+    return SWB200_OK;
+}
 
 int check_args(swb200_ctx* ctx, const void* a, const void* b, const int8_t* sm, int gap, const void* out, uint64_t n)
 {
@@ -565,15 +594,7 @@ int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool p
     if (G == 1 || n < 2 * G) return range(ctx->devs[0], 0, n);
     // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
     // every GPU DMA-writes its own slice of `scores`: that is the whole gather.
-    std::vector<std::thread> pool;
-    std::vector<int> rcs(G, SWB200_OK);
-    for (size_t k = 0; k < G; ++k) {
-        const uint64_t lo = n * k / G, hi = n * (k + 1) / G;
-        pool.emplace_back([=, &rcs] { rcs[k] = range(ctx->devs[k], lo, hi); });
-    }
-    for (auto& t : pool) t.join();
-    for (int r : rcs) if (r != SWB200_OK) return r;
-    return SWB200_OK;
+    return run_per_device(ctx, G, [&](size_t k) { return range(ctx->devs[k], n * k / G, n * (k + 1) / G); });
 }
 
 } // namespace
@@ -603,20 +624,26 @@ int swb200_init(swb200_ctx** out, const int* devices, int n_devices)
         return fail(nullptr, SWB200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)", e);
     if (n_devices == 0) n_devices = visible;
     if (n_devices > visible) return fail(nullptr, SWB200_ERR_NO_DEVICE, "more devices requested than visible");
-    swb200_ctx* ctx = new swb200_ctx;
-    for (int k = 0; k < n_devices; ++k) {
-        Device* d = new Device;
-        d->id = devices ? devices[k] : k;
-        ctx->devs.push_back(d);
-        int major = 0;
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d->id);
-        int rc = (major == 10) ? setup_device(ctx, d)
-                               : fail(ctx, SWB200_ERR_NO_DEVICE, "device is not compute capability 10.x (kernels are sm_100a only)");
-        if (rc != SWB200_OK) {
-            g_init_error = ctx->err;
-            swb200_shutdown(ctx);
-            return rc;
+    swb200_ctx* ctx = nullptr;
+    try {
+        ctx = new swb200_ctx;
+        for (int k = 0; k < n_devices; ++k) {
+            Device* d = new Device;
+            d->id = devices ? devices[k] : k;
+            ctx->devs.push_back(d);
+            int major = 0;
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d->id);
+            int rc = (major == 10) ? setup_device(ctx, d)
+                                   : fail(ctx, SWB200_ERR_NO_DEVICE, "device is not compute capability 10.x (kernels are sm_100a only)");
+            if (rc != SWB200_OK) {
+                g_init_error = ctx->err;
+                swb200_shutdown(ctx);
+                return rc;
+            }
         }
+    } catch (const std::exception& e) {          // allocation failure: a code, like every other error of this ABI
+        if (ctx) swb200_shutdown(ctx);
+        return fail(nullptr, SWB200_ERR_NOMEM, e.what());
     }
     *out = ctx;
     return SWB200_OK;
@@ -720,12 +747,20 @@ static int submit_impl(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2
     if (rc != SWB200_OK) return rc;
     std::array<int8_t, 16> m;
     memcpy(m.data(), sm, 16);
-    int* result = new int(SWB200_OK);
     std::lock_guard<std::mutex> lock(ctx->tickets_mu);
-    const uint64_t id = ctx->next_ticket++;
-    std::thread th([=] { *result = score_host(ctx, seq1, seq2, packed, m.data(), gap, scores, n); });
-    ctx->tickets.emplace(id, std::make_pair(std::move(th), result));
-    *ticket = id;
+    int* result = nullptr;
+    std::thread th;
+    try {
+        result = new int(SWB200_OK);
+        auto slot = ctx->tickets.emplace(ctx->next_ticket, std::make_pair(std::thread(), result)).first;   // the map node first: it cannot fail later
+        th = std::thread([=] { *result = score_host(ctx, seq1, seq2, packed, m.data(), gap, scores, n); });
+        slot->second.first = std::move(th);
+    } catch (const std::exception& e) {          // no thread, no memory: an error code, and no half-made ticket
+        ctx->tickets.erase(ctx->next_ticket);
+        delete result;
+        return fail(ctx, SWB200_ERR_NOMEM, e.what());
+    }
+    *ticket = ctx->next_ticket++;
     return SWB200_OK;
 }
 
