@@ -6,7 +6,7 @@ counter-based pair stream (swb200.counter_pairs, seed 10000), N up to 100 000 00
 Every score comes from the UNMODIFIED reference's SmithWaterman_simd9 (source.cpp:953-1071) compiled by oracle/Makefile;
 the first 200 000 pairs are also scored by its scalar SmithWaterman (source.cpp:35-60) and simd4 and must agree.
 A sum is independent of how the index range is cut into batches, ranks or GPUs, so it pins the streaming / sharded
-configurations at their full size (bench.py --workload stream, tests/test_streaming_gpu.py)."""
+configurations at their full size (bench.py --workload stream, tests/test_zz_fullsize_pins_gpu.py)."""
 import json
 import os
 import sys
