@@ -701,17 +701,21 @@ def run_semiglobal_arm(args):
     clocks = sampler.summary(t_wall0, t_wall1)
     e2e_ok = bool(np.array_equal(h_meta[0].array, dev_scores) and np.array_equal(h_meta[3].array, dev_nops))
 
-    # parity on a sample, against the oracle restatement (checker only)
-    from oracle import oracle as O
-    O.build()
-    ok = True
-    for i in range(0, n, max(1, n // 24)):
-        s, ey, ex, ops = O.semiglobal_xdrop(pa.array[i], pb.array[i])
-        ok = ok and s == h_meta[0].array[i] and ops.size == h_meta[3].array[i] and np.array_equal(h_ops.array[i, :ops.size], ops)
-
-    cpu = None if args.no_cpu_baseline else sg_cpu_reference(pa.array, pb.array, budget_s=20.0)
-    if cpu is not None:
-        ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
+    # The cpu_baseline leg (the only place this file runs anything under oracle/): the reference's aligner timed on the
+    # host cores, its scores compared with the GPU's, and -- the oracle as checker -- score and traceback of a sample of
+    # pairs.  With --no-cpu-baseline nothing under oracle/ is loaded and the committed whole-batch sums below stand alone.
+    ok = None
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        ok = True
+        for i in range(0, n, max(1, n // 24)):
+            s, ey, ex, ops = O.semiglobal_xdrop(pa.array[i], pb.array[i])
+            ok = ok and s == h_meta[0].array[i] and ops.size == h_meta[3].array[i] and np.array_equal(h_ops.array[i, :ops.size], ops)
+        cpu = sg_cpu_reference(pa.array, pb.array, budget_s=20.0)
+        if cpu is not None:
+            ok = ok and np.array_equal(cpu["scores"], h_meta[0].array[:cpu["sample_pairs"]])
     # the WHOLE batch against sums computed with the oracle restatement (tests/golden/make_semiglobal_batch_sums.py):
     # scores, end cells, op counts and a position-weighted sum of every op string.  None = no entry for this batch size.
     full_ok = None
@@ -760,7 +764,7 @@ def run_semiglobal_arm(args):
                      "traffic": None,
                      "hbm": {"achieved": trace_gbs + n * 2 * SG_LEN / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "algorithmic_bytes_per_round": SG_TRACE_BYTES_PER_ROUND * 2, "record_bytes_per_round": SG_RECORD_BYTES_PER_ROUND * 2}},
-        "verified": {"sample_equals_oracle_score_and_traceback": bool(ok), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n),
+        "verified": {"sample_equals_oracle_score_and_traceback": (None if ok is None else bool(ok)), "e2e_equals_device": e2e_ok, "min_end_rounds": int(rounds // n),
                      "whole_batch_sums_equal_oracle": full_ok},
     }
     if cpu is not None:

@@ -204,7 +204,10 @@ def test_stream_arm_assembles_its_line(bench, packed):
 def test_semiglobal_arm_assembles_its_line(bench, monkeypatch):
     monkeypatch.setattr(bench, "SG_LEN", 512)              # short sequences: the oracle aligns them in milliseconds
     monkeypatch.setattr(bench, "SG_ROUNDS_NOMINAL", 1024)
-    line = _run(bench.run_semiglobal_arm, _args(workload="semiglobal", pairs=12))
+    line = _run(bench.run_semiglobal_arm, _args(workload="semiglobal", pairs=12, no_cpu_baseline=True))
+    assert line["verified"]["sample_equals_oracle_score_and_traceback"] is None and "cpu_baseline" not in line   # nothing under oracle/ ran
+    monkeypatch.setattr(bench, "sg_cpu_reference", lambda a, b, budget_s=20.0: None)      # the reference build aligns 16384-mers only
+    line = _run(bench.run_semiglobal_arm, _args(workload="semiglobal", pairs=12, no_cpu_baseline=False))
     assert line["unit"] == "alignments/s" and line["config"]["pairs"] == 12
     v = line["verified"]
     assert v["sample_equals_oracle_score_and_traceback"] is True and v["e2e_equals_device"] is True
