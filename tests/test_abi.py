@@ -160,3 +160,31 @@ def test_host_packer_alignments_tails_and_the_streaming_store_path(swb):
                 want = c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)
                 assert np.array_equal(out_buf[j:j + n_codes // 4], want), (n_codes, off_in, off_out)
                 assert (out_buf[:j] == 0xAA).all() and (out_buf[j + n_codes // 4:] == 0xAA).all(), (n_codes, off_in, off_out)
+
+
+def test_the_product_never_touches_the_oracle_and_bench_only_in_its_baseline_legs():
+    # The oracle is test infrastructure: nothing under smith-waterman-simd_b200/ or include/ may import, link or load it,
+    # libswb200.so must not depend on it, and bench.py may reach it only inside the cpu_baseline / --impl reference legs.
+    import ast
+    import re
+    import subprocess
+    pkg = os.path.join(ROOT, "smith-waterman-simd_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".inc")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"(import\s+oracle|from\s+oracle|libsworacle|libswref|oracle/)", text), os.path.join(dirpath, f)
+    needed = subprocess.run(["readelf", "-d", os.path.join(pkg, "libswb200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "swref" not in needed
+    # bench.py: every `from oracle import ...` sits in a function of the baseline / reference legs or under `if not args.no_cpu_baseline`
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    allowed_functions = {"cpu_reference_run", "run_cpu_table", "sg_cpu_reference"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and node.module == "oracle":
+                if fn.name in allowed_functions:
+                    continue
+                guarded = any(isinstance(g, ast.If) and "no_cpu_baseline" in ast.unparse(g.test) and node in list(ast.walk(g))
+                              for g in ast.walk(fn))
+                assert guarded, (fn.name, node.lineno)
