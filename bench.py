@@ -128,32 +128,40 @@ def load_peaks() -> dict:
 
 
 # --------------------------------------------------------------------------- reference arm / CPU baseline
+WORKLOAD = ("configs[1]: 1M seeded random 128-mer pairs per GPU (rank 0 = reference stream source.cpp:2944-2953; rank r = counter stream "
+            "pairs [r*1M,(r+1)*1M)), matrix +10/-30, gap 15")
+MATRIX_SPEEDTEST = (10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10, -30, -30, -30, -30, 10)   # source.cpp:3041-3045
+GAP_SPEEDTEST = 15                                                                            # source.cpp:3046
+
+
 def cpu_reference_run(a, b, matrix, gap, steps, warmup, budget_s=150.0):
-    """Times the reference's simd4 (oracle/_ref, the unmodified source) -- or the oracle port
-    when that build is absent -- with all host threads.  Returns (kind, variant, cores, ms_per_step, sample_pairs)."""
+    """Times the reference's own AVX2 path (oracle/_ref, the unmodified source) -- or the oracle port when that build is
+    absent -- with all host threads.  simd4 is the README's reference point, simd9 its fastest variant on most CPUs
+    (README.md:12): BOTH are timed on 200 000 pairs and the faster one runs the measurement, so the baseline is the
+    reference at its best on THIS box.  Returns (kind, variant, cores, ms_per_step, sample_pairs, probe)."""
     from oracle import oracle as O   # allowed here: cpu_baseline / --impl reference legs only
     cores = os.cpu_count() or 1
     n = a.shape[0]
-    probe = min(n, 20_000)
+    probe_n = min(n, 200_000)
+    probe = {}
     if O.have_ref():
-        # the reference's AVX2 path: simd4 is the README's reference point, simd9 its fastest variant on
-        # most CPUs (README.md:12); time both on a probe and run the faster one, so the baseline is the
-        # reference at its best on THIS box
         best = None
         for v, nm in ((4, "SmithWaterman_simd4 (source.cpp:462-571)"), (9, "SmithWaterman_simd9 (source.cpp:953-1071)")):
-            O.ref_score_batch(v, a[:2000], b[:2000], matrix, gap, threads=cores)
-            t = time.perf_counter(); O.ref_score_batch(v, a[:probe], b[:probe], matrix, gap, threads=cores); dtv = time.perf_counter() - t
+            O.ref_score_batch(v, a[:20_000], b[:20_000], matrix, gap, threads=cores)
+            dtv = min(_timed(lambda: O.ref_score_batch(v, a[:probe_n], b[:probe_n], matrix, gap, threads=cores)) for _ in range(2))
+            probe[f"simd{v}_gcups"] = probe_n * CELLS_PER_PAIR / dtv / 1e9
             if best is None or dtv < best[0]:
                 best = (dtv, v, nm)
         dt, vbest, nm = best
-        kind, variant = "reference", nm + ", unmodified, g++ -O3 -mavx2 (faster of simd4/simd9 on this host)"
+        kind, variant = "reference", nm + f", unmodified, g++ -O3 -mavx2 (faster of simd4/simd9 on {probe_n} pairs on this host)"
         run = lambda m: O.ref_score_batch(vbest, a[:m], b[:m], matrix, gap, threads=cores)
     else:
         O.build()
         kind, variant = "port", "oracle/sw_oracle.c scalar restatement of source.cpp:35-60, gcc -O2"
         run = lambda m: O.score_batch(a[:m], b[:m], matrix, gap, threads=cores)
-        t = time.perf_counter(); run(probe); dt = time.perf_counter() - t
-    per_pair = dt / probe
+        probe_n = min(n, 20_000)
+        dt = _timed(lambda: run(probe_n))
+    per_pair = dt / probe_n
     # a step is the whole batch unless the whole run would blow the budget
     sample = n
     total = (steps + warmup) * n * per_pair
@@ -161,10 +169,14 @@ def cpu_reference_run(a, b, matrix, gap, steps, warmup, budget_s=150.0):
         sample = max(1000, int(n * budget_s / total))
     for _ in range(warmup):
         run(sample)
-    times = []
-    for _ in range(steps):
-        t = time.perf_counter(); run(sample); times.append(time.perf_counter() - t)
-    return kind, variant, cores, 1e3 * sum(times) / len(times), sample
+    times = [_timed(lambda: run(sample)) for _ in range(steps)]
+    return kind, variant, cores, 1e3 * sum(times) / len(times), sample, probe
+
+
+def _timed(fn) -> float:
+    t = time.perf_counter()
+    fn()
+    return time.perf_counter() - t
 
 
 def cpu_model() -> str:
@@ -183,47 +195,48 @@ def run_cpu_table(args):
     (scalar on a 50 000-pair sample), one thread and all host cores, both harness matrices.
     `python bench.py --impl reference --cpu-table` -> one JSON line per row."""
     from oracle import oracle as O
-    import swb200
     if not O.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libswref.so not built (no /root/reference here and no prebuilt file)"}))
         return
     cores = os.cpu_count() or 1
-    a, b = swb200.reference_stream(PAIRS_PER_GPU)
+    a, b = O.reference_stream(PAIRS_PER_GPU)
     names = {0: "scalar SmithWaterman (source.cpp:35-60)", 4: "SmithWaterman_simd4 (462-571)", 7: "SmithWaterman_simd7 (758-850)", 9: "SmithWaterman_simd9 (953-1071)"}
-    for label, matrix, gap in (("+10/-30 gap 15 (SpeedTest, source.cpp:3041-3046)", swb200.MATRIX_SPEEDTEST, 15),
-                               ("+1/-1 gap 1 (speedtest111x32, source.cpp:3202-3207)", swb200.MATRIX_111, 1)):
+    m111 = (1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1, -1, -1, -1, -1, 1)
+    for label, matrix, gap in (("+10/-30 gap 15 (SpeedTest, source.cpp:3041-3046)", MATRIX_SPEEDTEST, 15),
+                               ("+1/-1 gap 1 (speedtest111x32, source.cpp:3202-3207)", m111, 1)):
         for variant in (0, 4, 7, 9):
             for threads in (1, cores):
                 m = (50_000 if variant == 0 else 250_000) * (1 if threads == 1 else min(4, cores))
                 m = min(m, PAIRS_PER_GPU)
                 O.ref_score_batch(variant, a[:2000], b[:2000], matrix, gap, threads=threads)
-                t = time.perf_counter()
-                O.ref_score_batch(variant, a[:m], b[:m], matrix, gap, threads=threads)
-                dt = time.perf_counter() - t
+                dt = _timed(lambda: O.ref_score_batch(variant, a[:m], b[:m], matrix, gap, threads=threads))
                 print(json.dumps({"impl": "reference", "kernel": names[variant], "scoring": label, "threads": threads, "host_cores": cores,
                                   "cpu_model": cpu_model(), "sample_pairs": m, "ms_per_1M_pairs": dt / m * 1e9, "gcups": m * CELLS_PER_PAIR / dt / 1e9,
                                   "alignments_per_s": m / dt, "build": "g++ -std=c++17 -O3 -mavx2, unmodified source"}), flush=True)
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation on the box's host cores.  Nothing of the product is loaded in this process:
+    the inputs come from the oracle's restatement of the reference's generator (source.cpp:2944-2953), the scores from
+    oracle/_ref (the unmodified source.cpp)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if args.cpu_table:
         return run_cpu_table(args)
-    import swb200
-    # inputs come from the product's generator (a .so load, no GPU needed); scoring is all reference
-    a, b = swb200.reference_stream(PAIRS_PER_GPU)
-    kind, variant, cores, ms, sample = cpu_reference_run(a, b, swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST, args.steps, args.warmup)
+    from oracle import oracle as O
+    O.build()
+    a, b = O.reference_stream(PAIRS_PER_GPU)
+    kind, variant, cores, ms, sample, probe = cpu_reference_run(a, b, MATRIX_SPEEDTEST, GAP_SPEEDTEST, args.steps, args.warmup)
     gcups = sample * CELLS_PER_PAIR / (ms * 1e-3) / 1e9
     line = {
         "impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "alignments_per_s": sample / (ms * 1e-3),
-        "config": {"workload": "1M seeded random 128-mer pairs (reference stream, source.cpp:2944-2953), matrix +10/-30, gap 15",
-                   "pairs_per_step": sample, "cells_per_pair": CELLS_PER_PAIR, "cpu_model": cpu_model()},
-        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "variant": variant,
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "pairs_per_step": sample, "cells_per_pair": CELLS_PER_PAIR, "cpu_model": cpu_model(),
+                   "note": "the CPU arm scores rank 0's batch (the reference stream) whatever --gpus says; it has no GPUs to scale over"},
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "variant": variant, "probe_200k": probe,
                          "sample": f"{sample} of 1000000 pairs per step, {args.steps} steps, {cores} threads over contiguous index ranges"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -231,32 +244,329 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- B200 arm: the legs
+class Ranks:
+    """The ranks of this run: NCCL for the device-side barrier and the reductions of timing scalars (no data-path
+    collective), and a gloo group for the legs in which ranks must wait WITHOUT touching their GPU."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(self.world)))
+        self.dist = None
+        self.cpu_group = None
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+            try:
+                self.cpu_group = dist.new_group(backend="gloo")
+            except Exception as ex:   # the NCCL group still gives a (GPU-polling) barrier
+                log(f"bench.py: no gloo group ({ex}); CPU waits fall back to the NCCL barrier")
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        """Ranks meet without any GPU work (a blocked socket read), so a rank that is still measuring is not disturbed."""
+        if self.dist is None:
+            return
+        if self.cpu_group is not None:
+            self.dist.barrier(group=self.cpu_group)
+        else:
+            self.dist.barrier()
+
+    def max(self, v):
+        from sharding import max_over_ranks
+        return max_over_ranks(v, self.dist)
+
+    def sum(self, v):
+        from sharding import sum_over_ranks
+        return sum_over_ranks(v, self.dist)
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_host_calls(R: "Ranks", fn, steps: int, warmup: int = 3):
+    """ms per call of a blocking host call, max over ranks, every rank between the same two barriers."""
+    for _ in range(warmup):
+        fn()
+    R.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    R.barrier()
+    return R.max(1e3 * (time.perf_counter() - t0) / steps)
+
+
+def leg_host_ceiling(R: "Ranks", swb200, pa, cpus: int) -> dict:
+    """What the HOST can deliver, all ranks at once: (a) pinned H2D copies alone, (b) the cores' streaming reads alone,
+    (c) both together.  A byte-coded batch has to leave host DRAM once -- read by a core that packs it or by the DMA
+    engine -- so (c) / 256 B is the roofline of the end-to-end number for byte-coded input and (a) / 64 B that of the
+    2-bit wire format.  Aggregates are sums over ranks of bytes / the slowest rank's time."""
+    torch = R.torch
+    src = torch.from_numpy(pa.array)           # pinned (cudaHostAlloc): the copy below is a plain DMA
+    dst = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
+    nbytes = src.numel()
+    stream = torch.cuda.current_stream()
+
+    def dma(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+    dma(2)
+    R.barrier()
+    reps = 8
+    t = R.max(dma(reps))
+    h2d = R.sum(nbytes * reps) / t / 1e9
+    swb200.host_read_bandwidth(pa.array, cpus, 1)
+    R.barrier()
+    passes = 6
+    t0 = time.perf_counter()
+    swb200.host_read_bandwidth(pa.array, cpus, passes)
+    t = R.max(time.perf_counter() - t0)
+    cpu_read = R.sum(nbytes * passes) / t / 1e9
+    # both at once: the DMA loop runs on a second thread until the cores have finished their passes
+    stop = threading.Event()
+    copied = [0]
+
+    def dma_loop():
+        torch.cuda.set_device(R.local_rank)
+        s2 = torch.cuda.Stream()
+        with torch.cuda.stream(s2):
+            while not stop.is_set():
+                dst.copy_(src, non_blocking=True)
+                s2.synchronize()
+                copied[0] += nbytes
+    R.barrier()
+    th = threading.Thread(target=dma_loop)
+    t0 = time.perf_counter()
+    th.start()
+    swb200.host_read_bandwidth(pa.array, max(1, cpus - 1), passes)
+    dt = time.perf_counter() - t0
+    stop.set()
+    th.join()
+    both = R.sum(nbytes * passes + copied[0]) / R.max(dt) / 1e9
+    both_dma = R.sum(copied[0]) / R.max(dt) / 1e9
+    del dst
+    return {"h2d_pinned_gbs": h2d, "host_read_gbs": cpu_read, "h2d_and_read_together_gbs": both, "h2d_share_of_together_gbs": both_dma,
+            "threads_per_rank": cpus, "buffer_mb_per_rank": nbytes / 1e6,
+            "how": "all ranks at once between barriers; sum of bytes over ranks / slowest rank's time: torch pinned->device copies (CUDA events), "
+                   "swb200_host_read_bandwidth (AVX2 streaming reads, all of the rank's cores), then both concurrently"}
+
+
+def ceiling_gcups(bytes_per_s_g: float, bytes_per_pair: float) -> float:
+    return bytes_per_s_g * 1e9 / bytes_per_pair * CELLS_PER_PAIR / 1e9
+
+
+def leg_stream(R: "Ranks", swb200, ctx, pairs: int, packed: bool, gen_threads: int, matrix, gap) -> dict:
+    """BASELINE.json configs[2] + configs[4]: the index space [0, pairs) of the counter stream split in contiguous ranges
+    over the ranks (shard_range); every rank generates its pairs on host threads into pinned ring buffers and streams
+    them through swb200_submit[_packed].  End-to-end alignments/s = pairs / the slowest rank's wall time."""
+    from sharding import shard_range
+    from streaming import StreamRunner
+    lo, hi = shard_range(pairs, R.rank, R.world)
+    batch = 1 << 21
+    runner = StreamRunner(ctx, batch_pairs=batch, n_buffers=3, packed=packed, gen_threads=gen_threads)
+    runner.run(lo, min(hi - lo, 2 * batch), matrix, gap)          # warm-up: first touch of the pinned ring, staging allocation
+    R.barrier()
+    launches0 = ctx.launch_count
+    rep = runner.run(lo, hi - lo, matrix, gap)
+    R.torch.cuda.synchronize()
+    wall = R.max(rep.wall_s)
+    total = R.sum(rep.pairs)
+    score_sum = int(R.sum(rep.score_sum))
+    gen_s = R.max(rep.produce_s)
+    wait_s = R.max(rep.wait_s)
+    launches = R.sum(ctx.launch_count - launches0)
+    h2d, d2h = R.sum(rep.bytes_h2d), R.sum(rep.bytes_d2h)
+    runner.close()
+    if gen_s > 0.8 * wall:
+        bottleneck = "host generation (the producer threads were busy for > 80 % of the wall time)"
+    elif wait_s > 0.5 * wall:
+        bottleneck = "PCIe / kernel pipeline (the driver thread was blocked on in-flight batches for > 50 % of the wall time)"
+    else:
+        bottleneck = "mixed: host generation and the GPU pipeline alternate"
+    return {"alignments_per_s": total / wall, "gcups": total * CELLS_PER_PAIR / wall / 1e9, "wall_s": wall, "pairs": int(total),
+            "wire_format": "2-bit packed (source.cpp:1580-1583), 64 B/pair" if packed else "byte codes, 256 B/pair",
+            "batch_pairs": batch, "gen_threads_per_rank": gen_threads, "h2d_bytes": int(h2d), "d2h_bytes": int(d2h), "gpu_launches": int(launches),
+            "breakdown": {"host_generation_s_max_rank": gen_s, "blocked_on_gpu_pipeline_s_max_rank": wait_s, "bottleneck": bottleneck},
+            "score_sum": score_sum, "score_sum_equals_reference": stream_sum_check(pairs, score_sum)}
+
+
+def leg_inproc(R: "Ranks", swb200, n_per_gpu: int, matrix, gap, steps: int, restore_affinity) -> dict:
+    """The library's OWN sharding layer (north_star (c)): rank 0 alone opens one context on all N GPUs and pushes N x 1M
+    pairs through ONE swb200_score_batch call (contiguous index ranges, one host thread per GPU, host gather by direct
+    stores), byte-coded and 2-bit packed.  The other ranks wait on a CPU barrier; their GPUs are idle."""
+    out = None
+    if R.rank == 0:
+        try:
+            before = sorted(os.sched_getaffinity(0))
+            if restore_affinity:
+                os.sched_setaffinity(0, restore_affinity)     # this leg owns the whole box
+            G = R.world
+            n = G * n_per_gpu
+            ctxN = swb200.Context(devices=list(range(G)))
+            pa, pb = swb200.PinnedArray((n, 128), np.uint8), swb200.PinnedArray((n, 128), np.uint8)
+            ka, kb = swb200.PinnedArray((n, 32), np.uint8), swb200.PinnedArray((n, 32), np.uint8)
+            ps = swb200.PinnedArray((n,), np.int32)
+            swb200.counter_pairs(0, n, out=(pa.array, pb.array))
+            swb200.counter_pairs(0, n, packed=True, out=(ka.array, kb.array))
+            want = counter_prefix_sum(n)
+            res = {}
+            for name, (x, y, packed) in (("bytes", (pa, pb, False)), ("packed", (ka, kb, True))):
+                for _ in range(3):
+                    ctxN.score_batch(x.array, y.array, matrix, gap, out=ps.array, packed=packed)
+                l0 = ctxN.launch_count
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    ctxN.score_batch(x.array, y.array, matrix, gap, out=ps.array, packed=packed)
+                ms = 1e3 * (time.perf_counter() - t0) / steps
+                ssum = int(ps.array.sum(dtype=np.int64))
+                res[name] = {"value": n * CELLS_PER_PAIR / (ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms, "alignments_per_s": n / (ms * 1e-3),
+                             "h2d_bytes_per_step": 2 * n * (32 if packed else 128), "d2h_bytes_per_step": 4 * n,
+                             "gpu_launches_per_step": (ctxN.launch_count - l0) / steps,
+                             "score_sum_equals_reference": (None if want is None else bool(ssum == want))}
+            res["bytes"]["host_pack"] = ctxN.host_pack_stats()
+            out = {"api": f"ONE swb200_score_batch[_packed] call per step on a context of {G} GPUs, {n} pairs in pinned host arrays, scores gathered into one pinned host array",
+                   "n_gpus": G, "pairs_per_step": n, "steps": steps, "process": "rank 0 alone; the other ranks wait on a gloo barrier with idle GPUs", **res}
+            ctxN.close()
+            for p in (pa, pb, ka, kb, ps):
+                p.free()
+            os.sched_setaffinity(0, before)
+        except Exception as ex:   # an extra leg: report and carry on, and never leave the other ranks at the barrier
+            out = {"error": f"{type(ex).__name__}: {ex}"}
+    R.cpu_barrier()
+    return out
+
+
+def counter_prefix_sum(n: int):
+    """Sum of the reference's scores over counter-stream pairs [0, n) at +10/-30/15, from the committed golden file."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "counter_stream_sums.json")) as f:
+            g = json.load(f)
+        v = g["sum_of_scores_over_prefix"]["speedtest_10_-30_15"].get(str(n))
+        if v is None and n % 1_000_000 == 0:
+            blocks = g["sum_of_scores_block_1M"]["speedtest_10_-30_15"]
+            if all(str(k) in blocks for k in range(n // 1_000_000)):
+                v = sum(int(blocks[str(k)]) for k in range(n // 1_000_000))
+        return None if v is None else int(v)
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
+    """The reference's literal metric shape (SpeedTest, source.cpp:3036-3054): ONE fixed pair scored again and again,
+    "ms / 1M".  Here: microseconds per swb200_score_pair call on the first pair of the reference stream, timed around a
+    loop of direct C-ABI calls (ctypes overhead included)."""
+    import ctypes as C
+    lib, h = ctx._lib, ctx._h
+    m = np.asarray(matrix, dtype=np.int8)
+    s1, s2 = np.ascontiguousarray(a[0]), np.ascontiguousarray(b[0])
+    out = np.zeros(1, np.int32)
+    fn = lib.swb200_score_pair
+    args = (h, s1.ctypes.data, s2.ctypes.data, m.ctypes.data, C.c_int8(int(gap)), out.ctypes.data)
+    for _ in range(200):
+        fn(*args)
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        fn(*args)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    for _ in range(calls):
+        pass
+    loop_overhead = time.perf_counter() - t1
+    return {"us_per_call": 1e6 * dt / calls, "ms_per_1M_calls": 1e3 * dt / calls * 1e6, "calls": calls, "score": int(out[0]), "score_expected": 80,
+            "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
+            "api": "swb200_score_pair: the pair rides in the launch parameters of a one-warp-per-pair kernel; the result is a tagged word in mapped pinned memory the call spins on",
+            "shape": "SpeedTest (source.cpp:3036-3054): one fixed pair, repeated calls"}
+
+
+def leg_sweep(R: "Ranks", swb200, ctx, matrix, gap, steps: int, peak_tinstr: float) -> list:
+    """BASELINE.json configs[3], in the default line: L = 128 / 256 / 512 on whole-wave batches of the counter stream
+    re-cut to length L, device-resident, each with the oracle's committed score sum."""
+    torch = R.torch
+    rows = []
+    for L in swb200.SWEEP_LENGTHS:
+        info = ctx.kernel_info(matrix, gap, seq_len=L)
+        n = sweep_pairs(L, info)
+        h_a, h_b = swb200.counter_pairs(0, n * (L // 128))
+        d_a = torch.from_numpy(h_a.reshape(n, L)).cuda()
+        d_b = torch.from_numpy(h_b.reshape(n, L)).cuda()
+        del h_a, h_b
+        d_s = torch.empty(n, dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        gcups = n * L * L / (ms * 1e-3) / 1e9
+        score_sum = int(d_s.sum(dtype=torch.int64).item())
+        sum_ok = None
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
+                want = json.load(f)["by_length"][str(L)]["sum_of_scores_by_pairs"].get(str(n))
+            if want is not None:
+                sum_ok = bool(int(want) == score_sum)
+        except (OSError, KeyError, ValueError):
+            pass
+        rows.append({"seq_len": L, "pairs": n, "waves": n / max(1, info["sm_count"] * info["blocks_per_sm"] * info["threads_per_block"] * 2),
+                     "ms_per_launch": ms, "gcups": gcups, "alignments_per_s": n / (ms * 1e-3),
+                     "roofline_frac": gcups * 1e9 * ALGO_INSTR_PER_CELL / 1e12 / peak_tinstr, "vs_L128": None,
+                     "score_sum": score_sum, "score_sum_equals_oracle": sum_ok,
+                     "kernel": {k: info[k] for k in ("regs_per_thread", "threads_per_block", "blocks_per_sm", "smem_bytes_per_block")}})
+        del d_a, d_b, d_s
+    for r in rows:
+        r["vs_L128"] = r["gcups"] / rows[0]["gcups"]
+    return rows
+
+
+SASS_ALU_PER_STEP = 57.3          # ALU-pipe instructions per anti-diagonal step (16 words) of the shipped L = 128 kernel,
+SASS_CELLS_RATIO = 16640 / 16384  # counted from the built library by tools/sass_hist.py (profiles/r02/sass_hot_loops.json); steps x 16 / real cells
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
     import swb200
-    from sharding import max_over_ranks, sum_over_ranks
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ddist = dist if world > 1 else None
-
+    R = Ranks()
+    torch = R.torch
+    world, rank, local_rank = R.world, R.rank, R.local_rank
     matrix, gap = swb200.MATRIX_SPEEDTEST, swb200.GAP_SPEEDTEST
-    # multi-rank: run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off
-    numa = swb200.bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    # several ranks on one box: each gets its own share of the cores (the library sizes its PACK-lane pool from the CPUs the
+    # process may run on), on the NUMA node its GPU hangs off; pinned buffers are first-touched after this
+    cpu_share = swb200.bind_rank_cpus(local_rank, R.local_world) if world > 1 else {"before": sorted(os.sched_getaffinity(0)), "numa": None,
+                                                                                     "cpus": len(os.sched_getaffinity(0)), "share": None}
+    my_cpus = cpu_share["cpus"]
     ctx = swb200.Context(devices=[local_rank])
+    if args.pack_threads is not None:
+        ctx.set_host_pack_threads(args.pack_threads)
     info = ctx.kernel_info(matrix, gap)
     n = PAIRS_PER_GPU
 
-    # ---- this rank's batch, in PINNED host memory (the e2e leg copies from here every step)
+    # ---- this rank's batch, in PINNED host memory (the e2e legs copy from here every step)
     pa, pb = swb200.PinnedArray((n, 128), np.uint8), swb200.PinnedArray((n, 128), np.uint8)
     ps = swb200.PinnedArray((n,), np.int32)
     if rank == 0:
@@ -269,18 +579,12 @@ def run_b200_arm(args):
     d_s = torch.empty(n, dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ================= leg 1: device-resident (value, roofline)
     for _ in range(args.warmup):
         ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
+    R.barrier()
     launches0 = ctx.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.perf_counter()
@@ -288,14 +592,19 @@ def run_b200_arm(args):
     for i in range(args.steps):
         ctx.score_batch_device(d_a, d_b, matrix, gap, d_s)   # 256 MB of sequence data per launch: larger than the 126 MB L2
         ev[i + 1].record(stream)
-    barrier()
+    R.barrier()
     t_wall1 = time.perf_counter()
     launches_dev = ctx.launch_count - launches0
     ms_total = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    ms_step = max_over_ranks(ms_total / args.steps, ddist)
-    total_pairs = sum_over_ranks(n, ddist)
+    ms_step = R.max(ms_total / args.steps)
+    total_pairs = R.sum(n)
     gcups = total_pairs * CELLS_PER_PAIR / (ms_step * 1e-3) / 1e9
+    # the roofline's denominator, measured on this GPU right after the timed launches (clocks are still up)
+    try:
+        peak_live = ctx.measure_alu_peak(target_ms=50.0)
+    except Exception as ex:
+        peak_live = {"error": f"{type(ex).__name__}: {ex}"}
 
     scores = d_s.cpu().numpy()
     verified = None
@@ -312,108 +621,140 @@ def run_b200_arm(args):
                 block_state = 1.0 if int(scores.sum(dtype=np.int64)) == int(want) else -1.0
         except (OSError, KeyError, ValueError):
             pass
-    blocks_equal = sum_over_ranks(1.0 if block_state > 0 else 0.0, ddist)
-    blocks_differ = sum_over_ranks(1.0 if block_state < 0 else 0.0, ddist)
+    blocks_equal = R.sum(1.0 if block_state > 0 else 0.0)
+    blocks_differ = R.sum(1.0 if block_state < 0 else 0.0)
 
-    # ================= leg 2: end to end through the C-ABI host call (pinned host in/out)
-    # Host cores per GPU that compress sub-chunks to 2 bits before PCIe (include/swb200.h, "host-side
-    # 2-bit packing lanes").  One rank: the library's own default.  Several ranks share the box's cores.
-    if args.pack_threads is not None:
-        ctx.set_host_pack_threads(args.pack_threads)
-    elif world > 1:
-        ctx.set_host_pack_threads(max(0, (os.cpu_count() or 1) // world - 2))
+    # ================= leg 2: end to end through the C-ABI host call, byte-coded input (the reference's own layout)
+    def e2e_bytes():
+        ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)   # H2D + kernel + scores back; returns when they are on the host
     plain_ms = None
     if world == 1 and not args.no_plain_e2e:
         # the same call with the packing lanes off (every byte crosses PCIe), for the record
-        keep = ctx.host_pack_stats()["pack_threads_per_gpu"]
         ctx.set_host_pack_threads(0)
-        for _ in range(2):
-            ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
-        tp0 = time.perf_counter()
-        for _ in range(5):
-            ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
-        plain_ms = 1e3 * (time.perf_counter() - tp0) / 5
+        plain_ms = timed_host_calls(R, e2e_bytes, 5, warmup=2)
         ctx.set_host_pack_threads(args.pack_threads if args.pack_threads is not None else -1)
-        assert ctx.host_pack_stats()["pack_threads_per_gpu"] == keep
-    for _ in range(max(min(args.warmup, 3), 3)):
-        ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)
-    barrier()
+    e2e_bytes()
     pack0 = ctx.host_pack_stats()
     launches1 = ctx.launch_count
-    e2e_steps = args.steps
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.score_batch(pa.array, pb.array, matrix, gap, out=ps.array)   # H2D + kernels + D2H, returns when scores are on the host
-    barrier()
-    t1 = time.perf_counter()
-    sampler.stop()
-    launches_e2e = ctx.launch_count - launches1
+    e2e_ms = timed_host_calls(R, e2e_bytes, args.steps, warmup=3)
+    launches_e2e = (ctx.launch_count - launches1) - 3
     pack1 = ctx.host_pack_stats()
-    packed_frac = (pack1["packed_pairs"] - pack0["packed_pairs"]) / float(n * e2e_steps)
-    e2e_ms = max_over_ranks(1e3 * (t1 - t0) / e2e_steps, ddist)
+    packed_frac = (pack1["packed_pairs"] - pack0["packed_pairs"]) / float(n * (args.steps + 3))
     e2e_gcups = total_pairs * CELLS_PER_PAIR / (e2e_ms * 1e-3) / 1e9
     e2e_ok = bool(np.array_equal(ps.array, scores))
-    all_ok = sum_over_ranks(1.0 if e2e_ok else 0.0, ddist) == world
+    all_ok = R.sum(1.0 if e2e_ok else 0.0) == world
 
+    # ================= leg 3: the same call fed with the reference's 2-bit wire format (source.cpp:1580-1583), at EVERY N
+    pka, pkb = swb200.PinnedArray((n, 32), np.uint8), swb200.PinnedArray((n, 32), np.uint8)
+    psp = swb200.PinnedArray((n,), np.int32)
+    pka.array[...] = swb200.pack2bit(pa.array)
+    pkb.array[...] = swb200.pack2bit(pb.array)
+
+    def e2e_pk():
+        ctx.score_batch(pka.array, pkb.array, matrix, gap, out=psp.array, packed=True)
+    launches2 = ctx.launch_count
+    pk_ms = timed_host_calls(R, e2e_pk, args.steps, warmup=3)
+    launches_pk = (ctx.launch_count - launches2) / float(args.steps + 3)
+    pk_ok = R.sum(1.0 if np.array_equal(psp.array, scores) else 0.0) == world
     clocks = sampler.summary(t_wall0, t_wall1)
+    sampler.stop()
+    e2e_packed = {"value": total_pairs * CELLS_PER_PAIR / (pk_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": pk_ms,
+                  "alignments_per_s": total_pairs / (pk_ms * 1e-3), "fraction_of_device_resident_rate": ms_step / pk_ms,
+                  "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": 4 * n, "gpu_launches_per_step": launches_pk,
+                  "api": "swb200_score_batch_packed (pinned host arrays [n][32], 2 bits per base; one persistent kernel consumes the tiles as the copy engine lands them)",
+                  "scores_equal_device_leg": bool(pk_ok)}
 
-    # ---- the same host call fed with the reference's 2-bit wire format (`unpack`, source.cpp:1580-1583):
-    #      64 B per pair over PCIe instead of 256.  Reported beside `e2e`, never instead of it; one rank only
-    #      (no barrier inside, so a failure here cannot hang or lose the line).
-    e2e_packed = None
-    if world == 1:
+    # ================= leg 4: what the host can deliver (the roofline of the two numbers above)
+    host_ceiling = None
+    if not args.quick:
         try:
-            pka, pkb = swb200.PinnedArray((n, 32), np.uint8), swb200.PinnedArray((n, 32), np.uint8)
-            psp = swb200.PinnedArray((n,), np.int32)
-            pka.array[...] = swb200.pack2bit(pa.array)
-            pkb.array[...] = swb200.pack2bit(pb.array)
-            for _ in range(3):
-                ctx.score_batch(pka.array, pkb.array, matrix, gap, out=psp.array, packed=True)
-            torch.cuda.synchronize()
-            tq0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                ctx.score_batch(pka.array, pkb.array, matrix, gap, out=psp.array, packed=True)
-            torch.cuda.synchronize()
-            pk_ms = 1e3 * (time.perf_counter() - tq0) / e2e_steps
-            e2e_packed = {"value": n * CELLS_PER_PAIR / (pk_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": pk_ms,
-                          "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": 4 * n,
-                          "api": "swb200_score_batch_packed (pinned host arrays [n][32], 2 bits per base; expanded on the device)",
-                          "scores_equal_device_leg": bool(np.array_equal(psp.array, scores))}
-        except Exception as ex:   # an extra, never the headline: report and carry on
-            e2e_packed = {"error": f"{type(ex).__name__}: {ex}"}
+            host_ceiling = leg_host_ceiling(R, swb200, pa, my_cpus)
+            host_ceiling["byte_input_ceiling_gcups"] = ceiling_gcups(host_ceiling["h2d_and_read_together_gbs"], 256.0)
+            host_ceiling["byte_input_e2e_fraction_of_ceiling"] = e2e_gcups / host_ceiling["byte_input_ceiling_gcups"]
+            host_ceiling["packed_input_pcie_ceiling_gcups"] = ceiling_gcups(host_ceiling["h2d_pinned_gbs"], 64.0)
+            host_ceiling["packed_input_bound"] = ("kernel" if host_ceiling["packed_input_pcie_ceiling_gcups"] > gcups else "host -> device link (PCIe / host DRAM)")
+        except Exception as ex:
+            host_ceiling = {"error": f"{type(ex).__name__}: {ex}"}
+            R.barrier()
+
+    # ================= leg 5: configs[2] / configs[4] -- 100 M pairs sharded by index range, streamed from host generators
+    stream_legs = None
+    if not args.quick:
+        stream_legs = {}
+        gen_threads = max(1, my_cpus - 1)
+        for name, packed in (("packed", True), ("bytes", False)):
+            try:
+                stream_legs[name] = leg_stream(R, swb200, ctx, args.stream_pairs, packed, gen_threads, matrix, gap)
+            except Exception as ex:
+                stream_legs[name] = {"error": f"{type(ex).__name__}: {ex}"}
+                R.barrier()
+
+    # ================= leg 6: the library's own multi-GPU sharding layer, in ONE process (N > 1)
+    inproc = None
+    if world > 1 and not args.quick:
+        inproc = leg_inproc(R, swb200, n, matrix, gap, steps=min(args.steps, 10), restore_affinity=cpu_share["before"])
+
+    # ================= N = 1 only: length sweep, per-pair call, CPU baseline
+    sweep = per_pair = None
+    peak_t = peak_live.get("tinstr_per_s") if isinstance(peak_live, dict) else None
+    if world == 1 and not args.quick:
+        try:
+            sweep = leg_sweep(R, swb200, ctx, matrix, gap, steps=max(5, args.steps // 2), peak_tinstr=peak_t or 18.46)
+        except Exception as ex:
+            sweep = {"error": f"{type(ex).__name__}: {ex}"}
+        try:
+            per_pair = leg_per_pair(swb200, ctx, pa.array, pb.array, matrix, gap)
+        except Exception as ex:
+            per_pair = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---- roofline of the dominant kernel, from this rank's live CUDA-event launch times
     peaks = load_peaks()
     avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    alu_peak_tinstr = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * sm_mhz * 1e6 / 1e12
+    alu_peak_file = peaks["alu_lanes_per_clk_per_sm"] * info["sm_count"] * sm_mhz * 1e6 / 1e12
+    alu_peak_tinstr = peak_t if peak_t else alu_peak_file
     achieved_tinstr = n * CELLS_PER_PAIR * ALGO_INSTR_PER_CELL / (avg_launch_ms * 1e-3) / 1e12
+    executed_alu_tinstr = n * CELLS_PER_PAIR * SASS_CELLS_RATIO * (SASS_ALU_PER_STEP / 16.0) / (avg_launch_ms * 1e-3) / 1e12
     hbm_achieved = n * ALGO_BYTES_PER_PAIR / (avg_launch_ms * 1e-3) / 1e9
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "NCU_SUMMARY.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
     roofline = {
         "bound": "int_alu", "kernel": "swb::sw_kernel<FAST=%d, L=128, NT=%d, MINB=%d>" % (info["fast_path"], info["threads_per_block"], info["blocks_per_sm"]),
         "achieved": achieved_tinstr, "peak": alu_peak_tinstr, "unit": "Tinstr/s (thread-level packed int16x2 ALU instructions)",
         "frac": achieved_tinstr / alu_peak_tinstr,
-        "algorithmic_instr_per_cell": ALGO_INSTR_PER_CELL, "cells_per_launch": n * CELLS_PER_PAIR,
-        "avg_launch_ms": avg_launch_ms, "peak_src": f"{peaks['alu_src']}: {peaks['alu_lanes_per_clk_per_sm']} lanes/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz (median SM clock sampled during the run)",
-        "traffic": None,
+        "algorithmic_instr_per_cell": ALGO_INSTR_PER_CELL, "cells_per_launch": n * CELLS_PER_PAIR, "avg_launch_ms": avg_launch_ms,
+        "peak_live": peak_live,
+        "peak_src": ("measured live in this run by swb200_measure_alu_peak (independent VIADDMNMX.S16x2 chains on every SM, CUDA events)" if peak_t else
+                     f"{peaks['alu_src']}: {peaks['alu_lanes_per_clk_per_sm']} lanes/clk/SM x {info['sm_count']} SMs x {sm_mhz:.0f} MHz"),
+        "peak_from_file": {"tinstr_per_s": alu_peak_file, "src": f"{peaks['alu_src']} x {info['sm_count']} SMs x {sm_mhz:.0f} MHz (median SM clock sampled during the run)"},
+        "alu_pipe_busy": {"model": executed_alu_tinstr / alu_peak_tinstr,
+                          "how": f"ALU-pipe instructions the kernel EXECUTES ({SASS_ALU_PER_STEP} per 16-word step by SASS count = {SASS_ALU_PER_STEP / 16:.2f} per computed cell, "
+                                 f"{SASS_CELLS_RATIO:.4f} computed cells per real cell) / launch time / live peak",
+                          "ncu_pct": ncu.get("alu_pipe_pct"), "ncu_src": ncu.get("source")},
+        "traffic": ncu.get("dram_bytes_per_launch"),
         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
                 "algorithmic_bytes_per_pair": ALGO_BYTES_PER_PAIR, "peak_src": peaks["hbm_src"],
                 "note": "evidence that the sequence stream is not limiting (SURVEY.md 8d)"},
     }
-    try:
-        with open(os.path.join(ROOT, "profiles", "NCU_SUMMARY.json")) as f:
-            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        kind, variant, cores, ms, sample = cpu_reference_run(pa.array, pb.array, matrix, gap, steps=3, warmup=1, budget_s=40.0)
+        kind, variant, cores, ms, sample, probe = cpu_reference_run(pa.array, pb.array, matrix, gap, steps=3, warmup=1, budget_s=40.0)
         cpu_baseline = {"value": sample * CELLS_PER_PAIR / (ms * 1e-3) / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
-                        "variant": variant, "cpu_model": cpu_model(),
+                        "variant": variant, "cpu_model": cpu_model(), "probe_200k": probe,
                         "sample": f"{sample} of 1000000 pairs per pass, 3 timed passes, {cores} threads over contiguous index ranges",
                         "ms_per_1M_pairs": ms * 1e6 / sample}
+        if per_pair and "us_per_call" in per_pair:
+            try:
+                from oracle import oracle as O
+                per_pair["reference_simd4_us_per_call"] = O.ref_score_repeat(4, pa.array[0], pb.array[0], matrix, gap, 200_000) * 1e6
+            except Exception as ex:
+                per_pair["reference_simd4_us_per_call"] = f"{type(ex).__name__}: {ex}"
 
     if rank == 0:
         line = {
@@ -421,22 +762,29 @@ def run_b200_arm(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16x2", "data": "synthetic",
             "alignments_per_s": total_pairs / (ms_step * 1e-3),
-            "config": {"workload": "configs[1]: 1M seeded random 128-mer pairs per GPU (rank 0 = reference stream source.cpp:2944-2953; rank r = counter stream pairs [r*1M,(r+1)*1M)), matrix +10/-30, gap 15",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_gpu": n, "cells_per_pair": CELLS_PER_PAIR, "sharding": "contiguous index ranges, no collective",
-                       "l2": "inputs 256 MB per launch > 126 MB L2, no flush needed", "numa": numa,
-                       "kernel": info},
+                       "l2": "inputs 256 MB per launch > 126 MB L2, no flush needed", "host_cpus": os.cpu_count(),
+                       "cpus_of_this_rank": {k: cpu_share[k] for k in ("cpus", "share", "numa")}, "kernel": info},
             "clocks": clocks,
             "e2e": {"value": e2e_gcups, "unit": "GCUPS", "ms_per_step": e2e_ms, "alignments_per_s": total_pairs / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": int(round(2 * n * (128 * (1.0 - packed_frac) + 32 * packed_frac))), "d2h_bytes_per_step": 4 * n,
-                    "host_input_bytes_per_step": 2 * n * 128,
-                    "api": "swb200_score_batch (C ABI, pinned host byte arrays [n][128] in, int32 scores out; RAW lane + host 2-bit packing lanes, H2D/kernel/D2H overlapped)",
+                    "host_input_bytes_per_step": 2 * n * 128, "gpu_launches_per_step": launches_e2e / float(args.steps),
+                    "api": "swb200_score_batch (C ABI, pinned host byte arrays [n][128] in, int32 scores out): one persistent kernel per call; the calling thread DMA-copies "
+                           "raw pieces while PACK lanes compress others to 2 bits on host cores; scores are stored straight into the caller's pinned array",
                     "host_pack": {"threads_per_gpu": pack1["pack_threads_per_gpu"], "fraction_of_pairs_sent_packed": packed_frac,
                                   "plain_pipeline_ms_per_step": plain_ms,
                                   "note": "rank 0's split; wire compression only, no scoring on the host"},
+                    "bound": "host memory: every byte of the 256 B/pair input is read from host DRAM once (by a packing core or the DMA engine); see host_ceiling",
                     "scores_equal_device_leg": all_ok, "packed_input": e2e_packed},
+            "host_ceiling": host_ceiling,
+            "stream": (None if stream_legs is None else dict(stream_legs, pairs=args.stream_pairs,
+                       workload=f"configs[2]/[4]: {args.stream_pairs} counter-stream pairs sharded by contiguous index range over {world} rank(s); host threads -> pinned ring -> swb200_submit[_packed]")),
+            "e2e_inproc": inproc,
+            "sweep": sweep, "per_pair": per_pair,
             "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,
-            "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok,
+            "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok, "e2e_packed_equals_device": bool(pk_ok),
                          "other_ranks_score_sums_equal_reference": (None if blocks_equal + blocks_differ == 0 else bool(blocks_differ == 0)),
                          "other_ranks_checked": int(blocks_equal + blocks_differ)},
         }
@@ -445,9 +793,7 @@ def run_b200_arm(args):
         print(json.dumps(line), flush=True)
 
     ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.close()
 
 
 # --------------------------------------------------------------------------- streaming / 100M-pair mode
@@ -938,6 +1284,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
     ap.add_argument("--packed", action="store_true", help="stream the 2-bit packed wire format (64 B/pair)")
+    ap.add_argument("--quick", action="store_true", help="batch1m: only the device-resident and the two end-to-end legs (no host ceiling, stream, in-process, sweep, per-pair)")
+    ap.add_argument("--stream-pairs", type=int, default=100_000_000, help="batch1m: pairs of the sharded streaming leg (configs[2]/[4])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("bench.py: warmup raised to 3 (timing rules)")

@@ -77,7 +77,9 @@ int swb200_free_pinned(void* ptr);
  *   int SmithWaterman_simdN(const std::array<uint8_t,128>& seq1, const std::array<uint8_t,128>& seq2,
  *                           const std::array<int8_t,16>& score_matrix, const int8_t gap_penalty)
  * (source.cpp:462-466; identical signatures at 35-39, 62, 210, 341, 573, 666, 758, 852, 953).
- * The score is written to *score. */
+ * The score is written to *score.  The pair travels inside the launch parameters of a
+ * one-warp-per-pair kernel and the result comes back through a mapped word the call spins on:
+ * no copy, no stream synchronisation (the shape SpeedTest times, source.cpp:3036-3054). */
 int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
                       const int8_t* score_matrix, int8_t gap_penalty, int32_t* score);
 
@@ -86,8 +88,10 @@ int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
  * The batched-call precedent in the reference is SmithWaterman_8b111x32mark1
  * (source.cpp:1227-1234: 32 row-major 128-mers in, results into a `dest` array).
  * HOST arrays: seq1[n][128], seq2[n][128], scores[n].  Pairs are split in contiguous
- * index ranges over the context's GPUs; each GPU streams its range in chunks
- * (H2D, kernel, D2H overlapped) and writes its slice of `scores` directly. */
+ * index ranges over the context's GPUs.  Per GPU one persistent kernel consumes the range
+ * while its input is still crossing PCIe (tile flags written by the copy engine) and stores
+ * the scores straight into `scores` when that is pinned memory (swb200_alloc_pinned);
+ * up to 2048 pairs take a one-warp-per-pair latency kernel instead (as swb200_score_pair). */
 int swb200_score_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
                        const int8_t* score_matrix, int8_t gap_penalty,
                        int32_t* scores, uint64_t n);
@@ -203,10 +207,11 @@ int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const
  * swb200_score_batch therefore runs, per GPU, one RAW lane (the caller's bytes, 256 B per pair)
  * and `threads_per_gpu` PACK lanes (a host core compresses a sub-chunk to the reference's
  * 2-bit layout, source.cpp:1580-1583, into pinned staging; 64 B per pair cross the link and
- * the device expands them).  All lanes draw sub-chunks of 16384 pairs from one counter, so
+ * the device expands them).  All lanes draw pieces of 8192 pairs from one counter, so
  * the split adapts to the machine.  This is wire compression only: no score is ever computed
- * on the host.  threads_per_gpu: -1 = auto (CPUs this process may run on, minus two, per GPU;
- * env SWB200_PACK_THREADS overrides), 0 = off (every pair travels as bytes). */
+ * on the host.  threads_per_gpu: -1 = auto ((CPUs this process may run on - GPUs) / GPUs: the calling
+ * thread of every GPU is its RAW lane; env SWB200_PACK_THREADS overrides), 0 = off (every pair
+ * travels as bytes). */
 int swb200_set_host_pack_threads(swb200_ctx* ctx, int threads_per_gpu);
 /* Pairs sent packed / as bytes by host batches so far, and the lane count in effect. */
 int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64_t* raw_pairs, int* threads_per_gpu);
@@ -214,11 +219,20 @@ int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64
  * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);
 
+/* The integer-ALU issue peak of GPU `device_index`, measured now: independent chains of VIADDMNMX.S16x2 (the hot
+ * loop's own instruction) on every SM for about target_ms milliseconds; *tinstr_per_s = thread-level instructions per
+ * second / 1e12.  This is the roofline denominator SURVEY.md 8(d) asks to be measured on the box. */
+int swb200_measure_alu_peak(swb200_ctx* ctx, int device_index, double target_ms, double* tinstr_per_s, double* elapsed_ms);
+
 /* Resources of the semi-global aligner's kernel (fast_path is 0 there). */
 int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kernel_info* info);
 
 /* Kernel launches issued by this context since creation (all GPUs). */
 uint64_t swb200_launch_count(const swb200_ctx* ctx);
+
+/* Test hook: 0 sends small host batches (<= 2048 pairs) through the throughput kernel's chunk pipeline instead of
+ * the one-warp-per-pair latency kernel; 1 (default) restores the latter. */
+int swb200_set_latency_path(swb200_ctx* ctx, int on);
 
 /* Test hook: 1 forces the general (non-offset) kernel even where the fast one is exact. */
 int swb200_set_force_general(swb200_ctx* ctx, int on);
@@ -241,6 +255,11 @@ int swb200_gen_counter_pairs_packed(uint64_t seed, uint64_t first, uint64_t n,
  * counter-based like the stream above.  Host arrays [n][seq_len]. */
 int swb200_gen_related_pairs(uint64_t seed, uint64_t first, uint64_t n, int32_t seq_len, int sub_pct, int ins_pct, int del_pct,
                              uint8_t* seq1, uint8_t* seq2, int threads);
+
+/* Benchmark helper (bench.py `host_ceiling`): `threads` host threads stream-read contiguous shares of
+ * [buf, buf+bytes) `passes` times; *bytes_per_s = bytes * passes / wall time.  A byte-coded host batch must be read
+ * from host memory once, by a packing core or by the DMA engine: this is that roofline's CPU side. */
+int swb200_host_read_bandwidth(const void* buf, uint64_t bytes, int threads, int passes, double* bytes_per_s);
 
 /* FNV-1a-64 over int32 scores: h = 1469598103934665603; h = (h ^ (uint32)s) * 1099511628211. */
 uint64_t swb200_fnv1a64_i32(const int32_t* scores, uint64_t n);

@@ -125,6 +125,20 @@ def score_batch(seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap: int, thre
     return out
 
 
+def ref_score_repeat(variant: int, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap: int, calls: int) -> float:
+    """The reference's own way of timing (SpeedTest, source.cpp:3047-3055): ONE pair scored `calls` times by variant
+    0 = scalar, 1..9 = simd..simd9.  Returns seconds per call."""
+    import time
+    a = np.ascontiguousarray(seq1, dtype=np.uint8).reshape(128)
+    b = np.ascontiguousarray(seq2, dtype=np.uint8).reshape(128)
+    m = _mat(score_matrix)
+    lib = ref()
+    lib.swref_score_repeat(variant, _p(a, _u8p), _p(b, _u8p), _p(m, _i8p), int(gap), 1000)
+    t = time.perf_counter()
+    lib.swref_score_repeat(variant, _p(a, _u8p), _p(b, _u8p), _p(m, _i8p), int(gap), int(calls))
+    return (time.perf_counter() - t) / calls
+
+
 def ref_score_batch(variant: int, seq1: np.ndarray, seq2: np.ndarray, score_matrix, gap: int, threads: int = 1) -> np.ndarray:
     """The reference itself. variant 0 = scalar, 1..9 = SmithWaterman_simd..simd9. L must be 128."""
     seq1 = np.ascontiguousarray(seq1, dtype=np.uint8)

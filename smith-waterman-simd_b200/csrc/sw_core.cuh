@@ -137,11 +137,14 @@ SWB_HD uint32_t code_x4(uint32_t w, int idx)
     return (idx == 0) ? ((w << 2) & 0xcu) : ((w >> (8 * idx - 2)) & 0xcu);
 }
 
-// 8 bytes from a byte pointer that is 8-byte aligned
+// 8 bytes from a byte pointer that is 8-byte aligned.  COHERENT = false: the read-only path (ld.global.nc), for
+// arrays nobody writes while the kernel runs.  COHERENT = true: a plain load -- the persistent consumer kernel
+// (sw_feed_kernel.cuh) reads sequences that its own block expanded from the 2-bit wire format a moment ago.
+template <bool COHERENT = false>
 SWB_HD void ld8(const uint8_t* p, uint32_t& w0, uint32_t& w1)
 {
 #if defined(__CUDA_ARCH__)
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const uint2 v = COHERENT ? *reinterpret_cast<const uint2*>(p) : __ldg(reinterpret_cast<const uint2*>(p));
     w0 = v.x; w1 = v.y;
 #else
     w0 = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -149,10 +152,11 @@ SWB_HD void ld8(const uint8_t* p, uint32_t& w0, uint32_t& w1)
 #endif
 }
 
+template <bool COHERENT = false>
 SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 {
-    ld8(p, w[0], w[1]);
-    ld8(p + 8, w[2], w[3]);
+    ld8<COHERENT>(p, w[0], w[1]);
+    ld8<COHERENT>(p + 8, w[2], w[3]);
 }
 
 // One 16-step iteration.  WRAP = this iteration starts at a step that is a multiple of 128:
@@ -185,8 +189,11 @@ SWB_HD void ld16(const uint8_t* p, uint32_t (&w)[4])
 //          is popped at step T = c of its epoch, where Z_{T-1} = g(c+1); a value pushed at step T (frame g(T+2)) for
 //          column T-15 therefore goes in as H~ - 16g, and one pushed inside a wrap iteration at sub-step u < 15
 //          (column L-15+u, popped later in the SAME epoch) as H~ + (L-16)g.  One IMAD less per step.
+//   bit 2 (SW_V_COHERENT_LD): sequence loads are plain (coherent) loads instead of ld.global.nc -- no change to
+//          the arithmetic; used by the persistent consumer kernel, whose blocks write the bytes they then read.
 constexpr int SW_V_BEST_FMA = 1;
 constexpr int SW_V_FIFO_PREOFF = 2;
+constexpr int SW_V_COHERENT_LD = 4;
 
 template <bool FAST, bool WRAP, int L, int V, class Fifo, class Table>
 SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& prm, int col0,
@@ -197,8 +204,8 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
     bw_lo[0] = st.bq_lo[0]; bw_lo[1] = st.bq_lo[1]; bw_hi[0] = st.bq_hi[0]; bw_hi[1] = st.bq_hi[1];
     {
         const uint8_t* p = b_lo + (WRAP ? 0 : col0) + 8;
-        ld8(p, bw_lo[2], bw_lo[3]);
-        ld8(p + dq, bw_hi[2], bw_hi[3]);
+        ld8<(V & SW_V_COHERENT_LD) != 0>(p, bw_lo[2], bw_lo[3]);
+        ld8<(V & SW_V_COHERENT_LD) != 0>(p + dq, bw_hi[2], bw_hi[3]);
     }
     // A FIFO with long latency (global memory) is read ahead of use, like the bases.
     //   kPrefetch 1: 8..15 steps ahead -- words 8..15 of this iteration here, words 0..7 of the next at u = 8;
@@ -222,8 +229,8 @@ SWB_HD void sw_iter16(SwState& st, Fifo& fifo, const Table& t4, const SwParams& 
         if (u == 8) {
             const int nc = ((WRAP ? 0 : col0) + 16) & (L - 1);
             const uint8_t* p = b_lo + nc;
-            ld8(p, st.bq_lo[0], st.bq_lo[1]);
-            ld8(p + dq, st.bq_hi[0], st.bq_hi[1]);
+            ld8<(V & SW_V_COHERENT_LD) != 0>(p, st.bq_lo[0], st.bq_lo[1]);
+            ld8<(V & SW_V_COHERENT_LD) != 0>(p + dq, st.bq_hi[0], st.bq_hi[1]);
             if (Fifo::kPrefetch == 1) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) st.pq[q] = fifo.pop(nc + q);
@@ -338,9 +345,9 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
     st.dg0 = 0u;
 
     uint32_t an_lo[4], an_hi[4];
-    ld8(b_lo, st.bq_lo[0], st.bq_lo[1]);
-    ld8(b_lo + dqb, st.bq_hi[0], st.bq_hi[1]);
-    ld16(a_lo, an_lo); ld16(a_lo + dqa, an_hi);
+    ld8<(V & SW_V_COHERENT_LD) != 0>(b_lo, st.bq_lo[0], st.bq_lo[1]);
+    ld8<(V & SW_V_COHERENT_LD) != 0>(b_lo + dqb, st.bq_hi[0], st.bq_hi[1]);
+    ld16<(V & SW_V_COHERENT_LD) != 0>(a_lo, an_lo); ld16<(V & SW_V_COHERENT_LD) != 0>(a_lo + dqa, an_hi);
 
     for (int strip = 0; strip <= STRIPS; ++strip) {
         if (FAST && strip > 0) {
@@ -357,7 +364,7 @@ SWB_HD void sw_two_pairs(const uint8_t* a_lo, const uint8_t* b_lo, uint32_t dqa,
         for (int j = 1; j < L / 16; ++j) {
             if (j == L / 16 - 1) {   // one iteration ahead of the wrap that consumes them
                 const int ns = (strip + 1 < STRIPS) ? strip + 1 : STRIPS - 1;
-                ld16(a_lo + 16 * ns, an_lo); ld16(a_lo + 16 * ns + dqa, an_hi);
+                ld16<(V & SW_V_COHERENT_LD) != 0>(a_lo + 16 * ns, an_lo); ld16<(V & SW_V_COHERENT_LD) != 0>(a_lo + 16 * ns + dqa, an_hi);
             }
             sw_iter16<FAST, false, L, V>(st, fifo, t4, prm, 16 * j, b_lo, dqb, an_lo, an_hi, false);
         }

@@ -1,0 +1,162 @@
+// sw_feed_kernel.cuh -- the persistent CONSUMER kernel of the host batch packer.
+//
+// One launch scores one "epoch" of a host batch (up to the staging capacity of a region,
+// feed.inc) while its input is still crossing PCIe.  The grid is the resident block count of
+// the scoring kernel (SMs x 6 blocks of 64 threads); a block repeatedly
+//   1. claims the next work item (128 consecutive pairs) from a counter,
+//   2. waits until the 4096-pair tile holding the item has LANDED: the host enqueues, behind
+//      every input copy and on the same stream, a 4-byte copy that writes the tile's flag, so
+//      the copy engine itself publishes "tile t is in HBM, in format f" in stream order;
+//   3. if the tile arrived in the reference's 2-bit packing (source.cpp:1580-1583) expands
+//      its own 128 pairs into the byte staging (8 KiB in, 32 KiB out, L2-resident);
+//   4. scores them with the same per-thread code as sw_kernel (sw_core.cuh), and
+//   5. writes the scores straight to where the caller wants them -- mapped pinned host memory
+//      (zero-copy stores, 256 B per warp) or a device array.
+// So a host batch is ONE kernel launch however many copies feed it, nothing waits for a whole
+// chunk, and the only exposed PCIe time is the first tile's.
+//
+// The wait is bounded: a block that sees no flag for `timeout_ns` (or an abort word set by the
+// host after a failed enqueue) reports through `status` and every block leaves.
+#pragma once
+#include <cuda_runtime.h>
+#include "sw_kernel.cuh"
+
+namespace swb {
+
+constexpr int FEED_NT = 64;                    // threads per block (= sw_kernel's shape at L = 128)
+constexpr int FEED_MINB = 6;                   // resident blocks per SM
+constexpr int FEED_ITEM_PAIRS = 2 * FEED_NT;   // pairs per work item
+constexpr int FEED_TILE_PAIRS = 4096;          // flag granularity: one `ready` word per 4096 pairs
+constexpr int FEED_ITEMS_PER_TILE = FEED_TILE_PAIRS / FEED_ITEM_PAIRS;
+
+// `ready[t]` holds 2*epoch + format once tile t of launch `epoch` is in HBM.
+constexpr uint32_t FEED_FMT_RAW = 0;           // byte codes in raw1/raw2
+constexpr uint32_t FEED_FMT_PACKED = 1;        // 2-bit codes in pk1/pk2; the consuming block expands them into raw1/raw2
+
+enum : uint32_t { FEED_STATUS_OK = 0, FEED_STATUS_TIMEOUT = 1, FEED_STATUS_ABORTED = 2 };
+
+struct FeedArgs {
+    uint8_t* raw1;                  // [cap][128] byte-coded staging (device)
+    uint8_t* raw2;
+    const uint8_t* pk1;             // [cap][32] 2-bit staging (device)
+    const uint8_t* pk2;
+    int32_t* scores;                // [n] device array, or mapped pinned host memory
+    const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine
+    uint32_t* next_item;            // work counter, zeroed before the launch (stream-ordered)
+    volatile uint32_t* status;      // mapped pinned host word: FEED_STATUS_*
+    const volatile uint32_t* abort; // mapped pinned host word: non-zero = give up
+    unsigned long long timeout_ns;
+    uint32_t n;                     // pairs in this epoch
+    uint32_t epoch;                 // flags of this launch are >= 2*epoch
+    uint32_t scores_vec2;           // 1: scores is 8-byte aligned (int2 stores)
+};
+
+__device__ __forceinline__ uint32_t feed_ld_acquire(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long feed_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// 4 packed bytes (16 bases) -> 16 byte codes: code(4i + j) = (byte[i] >> 2j) & 3   (source.cpp:1580-1583)
+__device__ __forceinline__ uint4 feed_expand_word(uint32_t w)
+{
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const uint32_t x = (w >> (8 * b)) & 0xffu;
+        o[b] = (x & 3u) | (((x >> 2) & 3u) << 8) | (((x >> 4) & 3u) << 16) | (((x >> 6) & 3u) << 24);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// The block's own m pairs: m*32 packed bytes -> m*128 byte codes.
+__device__ __forceinline__ void feed_expand_item(const uint8_t* pk, uint8_t* raw, uint32_t m)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(pk);
+    uint4* dst = reinterpret_cast<uint4*>(raw);
+    for (uint32_t i = threadIdx.x; i < m * 2u; i += FEED_NT) {     // one uint4 = 64 bases = half a sequence
+        const uint4 v = __ldcg(src + i);
+        dst[4 * i + 0] = feed_expand_word(v.x);
+        dst[4 * i + 1] = feed_expand_word(v.y);
+        dst[4 * i + 2] = feed_expand_word(v.z);
+        dst[4 * i + 3] = feed_expand_word(v.w);
+    }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(FEED_NT, FEED_MINB)
+sw_feed_kernel(const FeedArgs fa, const SwParams prm)
+{
+    constexpr int L = SW_L;
+    constexpr int V = SW_DEFAULT_VARIANT | SW_V_COHERENT_LD;
+    extern __shared__ uint32_t smem[];
+    uint32_t* t4s = smem + L * FEED_NT;
+    __shared__ uint32_t s_item, s_fmt;
+    if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
+
+    const uint32_t n_items = (fa.n + FEED_ITEM_PAIRS - 1) / FEED_ITEM_PAIRS;
+    const uint32_t want = 2u * fa.epoch;
+    SmemFifo<FEED_NT> fifo{smem + threadIdx.x};
+    SmemTable t4{t4s};
+
+    for (;;) {
+        __syncthreads();                                   // s_item / s_fmt of the previous round have been read
+        if (threadIdx.x == 0) {
+            const uint32_t item = atomicAdd(fa.next_item, 1u);
+            uint32_t fmt = 0xffffffffu;                    // "leave"
+            if (item < n_items) {
+                const uint32_t* flag = fa.ready + item / FEED_ITEMS_PER_TILE;
+                uint32_t v = feed_ld_acquire(flag);
+                if (v < want || v > want + 1u) {           // not landed yet (a flag of an older epoch is smaller)
+                    const unsigned long long t0 = feed_now_ns();
+                    unsigned spins = 0;
+                    for (;;) {
+                        __nanosleep(100);
+                        v = feed_ld_acquire(flag);
+                        if (v >= want && v <= want + 1u) break;
+                        if ((++spins & 255u) == 0u) {
+                            if (*fa.abort) { *fa.status = FEED_STATUS_ABORTED; v = 0xffffffffu; break; }
+                            if (feed_now_ns() - t0 > fa.timeout_ns) { *fa.status = FEED_STATUS_TIMEOUT; v = 0xffffffffu; break; }
+                        }
+                    }
+                }
+                fmt = (v == 0xffffffffu) ? v : (v - want);
+                if (fmt == 0xffffffffu) atomicAdd(fa.next_item, 0x40000000u);   // every later claim is past the end: all blocks leave
+            }
+            s_item = item;
+            s_fmt = fmt;
+        }
+        __syncthreads();
+        const uint32_t item = s_item, fmt = s_fmt;
+        if (fmt == 0xffffffffu) return;
+
+        const uint32_t p0 = item * FEED_ITEM_PAIRS;
+        const uint32_t m = (fa.n - p0 < (uint32_t)FEED_ITEM_PAIRS) ? fa.n - p0 : (uint32_t)FEED_ITEM_PAIRS;
+        if (fmt == FEED_FMT_PACKED) {
+            feed_expand_item(fa.pk1 + (size_t)p0 * 32, fa.raw1 + (size_t)p0 * L, m);
+            feed_expand_item(fa.pk2 + (size_t)p0 * 32, fa.raw2 + (size_t)p0 * L, m);
+            __syncthreads();                               // the block's stores are visible to the block's (plain) loads
+        }
+        const uint32_t p = p0 + 2u * threadIdx.x;
+        if (p < fa.n) {
+            const bool two = p + 1u < fa.n;                // odd tail: the high half repeats the low pair
+            int32_t lo, hi;
+            sw_two_pairs<FAST, L, V>(fa.raw1 + (size_t)p * L, fa.raw2 + (size_t)p * L, two ? (uint32_t)L : 0u, two ? (uint32_t)L : 0u,
+                                     fifo, t4, prm, lo, hi);
+            if (two && fa.scores_vec2) *reinterpret_cast<int2*>(fa.scores + p) = make_int2(lo, hi);
+            else { fa.scores[p] = lo; if (two) fa.scores[p + 1] = hi; }
+        }
+    }
+}
+
+constexpr size_t feed_smem_bytes() { return sw_smem_bytes<SW_L, FEED_NT>(); }
+
+} // namespace swb

@@ -10,6 +10,7 @@
 
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -17,11 +18,14 @@
 #include <exception>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "sg_kernel.cuh"
+#include "sw_feed_kernel.cuh"
+#include "sw_pair_kernel.cuh"
 #include "sw_kernel.cuh"
 #include "sw_params.h"
 
@@ -31,58 +35,28 @@ namespace {
 
 using namespace swb;
 
-constexpr int kSlots = 3;        // chunks in flight per GPU
-constexpr uint64_t kChunkPairs = 1ull << 17;   // 131072 pairs of 128 bases = 16 MiB per sequence array per chunk (fewer pairs for longer sequences)
-
-// Host-packing lanes (see run_range_lanes): sub-chunks of kSubPairs pairs, kLaneDepth in flight per lane.
-constexpr uint64_t kSubPairs = 1ull << 14;     // 16384 pairs: 2 MiB per byte-coded array, 0.5 MiB packed
-constexpr int kLaneDepth = 8;                  // buffer sets per lane (array size)
-constexpr int kPackDepth = 3;                  // in flight per PACK lane: the host core is the slow stage
-constexpr int kRawDepth = 8;                   // in flight on the RAW lane: enough 4 MiB copies queued to keep the link busy
-                                               // while earlier sub-chunks wait for their kernel (measured: depth 3 left it at 14 GB/s)
-constexpr uint64_t kLanesMinPairs = 16 * kSubPairs;   // below this the plain chunk pipeline is used
+constexpr int kSlots = 3;        // chunks in flight per GPU (chunk pipeline, run_range)
+// Chunk pipeline: a chunk is two whole waves of the L = 128 kernel's resident pairs (148 SMs x 6 blocks x 64 threads x 2
+// pairs = 113 664 on a B200) and the same number of BYTES at every length, so no launch ends in a mostly empty wave
+// (round 1's fixed 131 072 pairs were 1.15 waves: 17 % of every chunk's kernel time was tail).
+constexpr uint64_t kChunkWaves = 2;
 
 thread_local std::string g_init_error;
+thread_local std::string g_last_error_copy;
 
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    uint8_t* d_seq1 = nullptr;       // [kChunkPairs][128]
+    uint8_t* d_seq1 = nullptr;       // [chunk_pairs][128]
     uint8_t* d_seq2 = nullptr;
-    uint8_t* d_pk1 = nullptr;        // [kChunkPairs][32]  2-bit packed staging
+    uint8_t* d_pk1 = nullptr;        // [chunk_pairs][32]  2-bit packed staging
     uint8_t* d_pk2 = nullptr;
-    int32_t* d_scores = nullptr;     // [kChunkPairs]
+    int32_t* d_scores = nullptr;     // [chunk_pairs]
     bool busy = false;
 };
 
-// One lane = one host thread + one stream + kLaneDepth sets of buffers.  A PACK lane compresses a
-// sub-chunk of the caller's byte codes to 2 bits per base on its host core (hostpack.cpp), sends
-// 64 B per pair over PCIe and expands them on the device; the RAW lane sends the caller's bytes
-// as they are (256 B per pair).  Both kinds pull sub-chunks from one counter, so the PCIe link
-// and the host cores are both kept busy and the split adapts to whatever machine this is.
-struct Lane {
-    bool pack = false;
-    int depth = 0;
-    cudaStream_t stream[kLaneDepth] = {};   // one per buffer set: sub-chunk k+1's copy must not queue behind sub-chunk k's kernel
-    cudaEvent_t done[kLaneDepth] = {};
-    bool busy[kLaneDepth] = {};
-    uint8_t* h_pk[kLaneDepth] = {};      // pinned [2][kSubPairs][32]   (pack lanes)
-    uint8_t* d_pk[kLaneDepth] = {};      // device [2][kSubPairs][32]   (pack lanes)
-    uint8_t* d_seq[kLaneDepth] = {};     // device [2][kSubPairs][128]: seq1 rows then seq2 rows
-    int32_t* d_scores[kLaneDepth] = {};
-    std::thread th;
-};
-
-struct LaneJob {
-    const uint8_t* seq1 = nullptr;
-    const uint8_t* seq2 = nullptr;
-    int32_t* scores = nullptr;
-    uint64_t lo = 0, hi = 0;
-    SwParams prm{};
-    std::atomic<uint64_t> next{0};
-    std::atomic<int> rc{0};
-    std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};
-};
+struct FeedState;                    // feed.inc: the persistent-kernel batch packer
+struct PairSlot;                     // pairpath.inc: the per-pair call's mapped slots
 
 struct Device {
     int id = -1;
@@ -102,14 +76,9 @@ struct Device {
         int32_t* d_meta = nullptr;       // [4][cap]: score, end_y, end_x, n_ops
         size_t cap_pairs = 0; int len = 0; bool with_ops = false;
     } sg_slots[4];
-    // lane pool (created on first use)
-    std::vector<Lane*> lanes;
-    std::mutex pool_mu;
-    std::condition_variable pool_cv, pool_done_cv;
-    uint64_t pool_gen = 0;
-    int pool_pending = 0;
-    bool pool_stop = false;
-    LaneJob* job = nullptr;
+    uint64_t chunk_pairs = 0;        // chunk pipeline: pairs of 128 bases per chunk (whole waves), set by setup_device
+    FeedState* feed = nullptr;       // persistent-kernel batch packer (feed.inc)
+    PairSlot* pair = nullptr;        // per-pair path (pairpath.inc), created on first use
 };
 
 } // namespace
@@ -121,6 +90,7 @@ struct swb200_ctx {
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};   // host batches: pairs sent 2-bit packed / as bytes
     int force_general = 0;
+    int latency_path = 1;            // small batches of 128-mers take the one-warp-per-pair kernel (pairpath.inc); test hook
     int pack_threads = -1;           // per GPU; -1 = auto (host cores available to this process), 0 = off
     std::mutex tickets_mu;
     std::map<uint64_t, std::pair<std::thread, int*>> tickets;
@@ -270,6 +240,8 @@ cudaError_t launch_unpack(const uint8_t* d_packed, uint8_t* d_codes, uint64_t n_
     return cudaGetLastError();
 }
 
+FeedState* feed_create();        // feed.inc
+
 int setup_device(swb200_ctx* ctx, Device* d)
 {
     SWB_CUDA(ctx, cudaSetDevice(d->id));
@@ -277,6 +249,12 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, (prepare_kernel<true, 128>()));  SWB_CUDA(ctx, (prepare_kernel<false, 128>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 256>()));  SWB_CUDA(ctx, (prepare_kernel<false, 256>()));
     SWB_CUDA(ctx, (prepare_kernel<true, 512>()));  SWB_CUDA(ctx, (prepare_kernel<false, 512>()));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw_feed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feed_smem_bytes()));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw_feed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feed_smem_bytes()));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw_feed_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SWB_CUDA(ctx, cudaFuncSetAttribute(sw_feed_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    d->chunk_pairs = kChunkWaves * (uint64_t)d->prop.multiProcessorCount * LenCfg<128>::MINB * LenCfg<128>::NT * 2;
+    d->feed = feed_create();
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
     SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
@@ -298,37 +276,47 @@ int setup_device(swb200_ctx* ctx, Device* d)
 // launches on caller-owned device arrays holds no large buffers.
 int ensure_staging(swb200_ctx* ctx, Device* d, bool packed)
 {
+    const uint64_t cp = d->chunk_pairs;
     for (Slot& s : d->slots) {
         if (!s.d_seq1) {
-            SWB_CUDA(ctx, cudaMalloc(&s.d_seq1, kChunkPairs * SWB200_SEQ_LEN));
-            SWB_CUDA(ctx, cudaMalloc(&s.d_seq2, kChunkPairs * SWB200_SEQ_LEN));
-            SWB_CUDA(ctx, cudaMalloc(&s.d_scores, kChunkPairs * sizeof(int32_t)));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_seq1, cp * SWB200_SEQ_LEN));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_seq2, cp * SWB200_SEQ_LEN));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_scores, cp * sizeof(int32_t)));
         }
         if (packed && !s.d_pk1) {
-            SWB_CUDA(ctx, cudaMalloc(&s.d_pk1, kChunkPairs * 32));
-            SWB_CUDA(ctx, cudaMalloc(&s.d_pk2, kChunkPairs * 32));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_pk1, cp * 32));
+            SWB_CUDA(ctx, cudaMalloc(&s.d_pk2, cp * 32));
         }
     }
     return SWB200_OK;
 }
 
-// One GPU's share [lo, hi) of a host batch: chunks of kChunkPairs cycle through kSlots
-// streams, so chunk c+1's H2D and chunk c-1's D2H run under chunk c's kernel.
-int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed, int L,
-              const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi, bool shared_target = false)
+// Whatever was enqueued on the chunk pipeline's slots has finished (errors ignored: this is the error path's drain, so
+// that no copy into the caller's arrays is still in flight when an error code is returned).
+void drain_slots(Device* d)
 {
-    if (hi <= lo) return SWB200_OK;
-    std::lock_guard<std::mutex> lock(d->mu);
+    for (Slot& s : d->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.busy = false;
+    }
+}
+
+// Chunk pipeline -- one GPU's share [lo, hi) of a host batch the persistent-kernel packer (feed.inc) does not take:
+// small batches, the length sweep's L = 256 / 512, and the one-vs-many shape.  Chunks of d->chunk_pairs * 128 / L pairs
+// cycle through kSlots streams, so chunk c+1's H2D and chunk c-1's D2H run under chunk c's kernel.
+int run_range_locked(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed, int L,
+                     const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi, bool shared_target)
+{
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     int rc = ensure_staging(ctx, d, packed);
     if (rc != SWB200_OK) return rc;
     const size_t in_stride = packed ? 32 : (size_t)L;
-    const uint64_t chunk = kChunkPairs * SWB200_SEQ_LEN / (uint64_t)L;    // same bytes per chunk at every length
+    const uint64_t chunk = d->chunk_pairs * SWB200_SEQ_LEN / (uint64_t)L;    // same bytes per chunk at every length
     int si = 0;
     for (uint64_t c0 = lo; c0 < hi; c0 += chunk, si = (si + 1) % kSlots) {
         Slot& s = d->slots[si];
         const uint64_t m = (hi - c0 < chunk) ? hi - c0 : chunk;
-        if (s.busy) SWB_CUDA(ctx, cudaEventSynchronize(s.done));
+        if (s.busy) { s.busy = false; SWB_CUDA(ctx, cudaEventSynchronize(s.done)); }
         uint8_t* in1 = packed ? s.d_pk1 : s.d_seq1;
         uint8_t* in2 = packed ? s.d_pk2 : s.d_seq2;
         SWB_CUDA(ctx, cudaMemcpyAsync(in1, seq1 + c0 * in_stride, m * in_stride, cudaMemcpyHostToDevice, s.stream));
@@ -346,193 +334,28 @@ int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* se
         s.busy = true;
     }
     for (Slot& s : d->slots)
-        if (s.busy) { SWB_CUDA(ctx, cudaEventSynchronize(s.done)); s.busy = false; }
+        if (s.busy) { s.busy = false; SWB_CUDA(ctx, cudaEventSynchronize(s.done)); }
     return SWB200_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Host-packing lanes.  PCIe moves the caller's byte-coded arrays at ~52 GB/s, i.e. 5 ms per
-// million pairs against 1.8 ms of kernel time.  The bytes carry 2 bits of information each, so
-// spare host cores compress sub-chunks to the reference's 2-bit wire format (hostpack.cpp) into
-// pinned staging while the RAW lane keeps the link busy with uncompressed sub-chunks.
-int available_cpus()
+int run_range(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, bool packed, int L,
+              const SwParams& prm, int32_t* scores, uint64_t lo, uint64_t hi, bool shared_target = false)
 {
-    cpu_set_t set;
-    CPU_ZERO(&set);
-    if (sched_getaffinity(0, sizeof set, &set) == 0) {
-        const int n = CPU_COUNT(&set);
-        if (n > 0) return n;
-    }
-    const unsigned hc = std::thread::hardware_concurrency();
-    return hc ? (int)hc : 1;
-}
-
-int pack_threads_per_gpu(const swb200_ctx* ctx)
-{
-    if (ctx->pack_threads >= 0) return ctx->pack_threads;
-    if (const char* e = getenv("SWB200_PACK_THREADS")) return atoi(e) < 0 ? 0 : atoi(e);
-    const int G = (int)ctx->devs.size();
-    int t = (available_cpus() - 1) / G - 1;      // one core per GPU stays with the RAW lane, one with the caller
-    if (t > 30) t = 30;
-    return t >= 3 ? t : 0;                       // a couple of cores cannot beat the link: plain pipeline
-}
-
-int lane_alloc(swb200_ctx* ctx, Lane* ln)
-{
-    ln->depth = ln->pack ? kPackDepth : kRawDepth;
-    for (int b = 0; b < ln->depth; ++b) {
-        SWB_CUDA(ctx, cudaStreamCreateWithFlags(&ln->stream[b], cudaStreamNonBlocking));
-        SWB_CUDA(ctx, cudaEventCreateWithFlags(&ln->done[b], cudaEventDisableTiming));
-        SWB_CUDA(ctx, cudaMalloc(&ln->d_seq[b], 2 * kSubPairs * SWB200_SEQ_LEN));
-        SWB_CUDA(ctx, cudaMalloc(&ln->d_scores[b], kSubPairs * sizeof(int32_t)));
-        if (ln->pack) {
-            SWB_CUDA(ctx, cudaHostAlloc(&ln->h_pk[b], 2 * kSubPairs * 32, cudaHostAllocPortable));
-            SWB_CUDA(ctx, cudaMalloc(&ln->d_pk[b], 2 * kSubPairs * 32));
-        }
-    }
-    return SWB200_OK;
-}
-
-void lane_free(Lane* ln)
-{
-    for (int b = 0; b < kLaneDepth; ++b) {
-        if (ln->done[b]) cudaEventDestroy(ln->done[b]);
-        cudaFree(ln->d_seq[b]); cudaFree(ln->d_scores[b]); cudaFree(ln->d_pk[b]);
-        if (ln->h_pk[b]) cudaFreeHost(ln->h_pk[b]);
-        if (ln->stream[b]) cudaStreamDestroy(ln->stream[b]);
-    }
-}
-
-// One lane's share of a job: sub-chunks taken from the job's counter until none are left.
-int lane_run(swb200_ctx* ctx, Lane* ln, LaneJob* job)
-{
-    const uint64_t n_sub = (job->hi - job->lo + kSubPairs - 1) / kSubPairs;
-    int b = 0;
-    for (;;) {
-        if (job->rc.load() != SWB200_OK) break;
-        const uint64_t idx = job->next.fetch_add(1);
-        if (idx >= n_sub) break;
-        const uint64_t c0 = job->lo + idx * kSubPairs;
-        const uint64_t m = (job->hi - c0 < kSubPairs) ? job->hi - c0 : kSubPairs;
-        if (ln->busy[b]) { SWB_CUDA(ctx, cudaEventSynchronize(ln->done[b])); ln->busy[b] = false; }
-        cudaStream_t st = ln->stream[b];
-        uint8_t* d1 = ln->d_seq[b];
-        uint8_t* d2 = ln->d_seq[b] + m * SWB200_SEQ_LEN;
-        if (ln->pack) {
-            pack2bit_host(job->seq1 + c0 * SWB200_SEQ_LEN, ln->h_pk[b], m * SWB200_SEQ_LEN);
-            pack2bit_host(job->seq2 + c0 * SWB200_SEQ_LEN, ln->h_pk[b] + m * 32, m * SWB200_SEQ_LEN);
-            SWB_CUDA(ctx, cudaMemcpyAsync(ln->d_pk[b], ln->h_pk[b], 2 * m * 32, cudaMemcpyHostToDevice, st));
-            SWB_CUDA(ctx, launch_unpack(ln->d_pk[b], ln->d_seq[b], 2 * m, st));   // seq1 rows then seq2 rows
-            ctx->launches += 1;
-            job->packed_pairs += m;
-        } else {
-            SWB_CUDA(ctx, cudaMemcpyAsync(d1, job->seq1 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, st));
-            SWB_CUDA(ctx, cudaMemcpyAsync(d2, job->seq2 + c0 * SWB200_SEQ_LEN, m * SWB200_SEQ_LEN, cudaMemcpyHostToDevice, st));
-            job->raw_pairs += m;
-        }
-        SWB_CUDA(ctx, launch_for(job->prm, SWB200_SEQ_LEN, d1, d2, ln->d_scores[b], m, st, false));
-        ctx->launches += 1;
-        SWB_CUDA(ctx, cudaMemcpyAsync(job->scores + c0, ln->d_scores[b], m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        SWB_CUDA(ctx, cudaEventRecord(ln->done[b], st));
-        ln->busy[b] = true;
-        b = (b + 1) % ln->depth;
-    }
-    for (int k = 0; k < ln->depth; ++k)
-        if (ln->busy[k]) { ln->busy[k] = false; SWB_CUDA(ctx, cudaEventSynchronize(ln->done[k])); }
-    return SWB200_OK;
-}
-
-// `seen` = the pool generation at the time the lane was created (a pool can be rebuilt after
-// earlier jobs, see swb200_set_host_pack_threads): the lane answers only to jobs posted later.
-void lane_main(swb200_ctx* ctx, Device* d, Lane* ln, uint64_t seen)
-{
-    cudaSetDevice(d->id);
-    for (;;) {
-        LaneJob* job;
-        {
-            std::unique_lock<std::mutex> lk(d->pool_mu);
-            d->pool_cv.wait(lk, [&] { return d->pool_stop || d->pool_gen != seen; });
-            if (d->pool_stop) return;
-            seen = d->pool_gen;
-            job = d->job;
-        }
-        const int rc = lane_run(ctx, ln, job);
-        if (rc != SWB200_OK) job->rc.store(rc);
-        {
-            std::lock_guard<std::mutex> lk(d->pool_mu);
-            if (--d->pool_pending == 0) d->pool_done_cv.notify_all();
-        }
-    }
-}
-
-void stop_lanes(Device* d)
-{
-    {
-        std::lock_guard<std::mutex> lk(d->pool_mu);
-        d->pool_stop = true;
-    }
-    d->pool_cv.notify_all();
-    for (Lane* ln : d->lanes) {
-        if (ln->th.joinable()) ln->th.join();
-        lane_free(ln);
-        delete ln;
-    }
-    d->lanes.clear();
-}
-
-// Creates the pool on first use: one RAW lane + `n_pack` PACK lanes.  Called under d->mu.
-int ensure_lanes(swb200_ctx* ctx, Device* d, int n_pack)
-{
-    if (!d->lanes.empty()) return SWB200_OK;
-    try {
-        for (int k = 0; k <= n_pack; ++k) {
-            Lane* ln = new Lane;
-            ln->pack = (k > 0);
-            d->lanes.push_back(ln);
-            const int rc = lane_alloc(ctx, ln);
-            if (rc != SWB200_OK) {           // no half-built pool: the next batch would wait on threads that do not exist
-                stop_lanes(d);
-                d->pool_stop = false;
-                return rc;
-            }
-        }
-        uint64_t gen;
-        {
-            std::lock_guard<std::mutex> lk(d->pool_mu);
-            gen = d->pool_gen;
-        }
-        for (Lane* ln : d->lanes) ln->th = std::thread(lane_main, ctx, d, ln, gen);
-    } catch (const std::exception& e) {      // a lane or its thread could not be made: take the pool down again (joins what started)
-        stop_lanes(d);
-        d->pool_stop = false;
-        return fail(ctx, SWB200_ERR_NOMEM, e.what());
-    }
-    return SWB200_OK;
-}
-
-// One GPU's share [lo, hi) of a byte-coded host batch through the lane pool.
-int run_range_lanes(swb200_ctx* ctx, Device* d, const uint8_t* seq1, const uint8_t* seq2, const SwParams& prm,
-                    int32_t* scores, uint64_t lo, uint64_t hi, int n_pack)
-{
+    if (hi <= lo) return SWB200_OK;
     std::lock_guard<std::mutex> lock(d->mu);
-    SWB_CUDA(ctx, cudaSetDevice(d->id));
-    int rc = ensure_lanes(ctx, d, n_pack);
-    if (rc != SWB200_OK) return rc;
-    LaneJob job;
-    job.seq1 = seq1; job.seq2 = seq2; job.scores = scores; job.lo = lo; job.hi = hi; job.prm = prm;
-    {
-        std::unique_lock<std::mutex> lk(d->pool_mu);
-        d->job = &job;
-        d->pool_pending = (int)d->lanes.size();
-        ++d->pool_gen;
-        d->pool_cv.notify_all();
-        d->pool_done_cv.wait(lk, [&] { return d->pool_pending == 0; });
-        d->job = nullptr;
-    }
-    ctx->packed_pairs += job.packed_pairs.load();
-    ctx->raw_pairs += job.raw_pairs.load();
-    return job.rc.load();
+    const int rc = run_range_locked(ctx, d, seq1, seq2, packed, L, prm, scores, lo, hi, shared_target);
+    if (rc != SWB200_OK) drain_slots(d);      // nothing may still be writing the caller's `scores` once the error is returned
+    return rc;
 }
+
+// The persistent-kernel batch packer (a textual part of this translation unit)
+#include "feed.inc"
+
+// The per-pair call's own path (a textual part of this translation unit)
+#include "pairpath.inc"
+
+// Live integer-pipe peak for the benchmark's roofline (a textual part of this translation unit)
+#include "peakprobe.inc"
 
 // Semi-global X-drop aligner: scratch, launches and the host pipeline (a textual part of this translation unit)
 #include "sg_host.inc"
@@ -583,13 +406,19 @@ int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool p
     int rc = check_args(ctx, seq1, seq2, sm, gap, scores, n);
     if (rc == SWB200_OK) rc = check_len(ctx, sm, L);
     if (rc != SWB200_OK || n == 0) return rc;
+    // A handful of pairs: the latency kernel (one warp per pair, no staging) -- the per-pair call lives here.
+    if (L == SWB200_SEQ_LEN && !packed && !shared_target && n <= kPairPathMax && ctx->latency_path && !ctx->force_general)
+        return pair_run(ctx, ctx->devs[0], seq1, seq2, sm, gap, scores, n);
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
-    // Large byte-coded batches of the reference shape go through the host-packing lanes.
-    const int n_pack = (!packed && !shared_target && L == SWB200_SEQ_LEN && n / G >= kLanesMinPairs) ? pack_threads_per_gpu(ctx) : 0;
+    // Batches of the reference shape go through the persistent-kernel packer (feed.inc); byte-coded ones with the host
+    // 2-bit packing lanes beside the raw copies.  Everything else (small batches, L = 256 / 512, one shared target)
+    // takes the chunk pipeline.
+    const bool feed = (L == SWB200_SEQ_LEN) && !shared_target && n / G >= kFeedMinPairs;
+    const int n_pack = (feed && !packed) ? pack_threads_per_gpu(ctx) : 0;
     auto range = [=](Device* d, uint64_t lo, uint64_t hi) {
-        return n_pack > 0 ? run_range_lanes(ctx, d, seq1, seq2, prm, scores, lo, hi, n_pack)
-                          : run_range(ctx, d, seq1, seq2, packed, L, prm, scores, lo, hi, shared_target);
+        return feed ? feed_run(ctx, d, seq1, seq2, packed, prm, scores, lo, hi, n_pack)
+                    : run_range(ctx, d, seq1, seq2, packed, L, prm, scores, lo, hi, shared_target);
     };
     if (G == 1 || n < 2 * G) return range(ctx->devs[0], 0, n);
     // Contiguous index ranges [k*n/G, (k+1)*n/G), one host thread per GPU;
@@ -622,14 +451,31 @@ int swb200_init(swb200_ctx** out, const int* devices, int n_devices)
     cudaError_t e = cudaGetDeviceCount(&visible);
     if (e != cudaSuccess || visible == 0)
         return fail(nullptr, SWB200_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)", e);
-    if (n_devices == 0) n_devices = visible;
-    if (n_devices > visible) return fail(nullptr, SWB200_ERR_NO_DEVICE, "more devices requested than visible");
+    // n_devices == 0: every USABLE device (compute capability 10.x, what swb200_device_count() reports); a device list
+    // makes no sense then.  Otherwise `devices` (or 0..n-1) is taken as given and a non-sm_100 device is an error.
+    std::vector<int> ids;
+    try {
+        if (n_devices == 0) {
+            if (devices) return fail(nullptr, SWB200_ERR_ARG, "swb200_init: a device list needs n_devices > 0");
+            for (int i = 0; i < visible; ++i) {
+                int major = 0;
+                if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ids.push_back(i);
+            }
+            if (ids.empty()) return fail(nullptr, SWB200_ERR_NO_DEVICE, "no compute capability 10.x device visible (kernels are sm_100a only)");
+        } else {
+            if (n_devices > visible) return fail(nullptr, SWB200_ERR_NO_DEVICE, "more devices requested than visible");
+            for (int k = 0; k < n_devices; ++k) ids.push_back(devices ? devices[k] : k);
+        }
+    } catch (const std::exception& e) {
+        return fail(nullptr, SWB200_ERR_NOMEM, e.what());
+    }
+    n_devices = (int)ids.size();
     swb200_ctx* ctx = nullptr;
     try {
         ctx = new swb200_ctx;
         for (int k = 0; k < n_devices; ++k) {
             Device* d = new Device;
-            d->id = devices ? devices[k] : k;
+            d->id = ids[k];
             ctx->devs.push_back(d);
             int major = 0;
             cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d->id);
@@ -659,7 +505,8 @@ void swb200_shutdown(swb200_ctx* ctx)
     }
     for (Device* d : ctx->devs) {
         cudaSetDevice(d->id);
-        stop_lanes(d);
+        feed_shutdown(d);
+        pair_shutdown(d);
         for (Slot& s : d->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             if (s.busy && s.done) cudaEventSynchronize(s.done);   // a packed-device call on the caller's stream may still read the staging
@@ -681,7 +528,14 @@ void swb200_shutdown(swb200_ctx* ctx)
 
 int swb200_n_devices(const swb200_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
-const char* swb200_last_error(const swb200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+const char* swb200_last_error(const swb200_ctx* ctx)
+{
+    if (!ctx) return g_init_error.c_str();
+    // worker threads may be writing ctx->err: copy it under the lock into this thread's own buffer
+    std::lock_guard<std::mutex> lk(const_cast<swb200_ctx*>(ctx)->err_mu);
+    g_last_error_copy = ctx->err;
+    return g_last_error_copy.c_str();
+}
 
 const char* swb200_strerror(int code)
 {
@@ -847,8 +701,8 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const ui
     // before its kernels have run: whoever uses slot 0 next waits on `done` (run_range does so through `busy`).
     Slot& s = d->slots[0];
     if (s.busy) SWB_CUDA(ctx, cudaStreamWaitEvent(st, s.done, 0));
-    for (uint64_t c0 = 0; c0 < n; c0 += kChunkPairs) {
-        const uint64_t m = (n - c0 < kChunkPairs) ? n - c0 : kChunkPairs;
+    for (uint64_t c0 = 0; c0 < n; c0 += d->chunk_pairs) {
+        const uint64_t m = (n - c0 < d->chunk_pairs) ? n - c0 : d->chunk_pairs;
         SWB_CUDA(ctx, launch_unpack(d_pk1 + c0 * 32, s.d_seq1, m, st));
         SWB_CUDA(ctx, launch_unpack(d_pk2 + c0 * 32, s.d_seq2, m, st));
         SWB_CUDA(ctx, launch_for(prm, SWB200_SEQ_LEN, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
@@ -866,6 +720,7 @@ int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_
     if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
     Device* d = ctx->devs[device_index];
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    std::lock_guard<std::mutex> lock(d->mu);     // the counter d_bad is one per device: calls on other streams / threads wait
     SWB_CUDA(ctx, cudaSetDevice(d->id));
     SWB_CUDA(ctx, cudaMemsetAsync(d->d_bad, 0, sizeof(unsigned long long), st));
     if (n_bytes) {
@@ -919,18 +774,20 @@ int swb200_kernel_info_for(swb200_ctx* ctx, int device_index, const int8_t* sm, 
 // Semi-global X-drop aligner: the C-ABI entry points (a textual part of this translation unit)
 #include "sg_abi.inc"
 
+int swb200_measure_alu_peak(swb200_ctx* ctx, int device_index, double target_ms, double* tinstr_per_s, double* elapsed_ms)
+{
+    if (!ctx || !tinstr_per_s) return SWB200_ERR_ARG;
+    if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
+    if (!(target_ms > 0.0) || target_ms > 2000.0) return fail(ctx, SWB200_ERR_ARG, "target_ms must be in (0, 2000]");
+    return measure_alu_peak(ctx, ctx->devs[device_index], target_ms, tinstr_per_s, elapsed_ms);
+}
+
 uint64_t swb200_launch_count(const swb200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int swb200_set_host_pack_threads(swb200_ctx* ctx, int threads_per_gpu)
 {
     if (!ctx) return SWB200_ERR_ARG;
-    for (Device* d : ctx->devs) {
-        std::lock_guard<std::mutex> lock(d->mu);
-        cudaSetDevice(d->id);
-        stop_lanes(d);                 // the pool is rebuilt with the new size on the next batch
-        d->pool_stop = false;
-    }
-    ctx->pack_threads = threads_per_gpu < 0 ? -1 : threads_per_gpu;
+    ctx->pack_threads = threads_per_gpu < 0 ? -1 : threads_per_gpu;    // the lane pool is rebuilt with the new size by the next batch
     return SWB200_OK;
 }
 
@@ -948,6 +805,13 @@ int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes
     if ((!codes || !packed) && n_codes) return SWB200_ERR_ARG;
     if (n_codes % 8) return SWB200_ERR_ARG;
     pack2bit_host(codes, packed, (size_t)n_codes);
+    return SWB200_OK;
+}
+
+int swb200_set_latency_path(swb200_ctx* ctx, int on)
+{
+    if (!ctx) return SWB200_ERR_ARG;
+    ctx->latency_path = on ? 1 : 0;
     return SWB200_OK;
 }
 

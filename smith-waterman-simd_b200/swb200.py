@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
     "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
-    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host",
+    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -115,6 +115,12 @@ def load_library():
     lib.swb200_launch_count.argtypes = [vp]
     lib.swb200_set_force_general.restype = i32
     lib.swb200_set_force_general.argtypes = [vp, i32]
+    lib.swb200_measure_alu_peak.restype = i32
+    lib.swb200_measure_alu_peak.argtypes = [vp, i32, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.swb200_host_read_bandwidth.restype = i32
+    lib.swb200_host_read_bandwidth.argtypes = [vp, u64, i32, i32, C.POINTER(C.c_double)]
+    lib.swb200_set_latency_path.restype = i32
+    lib.swb200_set_latency_path.argtypes = [vp, i32]
     lib.swb200_gen_reference_stream.restype = i32
     lib.swb200_gen_reference_stream.argtypes = [u64, u64, vp, vp]
     for name in ("swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed"):
@@ -242,6 +248,16 @@ class Context:
 
     def set_force_general(self, on: bool):
         self._check(self._lib.swb200_set_force_general(self._h, int(on)))
+
+    def measure_alu_peak(self, device_index: int = 0, target_ms: float = 50.0) -> dict:
+        """Integer-ALU issue peak of the GPU, measured now (VIADDMNMX.S16x2 chains on every SM): Tinstr/s."""
+        t, ms = C.c_double(), C.c_double()
+        self._check(self._lib.swb200_measure_alu_peak(self._h, device_index, float(target_ms), C.byref(t), C.byref(ms)))
+        return {"tinstr_per_s": float(t.value), "elapsed_ms": float(ms.value)}
+
+    def set_latency_path(self, on: bool):
+        """False: small host batches go through the throughput kernel instead of the one-warp-per-pair kernel (test hook)."""
+        self._check(self._lib.swb200_set_latency_path(self._h, int(on)))
 
     def kernel_info(self, score_matrix, gap_penalty, device_index: int = 0, seq_len: int = SEQ_LEN) -> dict:
         m = _matrix(score_matrix)
@@ -420,6 +436,28 @@ def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys") -> Optional[di
         return {"bound": False, "error": str(e)[:80]}
 
 
+def bind_rank_cpus(local_rank: int, local_world: int, device_index: Optional[int] = None) -> dict:
+    """One process per GPU on a shared box: gives rank `local_rank` of `local_world` its own contiguous share of the CPUs
+    this process may run on (of the GPU's NUMA node when sysfs names one), so that the library's auto-sized lane pool
+    -- (CPUs available - GPUs) / GPUs PACK lanes plus the calling thread -- adds up to the box instead of every rank
+    claiming all of it.  Returns what was done; undo with os.sched_setaffinity(0, result["before"])."""
+    before = sorted(os.sched_getaffinity(0))
+    numa = bind_to_gpu_numa_node(device_index if device_index is not None else local_rank) if local_world > 1 else None
+    allowed = sorted(os.sched_getaffinity(0))
+    out = {"before": before, "numa": numa, "cpus": len(allowed), "share": None}
+    if local_world > 1 and len(allowed) >= local_world:
+        # ranks whose GPUs sit on the same node split that node's CPUs among themselves; with one node that is everybody
+        peers = local_world if (numa is None or not numa.get("bound")) else max(1, local_world * len(allowed) // max(len(before), 1))
+        k = local_rank % peers
+        lo, hi = len(allowed) * k // peers, len(allowed) * (k + 1) // peers
+        mine = allowed[lo:hi]
+        if mine:
+            os.sched_setaffinity(0, mine)
+            out["share"] = [mine[0], mine[-1]]
+            out["cpus"] = len(mine)
+    return out
+
+
 _default_ctx: Optional[Context] = None
 
 
@@ -498,6 +536,16 @@ def pack2bit(codes: np.ndarray) -> np.ndarray:
     if rc != 0:
         raise SwbError(rc, "swb200_pack2bit_host")
     return out
+
+
+def host_read_bandwidth(buf: np.ndarray, threads: int, passes: int = 1) -> float:
+    """Bytes per second at which `threads` host threads stream-read `buf` (benchmark helper, bench.py host_ceiling)."""
+    assert buf.flags.c_contiguous
+    out = C.c_double()
+    rc = load_library().swb200_host_read_bandwidth(buf.ctypes.data, buf.nbytes, int(threads), int(passes), C.byref(out))
+    if rc != 0:
+        raise SwbError(rc, "swb200_host_read_bandwidth")
+    return float(out.value)
 
 
 def fnv1a64(scores: np.ndarray) -> int:

@@ -179,7 +179,7 @@ def test_the_product_never_touches_the_oracle_and_bench_only_in_its_baseline_leg
     # bench.py: every `from oracle import ...` sits in a function of the baseline / reference legs or under `if not args.no_cpu_baseline`
     src = open(os.path.join(ROOT, "bench.py")).read()
     tree = ast.parse(src)
-    allowed_functions = {"cpu_reference_run", "run_cpu_table", "sg_cpu_reference"}
+    allowed_functions = {"cpu_reference_run", "run_cpu_table", "sg_cpu_reference", "run_reference_arm"}   # the reference arm loads NOTHING of the product
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         for node in ast.walk(fn):
             if isinstance(node, ast.ImportFrom) and node.module == "oracle":

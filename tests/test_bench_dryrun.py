@@ -28,6 +28,11 @@ class _Event:
         return 2.0
 
 
+class _Stream:
+    def synchronize(self):
+        pass
+
+
 class _FakePinned:
     def __init__(self, shape, dtype):
         self.array = np.zeros(shape, dtype)
@@ -99,6 +104,15 @@ def _fake_context_class(oracle, swb200):
 
             class Lib:
                 @staticmethod
+                def swb200_score_pair(h, p1, p2, pm, gap, pout):
+                    a = np.frombuffer((C.c_uint8 * 128).from_address(p1), dtype=np.uint8)[None, :]
+                    b = np.frombuffer((C.c_uint8 * 128).from_address(p2), dtype=np.uint8)[None, :]
+                    m = np.frombuffer((C.c_int8 * 16).from_address(pm), dtype=np.int8)
+                    np.frombuffer((C.c_int32 * 1).from_address(pout), dtype=np.int32)[0] = oracle.score_batch(a, b, m, gap.value)[0]
+                    ctx.launch_count += 1
+                    return 0
+
+                @staticmethod
                 def swb200_semiglobal_xdrop_batch(h, pa, pb, length, n, p_score, p_ey, p_ex, p_nops, p_ops):
                     def view(ptr, count, ctype, dtype):
                         return np.frombuffer((ctype * count).from_address(ptr), dtype=dtype)
@@ -115,6 +129,9 @@ def _fake_context_class(oracle, swb200):
 
         def set_host_pack_threads(self, t):
             self._pack = 5 if t < 0 else t
+
+        def measure_alu_peak(self, device_index=0, target_ms=50.0):
+            return {"tinstr_per_s": 18.4, "elapsed_ms": target_ms}
 
         def host_pack_stats(self):
             return {"packed_pairs": self._packed_pairs, "raw_pairs": 0, "pack_threads_per_gpu": self._pack}
@@ -137,12 +154,16 @@ def bench(monkeypatch, oracle):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
     monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     real_empty = torch.empty
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
     monkeypatch.setattr(swb200, "Context", _fake_context_class(oracle, swb200))
     monkeypatch.setattr(swb200, "PinnedArray", _FakePinned)
     monkeypatch.setattr(mod, "PAIRS_PER_GPU", 3000)
+    mod.real_sweep_pairs = mod.sweep_pairs
+    monkeypatch.setattr(mod, "sweep_pairs", lambda L, info: 64)       # the default line carries the sweep: keep the oracle's share small
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     return mod
@@ -150,7 +171,8 @@ def bench(monkeypatch, oracle):
 
 def test_b200_arm_assembles_its_line(bench):
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="b200", no_cpu_baseline=False, pack_threads=None,
-                                 no_plain_e2e=False, cpu_table=False, workload="batch1m", pairs=0, batch_pairs=0, packed=False)
+                                 no_plain_e2e=False, cpu_table=False, workload="batch1m", pairs=0, batch_pairs=0, packed=False,
+                                 quick=False, stream_pairs=5000)
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         bench.run_b200_arm(args)
@@ -163,12 +185,20 @@ def test_b200_arm_assembles_its_line(bench):
     assert line["roofline"]["bound"] == "int_alu" and line["roofline"]["frac"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["verified"]["fnv1a64_ae56a1e6a1d57492_and_sum_75478815"] is False      # 3000 pairs, not the 1 M batch
+    # the legs the default line carries since round 2
+    assert line["roofline"]["peak_live"]["tinstr_per_s"] == 18.4 and line["roofline"]["peak"] == 18.4 and 0 < line["roofline"]["alu_pipe_busy"]["model"]
+    assert [r["seq_len"] for r in line["sweep"]] == [128, 256, 512] and all(r["pairs"] == 64 for r in line["sweep"])
+    assert line["per_pair"]["score"] == 80 and line["per_pair"]["us_per_call"] > 0 and line["per_pair"]["gpu_launches_per_call"] == 1
+    assert line["stream"]["packed"]["pairs"] == 5000 and line["stream"]["bytes"]["score_sum"] == line["stream"]["packed"]["score_sum"]
+    hc = line["host_ceiling"]
+    assert hc["h2d_pinned_gbs"] > 0 and hc["host_read_gbs"] > 0 and hc["byte_input_ceiling_gcups"] > 0
+    assert line["e2e_inproc"] is None and line["e2e"]["packed_input"]["gpu_launches_per_step"] > 0
     assert line["verified"]["other_ranks_score_sums_equal_reference"] is None           # one rank
 
 
 def _args(**kw):
     base = dict(gpus=1, steps=2, warmup=3, impl="b200", no_cpu_baseline=True, pack_threads=None, no_plain_e2e=False,
-                cpu_table=False, workload="batch1m", pairs=0, batch_pairs=0, packed=False)
+                cpu_table=False, workload="batch1m", pairs=0, batch_pairs=0, packed=False, quick=False, stream_pairs=4000)
     base.update(kw)
     return types.SimpleNamespace(**base)
 
@@ -182,7 +212,7 @@ def _run(fn, args):
 
 def test_sweep_arm_assembles_its_line(bench, monkeypatch):
     info = {"sm_count": 148, "blocks_per_sm": 6, "threads_per_block": 64}
-    assert [bench.sweep_pairs(L, dict(info, blocks_per_sm=b)) for L, b in ((128, 6), (256, 3), (512, 6))] == [1136640, 284160, 340992]
+    assert [bench.real_sweep_pairs(L, dict(info, blocks_per_sm=b)) for L, b in ((128, 6), (256, 3), (512, 6))] == [1136640, 284160, 340992]
     with open(os.path.join(ROOT, "tests", "golden", "sweep_sums.json")) as f:
         g = json.load(f)["by_length"]
     assert all(str(n) in g[L]["sum_of_scores_by_pairs"] for L, n in (("128", 1136640), ("256", 284160), ("512", 340992)))   # the B200's batches are pinned
@@ -232,6 +262,8 @@ def _two_rank_worker(rank, world, port, out_path):
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
     torch.cuda.Event = _Event
+    torch.cuda.Stream = _Stream
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.Tensor.cuda = lambda self, *a, **k: self
     real_empty = torch.empty
     torch.empty = lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"})
@@ -240,6 +272,7 @@ def _two_rank_worker(rank, world, port, out_path):
     swb200.Context = _fake_context_class(O, swb200)
     swb200.PinnedArray = _FakePinned
     swb200.bind_to_gpu_numa_node = lambda *a, **k: None
+    swb200.bind_rank_cpus = lambda lr, lw, device_index=None: {"before": sorted(os.sched_getaffinity(0)), "numa": None, "cpus": 2, "share": [lr, lr]}
     mod.PAIRS_PER_GPU = 1500
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
@@ -264,4 +297,9 @@ def test_b200_arm_two_ranks_on_gloo(tmp_path, oracle):
     assert line["value"] == pytest.approx(2 * 1500 * 16384 / (line["ms_per_step"] * 1e-3) / 1e9)
     assert line["verified"]["e2e_equals_device"] is True
     assert line["verified"]["other_ranks_checked"] == 0 and line["verified"]["other_ranks_score_sums_equal_reference"] is None   # 1500-pair blocks have no golden
-    assert "cpu_baseline" not in line and line["e2e"]["packed_input"] is None      # both are N = 1 only
+    assert "cpu_baseline" not in line and line["sweep"] is None and line["per_pair"] is None      # N = 1 only
+    assert line["e2e"]["packed_input"]["scores_equal_device_leg"] is True                           # at every N
+    inproc = line["e2e_inproc"]                                                                      # rank 0 alone drives both "GPUs"
+    assert inproc["n_gpus"] == 2 and inproc["pairs_per_step"] == 3000 and inproc["bytes"]["value"] > 0 and inproc["packed"]["value"] > 0
+    assert line["stream"]["packed"]["pairs"] == 4000 and line["stream"]["bytes"]["pairs"] == 4000   # the index space is sharded, not replicated
+    assert line["host_ceiling"]["h2d_pinned_gbs"] > 0

@@ -43,18 +43,51 @@ def test_first4096_golden_both_matrices(ctx, swb, oracle):
         assert np.array_equal(ctx.score_batch(a, b, sm, g), exp), name
 
 
-def test_structured_golden_all_param_sets_both_kernels(ctx, golden):
+def test_structured_golden_all_param_sets_all_three_kernels(ctx, golden):
+    # 480 structured pairs x 14 parameter sets (domain corners included) through every kernel that can score them:
+    # the one-warp-per-pair latency kernel (what a host batch this small takes by default), and the throughput
+    # kernel in its fast (offset) and general form.
     z = golden["structured_npz"]
     launches0 = ctx.launch_count
     try:
-        for force_general in (False, True):
+        for latency, force_general in ((True, False), (False, False), (False, True)):
+            ctx.set_latency_path(latency)
             ctx.set_force_general(force_general)
             for ps in golden["structured"]["param_sets"]:
                 got = ctx.score_batch(z["seq1"], z["seq2"], ps["matrix"], ps["gap"])
-                assert np.array_equal(got, z[ps["name"]].astype(np.int32)), (ps["name"], force_general)
+                assert np.array_equal(got, z[ps["name"]].astype(np.int32)), (ps["name"], latency, force_general)
     finally:
         ctx.set_force_general(False)
-    assert ctx.launch_count - launches0 == 2 * len(golden["structured"]["param_sets"])
+        ctx.set_latency_path(True)
+    assert ctx.launch_count - launches0 == 3 * len(golden["structured"]["param_sets"])
+
+
+def test_per_pair_call_over_the_whole_domain(ctx, swb, oracle, golden):
+    # swb200_score_pair (the pair rides in the launch parameters) and a 2-pair batch (mapped slot) on structured pairs,
+    # every parameter set of the golden file: equal to the fixture
+    z = golden["structured_npz"]
+    idx = list(range(0, z["seq1"].shape[0], 37))
+    for ps in golden["structured"]["param_sets"]:
+        want = z[ps["name"]].astype(np.int32)
+        got = [ctx.smith_waterman(z["seq1"][i], z["seq2"][i], ps["matrix"], ps["gap"]) for i in idx]
+        assert got == [int(want[i]) for i in idx], ps["name"]
+        two = ctx.score_batch(z["seq1"][5:7], z["seq2"][5:7], ps["matrix"], ps["gap"])
+        assert np.array_equal(two, want[5:7]), ps["name"]
+    # codes above 3 are the caller's error; the kernels mask them and never read out of bounds
+    bad = np.full(128, 7, np.uint8)
+    assert ctx.smith_waterman(bad, bad, swb.MATRIX_SPEEDTEST, 15) == 1280
+
+
+def test_latency_kernel_at_its_largest_batch(ctx, swb, oracle):
+    # 2048 pairs = the most the one-warp-per-pair kernel takes; 2049 is the first batch of the throughput kernel
+    a, b = swb.counter_pairs(424242, 2049)
+    want = oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)
+    l0 = ctx.launch_count
+    assert np.array_equal(ctx.score_batch(a[:2048], b[:2048], swb.MATRIX_SPEEDTEST, 15), want[:2048])
+    assert np.array_equal(ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15), want)
+    assert ctx.launch_count - l0 == 2
+    sm = mm(127, -127)
+    assert np.array_equal(ctx.score_batch(a[:2048], b[:2048], sm, 127), oracle.score_batch(a[:2048], b[:2048], sm, 127, threads=NCPU))
 
 
 def test_full_1m_batch_checksum(ctx, swb, oracle, golden):
@@ -88,17 +121,55 @@ def test_general_kernel_on_stream(ctx, swb, oracle):
     assert np.array_equal(ctx.score_batch(a[:5000], b[:5000], sm, 127), oracle.score_batch(a[:5000], b[:5000], sm, 127, threads=NCPU))
 
 
+@pytest.mark.parametrize("latency", [True, False])
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 127, 128, 255, 256, 257, 1023])
-def test_ragged_batch_sizes(ctx, swb, oracle, n):
+def test_ragged_batch_sizes(ctx, swb, oracle, n, latency):
     a, b = swb.counter_pairs(77, n)
-    got = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    ctx.set_latency_path(latency)           # the latency kernel (default for a batch this small) and the throughput kernel
+    try:
+        got = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    finally:
+        ctx.set_latency_path(True)
     assert got.shape == (n,)
     if n:
         assert np.array_equal(got, oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15))
 
 
+@pytest.mark.parametrize("n", [8192, 8193, 12287, 12289, 4096 * 5 + 129, 65536 + 1])
+@pytest.mark.parametrize("packed", [False, True])
+def test_ragged_batches_through_the_persistent_kernel(ctx, swb, oracle, n, packed):
+    # sizes around the tile (4096 pairs), work-item (128 pairs) and odd-pair boundaries of the consumer kernel, byte-coded and
+    # 2-bit input, pageable host arrays (device score staging + one D2H) -- equal to the oracle on every pair
+    a, b = swb.counter_pairs(1_234_567, n)
+    want = oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)
+    l0 = ctx.launch_count
+    if packed:
+        got = ctx.score_batch(oracle.pack2bit(a), oracle.pack2bit(b), swb.MATRIX_SPEEDTEST, 15, packed=True)
+    else:
+        got = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    assert ctx.launch_count - l0 == 1            # one persistent kernel, however many copies fed it
+    assert np.array_equal(got, want)
+
+
+def test_persistent_kernel_scores_into_an_unaligned_pinned_slice(ctx, swb, oracle):
+    # pinned arrays: the kernel stores scores straight into host memory; an odd offset takes the 4-byte store form
+    n = 20_000
+    a, b = swb.counter_pairs(55, n)
+    pa, pb, ps = swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n + 3,), np.int32)
+    pa.array[:] = a
+    pb.array[:] = b
+    ps.array[:] = -1
+    want = oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)
+    for off in (0, 1):
+        ps.array[:] = -1
+        ctx.score_batch(pa.array, pb.array, swb.MATRIX_SPEEDTEST, 15, out=ps.array[off:off + n])
+        assert np.array_equal(ps.array[off:off + n], want) and (ps.array[off + n:] == -1).all() and (ps.array[:off] == -1).all()
+    for p in (pa, pb, ps):
+        p.free()
+
+
 def test_multi_chunk_batch_with_pinned_buffers(ctx, swb, oracle):
-    # > 2 chunks of 131072 pairs so that every staging slot is reused; pinned in, pinned out
+    # 400 000 pairs, pinned in, pinned out: the persistent kernel stores straight into the pinned score array
     n = 3 * 131072 + 12345
     a, b = swb.counter_pairs(5_000_000, n)
     pa, pb, ps = swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n, 128), np.uint8), swb.PinnedArray((n,), np.int32)
@@ -125,7 +196,7 @@ def test_host_pack_lanes_equal_plain_pipeline(ctx, swb, oracle):
         s0 = ctx.host_pack_stats()
         plain = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
         s1 = ctx.host_pack_stats()
-        assert s1["packed_pairs"] == s0["packed_pairs"] and s1["raw_pairs"] == s0["raw_pairs"]   # lanes unused
+        assert s1["packed_pairs"] == s0["packed_pairs"] and s1["raw_pairs"] == s0["raw_pairs"] + n   # every pair travelled as bytes
         sample = np.r_[0:2048, n - 2048:n, np.arange(0, n, 1009)]
         assert np.array_equal(plain[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
         for t in (1, 5):

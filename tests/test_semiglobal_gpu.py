@@ -230,3 +230,24 @@ def test_all_visible_gpus_share_a_batch(swb, oracle):
         assert c.n_devices == g
         r = c.semiglobal_xdrop(a, b)
     check_against_oracle(oracle, r, a, b, list(range(0, n, 7)) + list(range(n - 40, n)))
+
+
+def test_score_only_calls_allocate_no_round_record_scratch(swb):
+    # A score-only call (ops == NULL) runs the RECORD = false forward kernel, which never touches the round records:
+    # on a FRESH context neither the host entry nor the device entry may allocate that scratch (512 KiB per pair at
+    # 16384 bases -- 2 GiB for this batch, per slot).  Device memory in use may grow by the input staging only (~0.7 GiB).
+    import torch
+    n, length = 4096, 16384
+    a, b = swb.related_pairs(0, n, length)
+    with swb.Context(n_devices=1) as c:
+        torch.cuda.synchronize()
+        free0, _ = torch.cuda.mem_get_info()
+        s = c.semiglobal_xdrop(a, b, traceback=False)
+        da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        out = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(3)]
+        c.semiglobal_xdrop_device(da, db, out[0], out[1], out[2])
+        torch.cuda.synchronize()
+        free1, _ = torch.cuda.mem_get_info()
+        assert np.array_equal(out[0].cpu().numpy(), s["score"])
+        used = free0 - free1
+        assert used < (3 << 29), f"{used / 2**20:.0f} MiB taken by a score-only batch: the round-record scratch was allocated"
