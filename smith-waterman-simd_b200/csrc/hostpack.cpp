@@ -7,6 +7,7 @@
 // Codes are masked to two bits (a code above 3 is the caller's error, include/swb200.h).
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #if defined(__x86_64__)
@@ -76,8 +77,11 @@ static void pack2bit_avx2_body(const uint8_t* codes, uint8_t* packed, size_t n_c
 
 static void pack2bit_avx2(const uint8_t* codes, uint8_t* packed, size_t n_codes)
 {
-    // non-temporal stores only for buffers big enough that the cache could not hold them anyway
-    if ((((uintptr_t)packed) & 31u) == 0 && n_codes >= (1u << 16)) pack2bit_avx2_body<true>(codes, packed, n_codes);
+    // non-temporal stores only for buffers big enough that the cache could not hold them anyway.
+    // SWB200_PACK_STREAM=0 keeps plain stores (tuning knob: a small pinned staging ring then stays in the core's L2, where
+    // the DMA engine's reads can be served without a trip to DRAM).
+    static const bool stream = [] { const char* e = getenv("SWB200_PACK_STREAM"); return !(e && e[0] == '0'); }();
+    if (stream && (((uintptr_t)packed) & 31u) == 0 && n_codes >= (1u << 16)) pack2bit_avx2_body<true>(codes, packed, n_codes);
     else pack2bit_avx2_body<false>(codes, packed, n_codes);
 }
 #endif

@@ -44,18 +44,26 @@ struct FeedArgs {
     const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine
     uint32_t* next_item;            // work counter, zeroed before the launch (stream-ordered)
     volatile uint32_t* status;      // mapped pinned host word: FEED_STATUS_*
-    const volatile uint32_t* abort; // mapped pinned host word: non-zero = give up
+    const volatile uint32_t* abort; // device word the host sets after a failed enqueue: non-zero = give up
     unsigned long long timeout_ns;
     uint32_t n;                     // pairs in this epoch
     uint32_t epoch;                 // flags of this launch are >= 2*epoch
     uint32_t scores_vec2;           // 1: scores is 8-byte aligned (int2 stores)
 };
 
-__device__ __forceinline__ uint32_t feed_ld_acquire(const uint32_t* p)
+// The flag is polled with a RELAXED system-scope load (one LDG.E.STRONG.SYS, served by L2 where the copy engine's
+// write lands).  An acquire load would be followed by CCTL.IVALL -- the whole SM's L1 invalidated on every poll, under
+// the feet of the five other blocks that are scoring -- so the acquire is a single fence once the flag has been seen.
+__device__ __forceinline__ uint32_t feed_ld_flag(const uint32_t* p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void feed_acquire_fence()
+{
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
 __device__ __forceinline__ unsigned long long feed_now_ns()
@@ -114,20 +122,22 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
             uint32_t fmt = 0xffffffffu;                    // "leave"
             if (item < n_items) {
                 const uint32_t* flag = fa.ready + item / FEED_ITEMS_PER_TILE;
-                uint32_t v = feed_ld_acquire(flag);
+                uint32_t v = feed_ld_flag(flag);
                 if (v < want || v > want + 1u) {           // not landed yet (a flag of an older epoch is smaller)
                     const unsigned long long t0 = feed_now_ns();
-                    unsigned spins = 0;
+                    unsigned spins = 0, nap = 100;
                     for (;;) {
-                        __nanosleep(100);
-                        v = feed_ld_acquire(flag);
+                        __nanosleep(nap);
+                        if (nap < 1600) nap *= 2;          // back off: hundreds of blocks may be waiting when the link is the bottleneck
+                        v = feed_ld_flag(flag);
                         if (v >= want && v <= want + 1u) break;
-                        if ((++spins & 255u) == 0u) {
+                        if ((++spins & 63u) == 0u) {
                             if (*fa.abort) { *fa.status = FEED_STATUS_ABORTED; v = 0xffffffffu; break; }
                             if (feed_now_ns() - t0 > fa.timeout_ns) { *fa.status = FEED_STATUS_TIMEOUT; v = 0xffffffffu; break; }
                         }
                     }
                 }
+                feed_acquire_fence();                      // the tile's bytes were written before its flag
                 fmt = (v == 0xffffffffu) ? v : (v - want);
                 if (fmt == 0xffffffffu) atomicAdd(fa.next_item, 0x40000000u);   // every later claim is past the end: all blocks leave
             }

@@ -1,0 +1,30 @@
+#!/bin/bash
+# One GPU lease = one call of this script under gpurun; every step runs under its own `timeout`, writes into gpurun_out/
+# and never stops the ones after it.   usage: tools/gpu_session.sh <tag> <step> [<step> ...]
+tag=$1; shift
+out=gpurun_out/$tag
+mkdir -p "$out"
+export SWB200_FEED_TIMEOUT_MS=${SWB200_FEED_TIMEOUT_MS:-8000}
+{ nvidia-smi -L; nproc; free -g | head -2; numactl -H 2>/dev/null | head -3; nvidia-smi topo -m 2>/dev/null | head -12; } > "$out/box.txt" 2>&1
+for step in "$@"; do
+  t0=$(date +%s)
+  case $step in
+    smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1 ;;
+    parity)   timeout 1200 python -m pytest tests/test_parity_gpu.py -x -q -m gpu > "$out/parity.log" 2>&1 ;;
+    gputests) timeout 2400 python -m pytest tests -x -q -m gpu > "$out/gputests.log" 2>&1 ;;
+    bench)    timeout 900 python bench.py > "$out/bench.json" 2> "$out/bench.err" ;;
+    benchq)   timeout 300 python bench.py --quick --no-cpu-baseline --steps 10 > "$out/benchq.json" 2> "$out/benchq.err" ;;
+    benchq_plain) SWB200_PACK_STREAM=0 timeout 300 python bench.py --quick --no-cpu-baseline --steps 10 > "$out/benchq_plainstores.json" 2> "$out/benchq_plainstores.err" ;;
+    refarm)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$out/reference_arm.json" 2> "$out/reference_arm.err" ;;
+    kbench)   timeout 120 tools/kbench > "$out/kbench.jsonl" 2>&1 ;;
+    bench2|bench4|bench8)
+              n=${step#bench}
+              timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n > "$out/bench_n$n.json" 2> "$out/bench_n$n.err" ;;
+    ncu_launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/ncu_launches.csv" python bench.py --quick --no-cpu-baseline --steps 3 --warmup 3 > "$out/ncu_launches.out" 2>&1 ;;
+    ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:sw_kernel -s 3 -c 1 -o "$out/ncu_full_sw_kernel" python bench.py --quick --no-cpu-baseline --steps 3 --warmup 3 > "$out/ncu_full.out" 2>&1
+              timeout 900 ncu --set full --clock-control none --import-source on -k regex:sw_feed_kernel -s 2 -c 1 -o "$out/ncu_full_sw_feed_kernel" python bench.py --quick --no-cpu-baseline --steps 3 --warmup 3 >> "$out/ncu_full.out" 2>&1 ;;
+    *) echo "unknown step $step" ;;
+  esac
+  echo "$step rc=$? $(( $(date +%s) - t0 )) s" | tee -a "$out/steps.txt"
+done
+tail -n 3 "$out"/*.log 2>/dev/null | tail -n 40
