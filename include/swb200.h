@@ -139,8 +139,9 @@ int swb200_score_batch_device(swb200_ctx* ctx, int device_index,
                               const uint8_t* d_seq1, const uint8_t* d_seq2,
                               const int8_t* score_matrix, int8_t gap_penalty,
                               int32_t* d_scores, uint64_t n, void* cuda_stream);
-/* The packed form expands chunk by chunk into the context's own byte staging (stream-ordered with the
- * other users of that staging: a later host batch or a call on another stream waits for this one). */
+/* The packed form is ONE launch per 2 M pairs of the persistent consumer kernel: a block expands its own 128 pairs
+ * into the context's byte staging (L2-resident) and scores them.  Calls on different streams share that staging:
+ * a later call waits, on the device, for the earlier one. */
 int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index,
                                      const uint8_t* d_seq1_packed, const uint8_t* d_seq2_packed,
                                      const int8_t* score_matrix, int8_t gap_penalty,

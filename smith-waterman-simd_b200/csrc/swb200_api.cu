@@ -692,25 +692,10 @@ int swb200_score_batch_packed_device(swb200_ctx* ctx, int device_index, const ui
     Device* d = ctx->devs[device_index];
     std::lock_guard<std::mutex> lock(d->mu);
     SWB_CUDA(ctx, cudaSetDevice(d->id));
-    rc = ensure_staging(ctx, d, false);
-    if (rc != SWB200_OK) return rc;
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general);
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    // Stream-ordered: unpack a chunk into slot 0's byte staging, score it, next chunk.
-    // The staging is shared with the host-batch pipeline and with calls on other streams, and this call returns
-    // before its kernels have run: whoever uses slot 0 next waits on `done` (run_range does so through `busy`).
-    Slot& s = d->slots[0];
-    if (s.busy) SWB_CUDA(ctx, cudaStreamWaitEvent(st, s.done, 0));
-    for (uint64_t c0 = 0; c0 < n; c0 += d->chunk_pairs) {
-        const uint64_t m = (n - c0 < d->chunk_pairs) ? n - c0 : d->chunk_pairs;
-        SWB_CUDA(ctx, launch_unpack(d_pk1 + c0 * 32, s.d_seq1, m, st));
-        SWB_CUDA(ctx, launch_unpack(d_pk2 + c0 * 32, s.d_seq2, m, st));
-        SWB_CUDA(ctx, launch_for(prm, SWB200_SEQ_LEN, s.d_seq1, s.d_seq2, d_scores + c0, m, st));
-        ctx->launches += 3;
-    }
-    SWB_CUDA(ctx, cudaEventRecord(s.done, st));
-    s.busy = true;
-    return SWB200_OK;
+    // The persistent consumer kernel with every tile flag already set: a block expands its own 128 pairs into the
+    // context's byte staging (L2-resident) and scores them -- one launch per 2 M pairs, stream-ordered on the caller's stream.
+    return feed_packed_resident(ctx, d, d_pk1, d_pk2, prm, d_scores, n, (cudaStream_t)cuda_stream);
 }
 
 int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_t* d_codes, uint64_t n_bytes,

@@ -15,6 +15,8 @@ for step in "$@"; do
     bench)    timeout 900 python bench.py > "$out/bench.json" 2> "$out/bench.err" ;;
     benchq)   timeout 300 python bench.py --quick --no-cpu-baseline --steps 10 > "$out/benchq.json" 2> "$out/benchq.err" ;;
     benchq_plain) SWB200_PACK_STREAM=0 timeout 300 python bench.py --quick --no-cpu-baseline --steps 10 > "$out/benchq_plainstores.json" 2> "$out/benchq_plainstores.err" ;;
+    benchq_tl) SWB200_FEED_TIMELINE=1 timeout 300 python bench.py --quick --no-cpu-baseline --steps 6 > "$out/benchq_timeline.json" 2> "$out/benchq_timeline.err" ;;
+    benchq_big) SWB200_FEED_FIRST_TILES=8 SWB200_FEED_TIMELINE=1 timeout 300 python bench.py --quick --no-cpu-baseline --steps 6 > "$out/benchq_first8.json" 2> "$out/benchq_first8.err" ;;
     refarm)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$out/reference_arm.json" 2> "$out/reference_arm.err" ;;
     kbench)   timeout 120 tools/kbench > "$out/kbench.jsonl" 2>&1 ;;
     bench2|bench4|bench8)
