@@ -33,6 +33,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before torch creates the CUDA context: see smith-waterman-simd_b200/swb200.py
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "smith-waterman-simd_b200")
 for p in (ROOT, PKG):
@@ -312,64 +314,81 @@ def timed_host_calls(R: "Ranks", fn, steps: int, warmup: int = 3):
     return R.max(1e3 * (time.perf_counter() - t0) / steps)
 
 
-def leg_host_ceiling(R: "Ranks", swb200, pa, cpus: int) -> dict:
+HOST_PROBE_MB = 1024
+
+
+def leg_host_ceiling(R: "Ranks", swb200, cpus: int) -> dict:
     """What the HOST can deliver, all ranks at once: (a) pinned H2D copies alone, (b) the cores' streaming reads alone,
     (c) both together.  A byte-coded batch has to leave host DRAM once -- read by a core that packs it or by the DMA
     engine -- so (c) / 256 B is the roofline of the end-to-end number for byte-coded input and (a) / 64 B that of the
-    2-bit wire format.  Aggregates are sums over ranks of bytes / the slowest rank's time."""
+    2-bit wire format.  The probe buffer (1 GiB of pinned memory per rank) is larger than any last-level cache, and every
+    phase runs for a few hundred milliseconds.  Aggregates are sums over ranks of bytes / the slowest rank's time."""
     torch = R.torch
-    src = torch.from_numpy(pa.array)           # pinned (cudaHostAlloc): the copy below is a plain DMA
-    dst = torch.empty(src.shape, dtype=torch.uint8, device="cuda")
-    nbytes = src.numel()
+    probe_mb = HOST_PROBE_MB
+    buf = swb200.PinnedArray((probe_mb << 20,), np.uint8)
+    buf.array[:] = 1                           # first touch on this rank's cores
+    src = torch.from_numpy(buf.array)          # pinned (cudaHostAlloc): the copies below are plain DMA
+    piece = min(256, probe_mb // 2) << 20
+    dst = torch.empty(piece, dtype=torch.uint8, device="cuda")
+    n_piece = src.numel() // piece
     stream = torch.cuda.current_stream()
 
     def dma(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(reps):
-            dst.copy_(src, non_blocking=True)
+        for k in range(reps):
+            dst.copy_(src[(k % n_piece) * piece:(k % n_piece + 1) * piece], non_blocking=True)
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e-3
     dma(2)
     R.barrier()
-    reps = 8
+    reps = 3 * n_piece                                         # 3 GiB: ~60 ms per rank alone, longer when the ranks share the host
     t = R.max(dma(reps))
-    h2d = R.sum(nbytes * reps) / t / 1e9
-    swb200.host_read_bandwidth(pa.array, cpus, 1)
+    h2d = R.sum(piece * reps) / t / 1e9
+    rate = swb200.host_read_bandwidth(buf.array, cpus, 1)       # one pass: warms nothing (1 GiB), gives the pass count for ~0.3 s
+    passes = max(2, int(R.max(0.3 * rate / buf.nbytes)) + 1)    # the same count on every rank
     R.barrier()
-    passes = 6
     t0 = time.perf_counter()
-    swb200.host_read_bandwidth(pa.array, cpus, passes)
+    swb200.host_read_bandwidth(buf.array, cpus, passes)
     t = R.max(time.perf_counter() - t0)
-    cpu_read = R.sum(nbytes * passes) / t / 1e9
+    cpu_read = R.sum(buf.nbytes * passes) / t / 1e9
     # both at once: the DMA loop runs on a second thread until the cores have finished their passes
     stop = threading.Event()
+    ready = threading.Event()
     copied = [0]
 
     def dma_loop():
         torch.cuda.set_device(R.local_rank)
         s2 = torch.cuda.Stream()
         with torch.cuda.stream(s2):
+            k = 0
+            ready.set()
             while not stop.is_set():
-                dst.copy_(src, non_blocking=True)
+                dst.copy_(src[(k % n_piece) * piece:(k % n_piece + 1) * piece], non_blocking=True)
                 s2.synchronize()
-                copied[0] += nbytes
-    R.barrier()
+                copied[0] += piece
+                k += 1
     th = threading.Thread(target=dma_loop)
-    t0 = time.perf_counter()
     th.start()
-    swb200.host_read_bandwidth(pa.array, max(1, cpus - 1), passes)
+    ready.wait()
+    R.barrier()
+    c0 = copied[0]
+    t0 = time.perf_counter()
+    swb200.host_read_bandwidth(buf.array, max(1, cpus - 1), passes)
     dt = time.perf_counter() - t0
+    c1 = copied[0]
     stop.set()
     th.join()
-    both = R.sum(nbytes * passes + copied[0]) / R.max(dt) / 1e9
-    both_dma = R.sum(copied[0]) / R.max(dt) / 1e9
-    del dst
+    tmax = R.max(dt)
+    both = R.sum(buf.nbytes * passes + (c1 - c0)) / tmax / 1e9
+    both_dma = R.sum(c1 - c0) / tmax / 1e9
+    del dst, src
+    buf.free()
     return {"h2d_pinned_gbs": h2d, "host_read_gbs": cpu_read, "h2d_and_read_together_gbs": both, "h2d_share_of_together_gbs": both_dma,
-            "threads_per_rank": cpus, "buffer_mb_per_rank": nbytes / 1e6,
-            "how": "all ranks at once between barriers; sum of bytes over ranks / slowest rank's time: torch pinned->device copies (CUDA events), "
-                   "swb200_host_read_bandwidth (AVX2 streaming reads, all of the rank's cores), then both concurrently"}
+            "threads_per_rank": cpus, "buffer_mb_per_rank": probe_mb, "read_passes": passes,
+            "how": "all ranks at once between barriers; sum of bytes over ranks / slowest rank's time: torch pinned->device copies of 256 MiB slices "
+                   "(CUDA events), swb200_host_read_bandwidth (AVX2 streaming reads on all of the rank's cores), then both concurrently"}
 
 
 def ceiling_gcups(bytes_per_s_g: float, bytes_per_pair: float) -> float:
@@ -494,10 +513,21 @@ def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
     for _ in range(calls):
         pass
     loop_overhead = time.perf_counter() - t1
-    return {"us_per_call": 1e6 * dt / calls, "ms_per_1M_calls": 1e3 * dt / calls * 1e6, "calls": calls, "score": int(out[0]), "score_expected": 80,
-            "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
-            "api": "swb200_score_pair: the pair rides in the launch parameters of a one-warp-per-pair kernel; the result is a tagged word in mapped pinned memory the call spins on",
-            "shape": "SpeedTest (source.cpp:3036-3054): one fixed pair, repeated calls"}
+    res = {"us_per_call": 1e6 * dt / calls, "ms_per_1M_calls": 1e3 * dt / calls * 1e6, "calls": calls, "score": int(out[0]), "score_expected": 80,
+           "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
+           "timed_from": "a Python loop of direct ctypes calls of swb200_score_pair",
+           "api": "swb200_score_pair: the pair rides in the launch parameters of a one-warp-per-pair kernel; the result is a tagged word in mapped pinned memory the call spins on",
+           "shape": "SpeedTest (source.cpp:3036-3054): one fixed pair, repeated calls"}
+    # the same loop in C++ (tools/speedtest_b200.cu, built by __graft_entry__.build()): no interpreter in the timed region,
+    # and beside it the floor of any per-call GPU path on this box (empty kernel + tagged mapped word + spin)
+    exe = os.path.join(ROOT, "tools", "speedtest_b200")
+    if os.path.exists(exe):
+        try:
+            p = subprocess.run([exe, "20000"], capture_output=True, text=True, timeout=120)
+            res["cpp_loop"] = json.loads(p.stdout.strip().splitlines()[-1])
+        except Exception as ex:
+            res["cpp_loop"] = {"error": f"{type(ex).__name__}: {ex}"}
+    return res
 
 
 def leg_sweep(R: "Ranks", swb200, ctx, matrix, gap, steps: int, peak_tinstr: float) -> list:
@@ -691,7 +721,7 @@ def run_b200_arm(args):
     host_ceiling = None
     if not args.quick:
         try:
-            host_ceiling = leg_host_ceiling(R, swb200, pa, my_cpus)
+            host_ceiling = leg_host_ceiling(R, swb200, my_cpus)
             host_ceiling["byte_input_ceiling_gcups"] = ceiling_gcups(host_ceiling["h2d_and_read_together_gbs"], 256.0)
             host_ceiling["byte_input_e2e_fraction_of_ceiling"] = e2e_gcups / host_ceiling["byte_input_ceiling_gcups"]
             host_ceiling["packed_input_pcie_ceiling_gcups"] = ceiling_gcups(host_ceiling["h2d_pinned_gbs"], 64.0)

@@ -46,6 +46,7 @@ inline uint64_t pair_word(uint64_t seed, uint64_t k, unsigned w)
 // The byte-coded stream was bound by this loop (profiles/r01/stream_100m_bytes_1gpu.json: 1.32 of 1.34 s in host
 // generation), so on x86-64 it is done in registers: the four 2-bit planes of the eight source bytes (x, x>>2, x>>4,
 // x>>6) interleaved byte-wise and then word-wise put plane k of byte i at output 4i+k; one mask at the end.
+template <bool STREAM = false>
 inline void expand32(uint64_t x, uint8_t* d)
 {
 #if defined(__SSE2__)
@@ -53,8 +54,15 @@ inline void expand32(uint64_t x, uint8_t* d)
     const __m128i p01 = _mm_unpacklo_epi8(v0, _mm_srli_epi64(v0, 2));                         // b0>>0, b0>>2, b1>>0, b1>>2, ...
     const __m128i p23 = _mm_unpacklo_epi8(_mm_srli_epi64(v0, 4), _mm_srli_epi64(v0, 6));      // b0>>4, b0>>6, b1>>4, ...
     const __m128i m3 = _mm_set1_epi8(3);
-    _mm_storeu_si128((__m128i*)d, _mm_and_si128(_mm_unpacklo_epi16(p01, p23), m3));           // source bytes 0..3 -> codes 0..15
-    _mm_storeu_si128((__m128i*)(d + 16), _mm_and_si128(_mm_unpackhi_epi16(p01, p23), m3));    // source bytes 4..7 -> codes 16..31
+    const __m128i lo = _mm_and_si128(_mm_unpacklo_epi16(p01, p23), m3);           // source bytes 0..3 -> codes 0..15
+    const __m128i hi = _mm_and_si128(_mm_unpackhi_epi16(p01, p23), m3);           // source bytes 4..7 -> codes 16..31
+    if (STREAM) {      // the consumer of a stream buffer is the DMA engine or a packing core, not this core: no read-for-ownership, no cache line
+        _mm_stream_si128((__m128i*)d, lo);
+        _mm_stream_si128((__m128i*)(d + 16), hi);
+    } else {
+        _mm_storeu_si128((__m128i*)d, lo);
+        _mm_storeu_si128((__m128i*)(d + 16), hi);
+    }
 #else
     for (int i = 0; i < 32; ++i) d[i] = (uint8_t)((x >> (2 * i)) & 3);
 #endif
@@ -89,6 +97,18 @@ void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t*
 #if defined(__x86_64__)
     static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
     if (packed && have_avx512) { gen_range_packed_avx512(seed, first, lo, hi, seq1, seq2); return; }
+#endif
+#if defined(__SSE2__)
+    // Large byte-coded ranges into 16-byte aligned arrays (the pinned ring buffers of the streaming mode) are written with
+    // non-temporal stores: round 2's 100 M-pair byte stream was bound by this loop's memory traffic (38 GB/s of stores plus
+    // as much read-for-ownership on 15 threads), and nobody reads the lines from this core's cache afterwards.
+    if (!packed && hi - lo >= 4096 && ((((uintptr_t)seq1) | ((uintptr_t)seq2)) & 15u) == 0) {
+        for (uint64_t p = lo; p < hi; ++p)
+            for (unsigned w = 0; w < 8; ++w)
+                expand32<true>(pair_word(seed, first + p, w), ((w < 4) ? seq1 : seq2) + p * 128 + (w & 3) * 32);
+        _mm_sfence();
+        return;
+    }
 #endif
     for (uint64_t p = lo; p < hi; ++p) {
         for (unsigned w = 0; w < 8; ++w) {

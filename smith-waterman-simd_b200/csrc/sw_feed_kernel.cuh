@@ -15,6 +15,14 @@
 // So a host batch is ONE kernel launch however many copies feed it, nothing waits for a whole
 // chunk, and the only exposed PCIe time is the first tile's.
 //
+// THE RULE that keeps this safe: a launch only ever waits for copies that were ENQUEUED BEFORE IT.
+// Streams are multiplexed onto a few in-order hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by
+// default); a copy enqueued behind a spinning kernel on a queue it happens to share would never
+// start, and the kernel would wait for it for ever.  Work enqueued earlier is ahead of the kernel
+// on every queue.  Input that the host produces while the GPU is already scoring (byte-coded
+// batches compressed by the PACK lanes) is therefore cut into WINDOWS, each with its own launch,
+// issued when the window's last piece has been enqueued (feed.inc).
+//
 // The wait is bounded: a block that sees no flag for `timeout_ns` (or an abort word set by the
 // host after a failed enqueue) reports through `status` and every block leaves.
 #pragma once
@@ -42,7 +50,9 @@ struct FeedArgs {
     const uint8_t* pk2;
     int32_t* scores;                // [n] device array, or mapped pinned host memory
     const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine
-    uint32_t* next_item;            // work counter, zeroed before the launch (stream-ordered)
+    uint32_t* next_item;            // this launch's work counter, zeroed before the launch (stream-ordered)
+    uint32_t first_item;            // the launch scores items [first_item, first_item + n_items) of the epoch
+    uint32_t n_items;
     volatile uint32_t* status;      // mapped pinned host word: FEED_STATUS_*
     const volatile uint32_t* abort; // device word the host sets after a failed enqueue: non-zero = give up
     unsigned long long timeout_ns;
@@ -85,17 +95,25 @@ __device__ __forceinline__ uint4 feed_expand_word(uint32_t w)
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// The block's own m pairs: m*32 packed bytes -> m*128 byte codes.
+// The block's own m pairs of one sequence array: m*32 packed bytes -> m*128 byte codes.  One 32-bit word (16 bases) per
+// thread and step, so a warp reads 128 contiguous bytes and writes 512; all 16 loads of a thread are issued before the
+// first store (the expansion is a latency chain otherwise: 9 us per item measured, 4.7 % of the kernel).
 __device__ __forceinline__ void feed_expand_item(const uint8_t* pk, uint8_t* raw, uint32_t m)
 {
-    const uint4* src = reinterpret_cast<const uint4*>(pk);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pk);
     uint4* dst = reinterpret_cast<uint4*>(raw);
-    for (uint32_t i = threadIdx.x; i < m * 2u; i += FEED_NT) {     // one uint4 = 64 bases = half a sequence
-        const uint4 v = __ldcg(src + i);
-        dst[4 * i + 0] = feed_expand_word(v.x);
-        dst[4 * i + 1] = feed_expand_word(v.y);
-        dst[4 * i + 2] = feed_expand_word(v.z);
-        dst[4 * i + 3] = feed_expand_word(v.w);
+    const uint32_t n_words = m * 8u;                                   // 8 words per sequence
+    constexpr int PER = FEED_ITEM_PAIRS * 8 / FEED_NT;                 // 16 words per thread for a full item
+    uint32_t w[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t i = threadIdx.x + (uint32_t)j * FEED_NT;
+        w[j] = (i < n_words) ? __ldcg(src + i) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t i = threadIdx.x + (uint32_t)j * FEED_NT;
+        if (i < n_words) dst[i] = feed_expand_word(w[j]);
     }
 }
 
@@ -110,7 +128,6 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
     __shared__ uint32_t s_item, s_fmt;
     if (threadIdx.x < 4) t4s[threadIdx.x] = prm.t4[threadIdx.x];
 
-    const uint32_t n_items = (fa.n + FEED_ITEM_PAIRS - 1) / FEED_ITEM_PAIRS;
     const uint32_t want = 2u * fa.epoch;
     SmemFifo<FEED_NT> fifo{smem + threadIdx.x};
     SmemTable t4{t4s};
@@ -118,9 +135,10 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
     for (;;) {
         __syncthreads();                                   // s_item / s_fmt of the previous round have been read
         if (threadIdx.x == 0) {
-            const uint32_t item = atomicAdd(fa.next_item, 1u);
+            uint32_t item = atomicAdd(fa.next_item, 1u);
             uint32_t fmt = 0xffffffffu;                    // "leave"
-            if (item < n_items) {
+            if (item < fa.n_items) {
+                item += fa.first_item;
                 const uint32_t* flag = fa.ready + item / FEED_ITEMS_PER_TILE;
                 uint32_t v = feed_ld_flag(flag);
                 if (v < want || v > want + 1u) {           // not landed yet (a flag of an older epoch is smaller)

@@ -35,6 +35,7 @@ struct PairArgs {
     uint32_t seq;                        // this call's tag
     uint32_t t4[4];                      // t4[a] = bytes S[a][0..3]
     int32_t gap;
+    uint32_t seq2_stride;                // 128, or 0: every pair against the one target at seq2 (SmithWaterman_8b111x32mark1, source.cpp:1227-1234)
     uint32_t inline_pair;                // 1: n == 1 and the pair is in inl1 / inl2
     uint32_t inl1[32], inl2[32];
 };
@@ -59,7 +60,7 @@ sw_pair_kernel(const PairArgs pa)
     if (pa.inline_pair) { aw = pa.inl1[lane]; bw = pa.inl2[lane]; }
     else {
         aw = reinterpret_cast<const uint32_t*>(pa.seq1 + (size_t)p * 128)[lane];
-        bw = reinterpret_cast<const uint32_t*>(pa.seq2 + (size_t)p * 128)[lane];
+        bw = reinterpret_cast<const uint32_t*>(pa.seq2 + (size_t)p * pa.seq2_stride)[lane];
     }
     for (int i = lane; i < PAIR_SEL_WORDS; i += 32) sel[i] = 0xCCC4u;          // byte 4 of {profile, 0x80808080}: -128
     __syncwarp();

@@ -407,8 +407,8 @@ int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool p
     if (rc == SWB200_OK) rc = check_len(ctx, sm, L);
     if (rc != SWB200_OK || n == 0) return rc;
     // A handful of pairs: the latency kernel (one warp per pair, no staging) -- the per-pair call lives here.
-    if (L == SWB200_SEQ_LEN && !packed && !shared_target && n <= kPairPathMax && ctx->latency_path && !ctx->force_general)
-        return pair_run(ctx, ctx->devs[0], seq1, seq2, sm, gap, scores, n);
+    if (L == SWB200_SEQ_LEN && !packed && n <= kPairPathMax && ctx->latency_path && !ctx->force_general)
+        return pair_run(ctx, ctx->devs[0], seq1, seq2, sm, gap, scores, n, shared_target);
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
     // Batches of the reference shape go through the persistent-kernel packer (feed.inc); byte-coded ones with the host

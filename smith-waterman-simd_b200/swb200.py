@@ -15,6 +15,12 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+# Streams are multiplexed onto this many in-order hardware queues (default 8).  The batch packer uses a stream per PACK
+# lane plus kernel / copy streams per staging region; with more queues fewer of them share one, so copies and the
+# consumer kernel overlap as intended.  (Correctness never depends on it -- see csrc/sw_feed_kernel.cuh -- and the
+# variable only takes effect if it is set before the process creates its CUDA context.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libswb200.so")
 SEQ_LEN = 128

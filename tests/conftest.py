@@ -5,6 +5,8 @@ import sys
 import numpy as np
 import pytest
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context exists: see smith-waterman-simd_b200/swb200.py
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "smith-waterman-simd_b200")
 for p in (ROOT, PKG):

@@ -36,6 +36,7 @@ class _Stream:
 class _FakePinned:
     def __init__(self, shape, dtype):
         self.array = np.zeros(shape, dtype)
+        self.nbytes = self.array.nbytes
 
     def free(self):
         pass
@@ -162,6 +163,7 @@ def bench(monkeypatch, oracle):
     monkeypatch.setattr(swb200, "Context", _fake_context_class(oracle, swb200))
     monkeypatch.setattr(swb200, "PinnedArray", _FakePinned)
     monkeypatch.setattr(mod, "PAIRS_PER_GPU", 3000)
+    monkeypatch.setattr(mod, "HOST_PROBE_MB", 8)
     mod.real_sweep_pairs = mod.sweep_pairs
     monkeypatch.setattr(mod, "sweep_pairs", lambda L, info: 64)       # the default line carries the sweep: keep the oracle's share small
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
@@ -191,6 +193,7 @@ def test_b200_arm_assembles_its_line(bench):
     assert line["per_pair"]["score"] == 80 and line["per_pair"]["us_per_call"] > 0 and line["per_pair"]["gpu_launches_per_call"] == 1
     assert line["stream"]["packed"]["pairs"] == 5000 and line["stream"]["bytes"]["score_sum"] == line["stream"]["packed"]["score_sum"]
     hc = line["host_ceiling"]
+    assert "error" not in hc, hc
     assert hc["h2d_pinned_gbs"] > 0 and hc["host_read_gbs"] > 0 and hc["byte_input_ceiling_gcups"] > 0
     assert line["e2e_inproc"] is None and line["e2e"]["packed_input"]["gpu_launches_per_step"] > 0
     assert line["verified"]["other_ranks_score_sums_equal_reference"] is None           # one rank
@@ -274,6 +277,7 @@ def _two_rank_worker(rank, world, port, out_path):
     swb200.bind_to_gpu_numa_node = lambda *a, **k: None
     swb200.bind_rank_cpus = lambda lr, lw, device_index=None: {"before": sorted(os.sched_getaffinity(0)), "numa": None, "cpus": 2, "share": [lr, lr]}
     mod.PAIRS_PER_GPU = 1500
+    mod.HOST_PROBE_MB = 8
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         mod.run_b200_arm(_args())
