@@ -50,7 +50,8 @@ struct FeedArgs {
     const uint8_t* pk2;
     int32_t* scores;                // [n] device array, or mapped pinned host memory
     const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine
-    uint32_t* next_item;            // this launch's work counter, zeroed before the launch (stream-ordered)
+    uint32_t* next_item;            // this launch's work counter: never reset, the host knows where it stands ...
+    uint32_t item_base;             // ... before this launch (a launch of n items on g blocks adds exactly n + g)
     uint32_t first_item;            // the launch scores items [first_item, first_item + n_items) of the epoch
     uint32_t n_items;
     volatile uint32_t* status;      // mapped pinned host word: FEED_STATUS_*
@@ -135,7 +136,7 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
     for (;;) {
         __syncthreads();                                   // s_item / s_fmt of the previous round have been read
         if (threadIdx.x == 0) {
-            uint32_t item = atomicAdd(fa.next_item, 1u);
+            uint32_t item = atomicAdd(fa.next_item, 1u) - fa.item_base;
             uint32_t fmt = 0xffffffffu;                    // "leave"
             if (item < fa.n_items) {
                 item += fa.first_item;

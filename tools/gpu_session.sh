@@ -17,6 +17,13 @@ for step in "$@"; do
     benchq_plain) SWB200_PACK_STREAM=0 timeout 300 python bench.py --quick --no-cpu-baseline --steps 10 > "$out/benchq_plainstores.json" 2> "$out/benchq_plainstores.err" ;;
     benchq_tl) SWB200_FEED_TIMELINE=1 timeout 300 python bench.py --quick --no-cpu-baseline --steps 6 > "$out/benchq_timeline.json" 2> "$out/benchq_timeline.err" ;;
     benchq_big) SWB200_FEED_FIRST_TILES=8 SWB200_FEED_TIMELINE=1 timeout 300 python bench.py --quick --no-cpu-baseline --steps 6 > "$out/benchq_first8.json" 2> "$out/benchq_first8.err" ;;
+    lanes_matrix)
+              for cfg in "2 15" "4 15" "8 15" "2 7" "4 7" "2 11"; do set -- $cfg
+                echo "== lane tiles $1, pack threads $2" >> "$out/lanes_matrix.txt"
+                SWB200_FEED_LANE_TILES=$1 SWB200_FEED_TIMELINE=1 timeout 200 python bench.py --quick --no-cpu-baseline --no-plain-e2e --steps 6 --pack-threads $2 2>&1 >/dev/null | grep timeline | sed -n '6,8p' >> "$out/lanes_matrix.txt"
+              done
+              echo "== plain stores" >> "$out/lanes_matrix.txt"
+              SWB200_PACK_STREAM=0 SWB200_FEED_TIMELINE=1 timeout 200 python bench.py --quick --no-cpu-baseline --no-plain-e2e --steps 6 2>&1 >/dev/null | grep timeline | sed -n '6,8p' >> "$out/lanes_matrix.txt" ;;
     refarm)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$out/reference_arm.json" 2> "$out/reference_arm.err" ;;
     kbench)   timeout 120 tools/kbench > "$out/kbench.jsonl" 2>&1 ;;
     bench2|bench4|bench8)
