@@ -60,6 +60,9 @@ struct FeedArgs {
     uint32_t n;                     // pairs in this epoch
     uint32_t epoch;                 // flags of this launch are >= 2*epoch
     uint32_t scores_vec2;           // 1: scores is 8-byte aligned (int2 stores)
+    uint32_t all_there;             // 1: every tile was complete before the launch (device-resident input, or 2-bit input the
+                                    //    blocks pull straight from the caller's pinned arrays): no flags, no fence; format = fmt_all
+    uint32_t fmt_all;
 };
 
 // The flag is polled with a RELAXED system-scope load (one LDG.E.STRONG.SYS, served by L2 where the copy engine's
@@ -138,7 +141,10 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
         if (threadIdx.x == 0) {
             uint32_t item = atomicAdd(fa.next_item, 1u) - fa.item_base;
             uint32_t fmt = 0xffffffffu;                    // "leave"
-            if (item < fa.n_items) {
+            if (item < fa.n_items && fa.all_there) {
+                item += fa.first_item;
+                fmt = fa.fmt_all;
+            } else if (item < fa.n_items) {
                 item += fa.first_item;
                 const uint32_t* flag = fa.ready + item / FEED_ITEMS_PER_TILE;
                 uint32_t v = feed_ld_flag(flag);
@@ -183,6 +189,43 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
             if (two && fa.scores_vec2) *reinterpret_cast<int2*>(fa.scores + p) = make_int2(lo, hi);
             else { fa.scores[p] = lo; if (two) fa.scores[p + 1] = hi; }
         }
+    }
+}
+
+// The RELAY of a laned epoch: one warp that mirrors tile flags the host's PACK lanes set with plain CPU stores (in mapped
+// pinned memory) into the device flag array the consumer blocks poll -- so that hundreds of waiting blocks poll L2, and
+// only this warp polls across PCIe.  A host flag holds 2*epoch + format once the tile's 2-bit bytes are in the pinned
+// staging (the consumer pulls them over PCIe), or 2*epoch + FEED_FMT_BY_DMA when the RAW lane has enqueued the tile's
+// copies (the copy engine then writes the device flag itself).  The warp leaves when every tile has been accounted for.
+constexpr uint32_t FEED_FMT_BY_DMA = 2;
+
+__global__ void __launch_bounds__(32) feed_relay_kernel(const uint32_t* h_flags, uint32_t* d_flags, uint32_t n_tiles, uint32_t epoch,
+                                                         const volatile uint32_t* abort, unsigned long long timeout_ns)
+{
+    const uint32_t want = 2u * epoch;
+    const unsigned long long t0 = feed_now_ns();
+    uint32_t done_mask_lo = 0;                       // bit j: tile lane + 32*j accounted for (n_tiles <= 32 * 32 * ... see loop)
+    unsigned spins = 0;
+    for (;;) {
+        bool all = true;
+        for (uint32_t j = 0, t = threadIdx.x; t < n_tiles; ++j, t += 32) {
+            if (j < 32 && (done_mask_lo >> j) & 1u) continue;
+            const uint32_t v = feed_ld_flag(h_flags + t);                  // a PCIe read of host memory
+            if (v >= want && v <= want + FEED_FMT_BY_DMA) {
+                if (v != want + FEED_FMT_BY_DMA) {
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(d_flags + t), "r"(v) : "memory");
+                }
+                if (j < 32) done_mask_lo |= 1u << j;
+            } else {
+                all = false;
+            }
+        }
+        if (__all_sync(0xffffffffu, all)) return;
+        if ((++spins & 127u) == 0u) {
+            if (*abort) return;
+            if (feed_now_ns() - t0 > 4ull * timeout_ns) return;            // the consumers report the timeout
+        }
+        __nanosleep(500);
     }
 }
 

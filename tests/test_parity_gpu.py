@@ -151,6 +151,26 @@ def test_ragged_batches_through_the_persistent_kernel(ctx, swb, oracle, n, packe
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [8192, 40_001, 300_007])
+def test_pinned_2bit_input_is_pulled_by_the_kernel(ctx, swb, oracle, n):
+    # 2-bit input in PINNED arrays: no copy at all, the blocks load their pairs across PCIe themselves (one launch);
+    # also from a row offset into the pinned arrays (the pointers are then interior to the allocation)
+    a, b = swb.counter_pairs(31_000_000, n + 5)
+    ka, kb = swb.PinnedArray((n + 5, 32), np.uint8), swb.PinnedArray((n + 5, 32), np.uint8)
+    ka.array[...] = oracle.pack2bit(a)
+    kb.array[...] = oracle.pack2bit(b)
+    out = swb.PinnedArray((n,), np.int32)
+    want = oracle.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15, threads=NCPU)
+    for off in (0, 5):
+        out.array[:] = -1
+        l0 = ctx.launch_count
+        ctx.score_batch(ka.array[off:off + n], kb.array[off:off + n], swb.MATRIX_SPEEDTEST, 15, out=out.array, packed=True)
+        assert ctx.launch_count - l0 == 1
+        assert np.array_equal(out.array, want[off:off + n]), off
+    for p in (ka, kb, out):
+        p.free()
+
+
 def test_persistent_kernel_scores_into_an_unaligned_pinned_slice(ctx, swb, oracle):
     # pinned arrays: the kernel stores scores straight into host memory; an odd offset takes the 4-byte store form
     n = 20_000

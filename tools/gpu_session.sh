@@ -24,6 +24,7 @@ for step in "$@"; do
               done
               echo "== plain stores" >> "$out/lanes_matrix.txt"
               SWB200_PACK_STREAM=0 SWB200_FEED_TIMELINE=1 timeout 200 python bench.py --quick --no-cpu-baseline --no-plain-e2e --steps 6 2>&1 >/dev/null | grep timeline | sed -n '6,8p' >> "$out/lanes_matrix.txt" ;;
+    zcprobe)  timeout 200 python tools/zero_copy_probe.py > "$out/zero_copy_probe.json" 2> "$out/zero_copy_probe.err" ;;
     refarm)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$out/reference_arm.json" 2> "$out/reference_arm.err" ;;
     kbench)   timeout 120 tools/kbench > "$out/kbench.jsonl" 2>&1 ;;
     bench2|bench4|bench8)
