@@ -72,6 +72,7 @@ inline void expand32(uint64_t x, uint8_t* d)
 // The packed stream is 64 raw bytes per pair -- its eight splitmix64 draws -- so with AVX-512 (64-bit lane multiply,
 // vpmullq) one vector computes a whole pair: lanes 0..3 are seq1's 32 packed bytes, lanes 4..7 seq2's.  Eight GPUs
 // consume about 3.4 G packed pairs/s; the scalar loop gives 46 M pairs/s per thread.
+template <bool STREAM>
 __attribute__((target("avx512f,avx512dq")))
 void gen_range_packed_avx512(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t* seq1, uint8_t* seq2)
 {
@@ -86,9 +87,15 @@ void gen_range_packed_avx512(uint64_t seed, uint64_t first, uint64_t lo, uint64_
         x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 30)), m1);
         x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 27)), m2);
         x = _mm512_xor_si512(x, _mm512_srli_epi64(x, 31));
-        _mm256_storeu_si256((__m256i*)(seq1 + p * 32), _mm512_castsi512_si256(x));
-        _mm256_storeu_si256((__m256i*)(seq2 + p * 32), _mm512_extracti64x4_epi64(x, 1));
+        if (STREAM) {      // large ranges into aligned (pinned) buffers: nobody reads them from this core's cache, see gen_range
+            _mm256_stream_si256((__m256i*)(seq1 + p * 32), _mm512_castsi512_si256(x));
+            _mm256_stream_si256((__m256i*)(seq2 + p * 32), _mm512_extracti64x4_epi64(x, 1));
+        } else {
+            _mm256_storeu_si256((__m256i*)(seq1 + p * 32), _mm512_castsi512_si256(x));
+            _mm256_storeu_si256((__m256i*)(seq2 + p * 32), _mm512_extracti64x4_epi64(x, 1));
+        }
     }
+    if (STREAM) _mm_sfence();
 }
 #endif
 
@@ -96,7 +103,11 @@ void gen_range(uint64_t seed, uint64_t first, uint64_t lo, uint64_t hi, uint8_t*
 {
 #if defined(__x86_64__)
     static const bool have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512dq");
-    if (packed && have_avx512) { gen_range_packed_avx512(seed, first, lo, hi, seq1, seq2); return; }
+    if (packed && have_avx512) {
+        if (hi - lo >= 4096 && ((((uintptr_t)seq1) | ((uintptr_t)seq2)) & 31u) == 0) gen_range_packed_avx512<true>(seed, first, lo, hi, seq1, seq2);
+        else gen_range_packed_avx512<false>(seed, first, lo, hi, seq1, seq2);
+        return;
+    }
 #endif
 #if defined(__SSE2__)
     // Large byte-coded ranges into 16-byte aligned arrays (the pinned ring buffers of the streaming mode) are written with

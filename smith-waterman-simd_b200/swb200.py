@@ -42,7 +42,7 @@ ABI_SYMBOLS = (
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
     "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
-    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak",
+    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak", "swb200_host_pack_tuning",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -149,6 +149,8 @@ def load_library():
     lib.swb200_set_host_pack_threads.argtypes = [vp, i32]
     lib.swb200_host_pack_stats.restype = i32
     lib.swb200_host_pack_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
+    lib.swb200_host_pack_tuning.restype = i32
+    lib.swb200_host_pack_tuning.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double)]
     lib.swb200_pack2bit_host.restype = i32
     lib.swb200_pack2bit_host.argtypes = [vp, vp, u64]
     _lib = lib
@@ -251,6 +253,13 @@ class Context:
         p, r, t = C.c_uint64(), C.c_uint64(), C.c_int()
         self._check(self._lib.swb200_host_pack_stats(self._h, C.byref(p), C.byref(r), C.byref(t)))
         return {"packed_pairs": int(p.value), "raw_pairs": int(r.value), "pack_threads_per_gpu": int(t.value)}
+
+    def host_pack_tuning(self, device_index: int = 0) -> dict:
+        """The auto-tuner of the PACK-lane count: lanes it currently prefers, and the pairs/s it saw with all / half / none."""
+        lanes = C.c_int()
+        rates = (C.c_double * 3)()
+        self._check(self._lib.swb200_host_pack_tuning(self._h, device_index, C.byref(lanes), rates))
+        return {"lanes_in_use": int(lanes.value), "pairs_per_s": {"all_lanes": rates[0], "half": rates[1], "none": rates[2]}}
 
     def set_force_general(self, on: bool):
         self._check(self._lib.swb200_set_force_general(self._h, int(on)))

@@ -131,6 +131,9 @@ def _fake_context_class(oracle, swb200):
         def set_host_pack_threads(self, t):
             self._pack = 5 if t < 0 else t
 
+        def host_pack_tuning(self, device_index=0):
+            return {"lanes_in_use": self._pack, "pairs_per_s": {"all_lanes": 1.0, "half": 0.5, "none": 0.25}}
+
         def measure_alu_peak(self, device_index=0, target_ms=50.0):
             return {"tinstr_per_s": 18.4, "elapsed_ms": target_ms}
 
