@@ -49,7 +49,8 @@ struct FeedArgs {
     const uint8_t* pk1;             // [cap][32] 2-bit staging (device)
     const uint8_t* pk2;
     int32_t* scores;                // [n] device array, or mapped pinned host memory
-    const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine
+    const uint32_t* ready;          // [ceil(n / 4096)] tile flags, written by the copy engine (and mirrored there by the relay)
+    const uint32_t* host_flags;     // LANES epochs: the PACK lanes' own flag words in mapped pinned memory (else NULL), see below
     uint32_t* next_item;            // this launch's work counter: never reset, the host knows where it stands ...
     uint32_t item_base;             // ... before this launch (a launch of n items on g blocks adds exactly n + g)
     uint32_t first_item;            // the launch scores items [first_item, first_item + n_items) of the epoch
@@ -156,6 +157,13 @@ sw_feed_kernel(const FeedArgs fa, const SwParams prm)
                         if (nap < 1600) nap *= 2;          // back off: hundreds of blocks may be waiting when the link is the bottleneck
                         v = feed_ld_flag(flag);
                         if (v >= want && v <= want + 1u) break;
+                        // Progress must not depend on the relay warp finding a place on an SM (the consumer blocks leave it
+                        // barely a warp's worth of registers): now and then a waiting block looks at its tile's flag in host
+                        // memory itself -- a PCIe read, so rarely.
+                        if (fa.host_flags && (spins & 31u) == 31u) {
+                            const uint32_t h = feed_ld_flag(fa.host_flags + (flag - fa.ready));
+                            if (h == want + FEED_FMT_PACKED) { v = h; break; }
+                        }
                         if ((++spins & 63u) == 0u) {
                             if (*fa.abort) { *fa.status = FEED_STATUS_ABORTED; v = 0xffffffffu; break; }
                             if (feed_now_ns() - t0 > fa.timeout_ns) { *fa.status = FEED_STATUS_TIMEOUT; v = 0xffffffffu; break; }

@@ -232,6 +232,26 @@ def test_host_pack_lanes_equal_plain_pipeline(ctx, swb, oracle):
         ctx.set_host_pack_threads(-1)
 
 
+def test_lanes_epoch_makes_progress_without_the_relay_warp(ctx, swb, oracle, monkeypatch):
+    # The relay warp mirrors the PACK lanes' host flags into device memory; should it find no room on an SM, every waiting
+    # block looks at its tile's host flag itself now and then.  With the relay switched off that path carries the whole batch.
+    n = 400_000
+    a, b = swb.counter_pairs(77_000_000, n)
+    want = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+    monkeypatch.setenv("SWB200_FEED_NO_RELAY", "1")
+    try:
+        ctx.set_host_pack_threads(6)
+        s0 = ctx.host_pack_stats()
+        got = ctx.score_batch(a, b, swb.MATRIX_SPEEDTEST, 15)
+        s1 = ctx.host_pack_stats()
+    finally:
+        ctx.set_host_pack_threads(-1)
+    assert s1["packed_pairs"] > s0["packed_pairs"]
+    assert np.array_equal(got, want)
+    sample = np.r_[0:1024, n - 1024:n]
+    assert np.array_equal(got[sample], oracle.score_batch(a[sample], b[sample], swb.MATRIX_SPEEDTEST, 15, threads=NCPU))
+
+
 def test_domain_properties_at_scale(ctx, swb):
     # size-independent properties on 300 000 pairs (no oracle needed)
     n = 300_000
