@@ -451,7 +451,7 @@ def leg_inproc(R: "Ranks", swb200, n_per_gpu: int, matrix, gap, steps: int, rest
             want = counter_prefix_sum(n)
             res = {}
             for name, (x, y, packed) in (("bytes", (pa, pb, False)), ("packed", (ka, kb, True))):
-                for _ in range(3 if packed else 8):      # byte-coded: the lane-count tuner's exploration calls come first
+                for _ in range(3 if packed else 10):     # byte-coded: the lane tuner's exploration calls come first
                     ctxN.score_batch(x.array, y.array, matrix, gap, out=ps.array, packed=packed)
                 l0 = ctxN.launch_count
                 t0 = time.perf_counter()
@@ -686,7 +686,7 @@ def run_b200_arm(args):
         ctx.set_host_pack_threads(0)
         plain_ms = timed_host_calls(R, e2e_bytes, 5, warmup=2)
         ctx.set_host_pack_threads(args.pack_threads if args.pack_threads is not None else -1)
-    for _ in range(8):           # the library tries its PACK-lane counts (all / half / none, twice each) on the first calls and then keeps the fastest
+    for _ in range(10):          # the library tries its four lane configurations (twice each) on the first calls and then keeps the fastest
         e2e_bytes()
     pack0 = ctx.host_pack_stats()
     launches1 = ctx.launch_count

@@ -216,11 +216,13 @@ int swb200_kernel_info_len(swb200_ctx* ctx, int device_index, int seq_len, const
 int swb200_set_host_pack_threads(swb200_ctx* ctx, int threads_per_gpu);
 /* Pairs sent packed / as bytes by host batches so far, and the lane count in effect. */
 int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64_t* raw_pairs, int* threads_per_gpu);
-/* With threads_per_gpu = -1 the library also tunes how many of its lanes take part: large byte-coded batches try all,
- * half and none of them in turn and keep the fastest (what pays depends on whether the PCIe link or the host's DRAM
- * is the scarcer resource, i.e. on how many GPUs share the host).  lanes_in_use: the count currently preferred on GPU
- * device_index; pairs_per_s_all_half_none[3]: the throughput seen with each candidate (0 = not tried yet). */
-int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_in_use, double* pairs_per_s_all_half_none);
+/* With threads_per_gpu = -1 the library also tunes which of its lanes take part: large byte-coded batches try, in turn,
+ * all PACK lanes + the RAW lane, all PACK lanes with the calling thread packing too (no DMA), half the PACK lanes + the
+ * RAW lane, and the RAW lane alone, and keep the fastest (what pays depends on whether the PCIe link, the host's cores or
+ * its DRAM is the scarcer resource, i.e. on how many GPUs share the host).  lanes_in_use / raw_lane_in_use: what is
+ * currently preferred on GPU device_index; pairs_per_s[4]: the throughput seen with each candidate in the order above
+ * (0 = not tried yet). */
+int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_in_use, int* raw_lane_in_use, double* pairs_per_s);
 /* The packer itself (inverse of the reference's `unpack`, source.cpp:1580-1583), for callers
  * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);

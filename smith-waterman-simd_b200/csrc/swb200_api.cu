@@ -785,15 +785,17 @@ int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64
     return SWB200_OK;
 }
 
-int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_in_use, double* pairs_per_s_all_half_none)
+int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_in_use, int* raw_lane_in_use, double* pairs_per_s)
 {
     if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) return SWB200_ERR_ARG;
     Device* d = ctx->devs[device_index];
     std::lock_guard<std::mutex> lock(d->mu);
     const FeedState& fs = *d->feed;
     const int n_pack = pack_threads_per_gpu(ctx);
-    if (lanes_in_use) *lanes_in_use = (ctx->pack_threads < 0 && fs.tune_calls > 0) ? feed_tune_lanes(fs.tune_best, n_pack) : n_pack;
-    if (pairs_per_s_all_half_none) for (int k = 0; k < FeedState::kTuneCandidates; ++k) pairs_per_s_all_half_none[k] = fs.tune_rate[k];
+    const bool tuned = ctx->pack_threads < 0 && fs.tune_calls > 0;
+    if (lanes_in_use) *lanes_in_use = tuned ? feed_tune_lanes(fs.tune_best, n_pack) : n_pack;
+    if (raw_lane_in_use) *raw_lane_in_use = tuned ? (feed_tune_raw(fs.tune_best) ? 1 : 0) : 1;
+    if (pairs_per_s) for (int k = 0; k < FeedState::kTuneCandidates; ++k) pairs_per_s[k] = fs.tune_rate[k];
     return SWB200_OK;
 }
 

@@ -150,7 +150,7 @@ def load_library():
     lib.swb200_host_pack_stats.restype = i32
     lib.swb200_host_pack_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
     lib.swb200_host_pack_tuning.restype = i32
-    lib.swb200_host_pack_tuning.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_double)]
+    lib.swb200_host_pack_tuning.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
     lib.swb200_pack2bit_host.restype = i32
     lib.swb200_pack2bit_host.argtypes = [vp, vp, u64]
     _lib = lib
@@ -256,10 +256,11 @@ class Context:
 
     def host_pack_tuning(self, device_index: int = 0) -> dict:
         """The auto-tuner of the PACK-lane count: lanes it currently prefers, and the pairs/s it saw with all / half / none."""
-        lanes = C.c_int()
-        rates = (C.c_double * 3)()
-        self._check(self._lib.swb200_host_pack_tuning(self._h, device_index, C.byref(lanes), rates))
-        return {"lanes_in_use": int(lanes.value), "pairs_per_s": {"all_lanes": rates[0], "half": rates[1], "none": rates[2]}}
+        lanes, raw = C.c_int(), C.c_int()
+        rates = (C.c_double * 4)()
+        self._check(self._lib.swb200_host_pack_tuning(self._h, device_index, C.byref(lanes), C.byref(raw), rates))
+        return {"lanes_in_use": int(lanes.value), "raw_lane_in_use": bool(raw.value),
+                "pairs_per_s": {"all_lanes_and_raw_lane": rates[0], "all_lanes_no_dma": rates[1], "half_the_lanes_and_raw_lane": rates[2], "raw_lane_only": rates[3]}}
 
     def set_force_general(self, on: bool):
         self._check(self._lib.swb200_set_force_general(self._h, int(on)))
