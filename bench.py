@@ -516,7 +516,7 @@ def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
     res = {"us_per_call": 1e6 * dt / calls, "ms_per_1M_calls": 1e3 * dt / calls * 1e6, "calls": calls, "score": int(out[0]), "score_expected": 80,
            "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
            "timed_from": "a Python loop of direct ctypes calls of swb200_score_pair",
-           "api": "swb200_score_pair: the pair rides in the launch parameters of a one-warp-per-pair kernel; the result is a tagged word in mapped pinned memory the call spins on",
+           "api": "swb200_score_pair: the call writes the pair into a 320-byte doorbell in mapped pinned memory; a resident one-warp server kernel polls it across PCIe, scores the pair and stores a tagged word into mapped pinned memory the call spins on (no launch per call; the server leaves by itself after 200 us without a call)",
            "shape": "SpeedTest (source.cpp:3036-3054): one fixed pair, repeated calls"}
     # the same loop in C++ (tools/speedtest_b200.cu, built by __graft_entry__.build()): no interpreter in the timed region,
     # and beside it the floor of any per-call GPU path on this box (empty kernel + tagged mapped word + spin)

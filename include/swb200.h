@@ -77,9 +77,13 @@ int swb200_free_pinned(void* ptr);
  *   int SmithWaterman_simdN(const std::array<uint8_t,128>& seq1, const std::array<uint8_t,128>& seq2,
  *                           const std::array<int8_t,16>& score_matrix, const int8_t gap_penalty)
  * (source.cpp:462-466; identical signatures at 35-39, 62, 210, 341, 573, 666, 758, 852, 953).
- * The score is written to *score.  The pair travels inside the launch parameters of a
- * one-warp-per-pair kernel and the result comes back through a mapped word the call spins on:
- * no copy, no stream synchronisation (the shape SpeedTest times, source.cpp:3036-3054). */
+ * The score is written to *score.  The call rings a DOORBELL: it writes the pair, the matrix and the
+ * gap into 320 bytes of mapped pinned memory that a resident one-warp server kernel polls, and spins on
+ * the mapped word the server stores the tagged score into -- no launch, no copy, no stream
+ * synchronisation in a run of calls (the shape SpeedTest times, source.cpp:3036-3054).  The server
+ * leaves by itself when no call has come for SWB200_PAIR_LINGER_US (environment, default 200; 0 = no
+ * resident server: one launch per call with the pair in the launch parameters); the next call launches
+ * a new one.  Calls from several threads are serialised per context. */
 int swb200_score_pair(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2,
                       const int8_t* score_matrix, int8_t gap_penalty, int32_t* score);
 
@@ -223,6 +227,12 @@ int swb200_host_pack_stats(const swb200_ctx* ctx, uint64_t* packed_pairs, uint64
  * currently preferred on GPU device_index; pairs_per_s[4]: the throughput seen with each candidate in the order above
  * (0 = not tried yet). */
 int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_in_use, int* raw_lane_in_use, double* pairs_per_s);
+/* The per-pair call's resident server (swb200_score_pair): how many server kernels this context has launched so far,
+ * how many calls went through its doorbell, and what the server itself measured for the last one -- nanoseconds from
+ * the poll that brought the request to the store of the result (the sweep of the 128 x 128 matrix by one warp).
+ * Any pointer may be NULL. */
+int swb200_pair_path_stats(const swb200_ctx* ctx, uint64_t* server_launches, uint64_t* doorbell_calls, uint32_t* last_sweep_ns);
+
 /* The packer itself (inverse of the reference's `unpack`, source.cpp:1580-1583), for callers
  * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);
@@ -239,7 +249,8 @@ int swb200_semiglobal_kernel_info(swb200_ctx* ctx, int device_index, swb200_kern
 uint64_t swb200_launch_count(const swb200_ctx* ctx);
 
 /* Test hook: 0 sends small host batches (<= 2048 pairs) through the throughput kernel's chunk pipeline instead of
- * the one-warp-per-pair latency kernel; 1 (default) restores the latter. */
+ * the one-warp-per-pair latency kernels; 1 (default) restores the latter; 2 = the latency kernels with one launch per
+ * call even for a single pair (no resident server). */
 int swb200_set_latency_path(swb200_ctx* ctx, int on);
 
 /* Test hook: 1 forces the general (non-offset) kernel even where the fast one is exact. */

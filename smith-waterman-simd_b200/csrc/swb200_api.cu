@@ -91,6 +91,7 @@ struct swb200_ctx {
     std::atomic<uint64_t> packed_pairs{0}, raw_pairs{0};   // host batches: pairs sent 2-bit packed / as bytes
     int force_general = 0;
     int latency_path = 1;            // small batches of 128-mers take the one-warp-per-pair kernel (pairpath.inc); test hook
+    int pair_doorbell = 1;           // a single pair goes to the resident server kernel through its doorbell (pairpath.inc); test hook
     int pack_threads = -1;           // per GPU; -1 = auto (host cores available to this process), 0 = off
     std::mutex tickets_mu;
     std::map<uint64_t, std::pair<std::thread, int*>> tickets;
@@ -411,6 +412,7 @@ int score_host(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, bool p
         return pair_run(ctx, ctx->devs[0], seq1, seq2, sm, gap, scores, n, shared_target);
     const SwParams prm = sw_make_params(sm, gap, ctx->force_general, L);
     const size_t G = ctx->devs.size();
+    pair_dismiss(ctx->devs[0]);          // a resident per-pair server (GPU 0 only) makes room
     // Batches of the reference shape go through the persistent-kernel packer (feed.inc); byte-coded ones with the host
     // 2-bit packing lanes beside the raw copies.  Everything else (small batches, L = 256 / 512, one shared target)
     // takes the chunk pipeline.
@@ -654,6 +656,7 @@ static int device_args(swb200_ctx* ctx, int device_index, const void* a, const v
     if (!ctx) return SWB200_ERR_ARG;
     if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SWB200_ERR_ARG, "device_index out of range");
     if (n && ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15u)) return fail(ctx, SWB200_ERR_ARG, "device arrays must be 16-byte aligned");
+    pair_dismiss(ctx->devs[device_index]);       // a resident per-pair server makes room for the caller's launch
     return SWB200_OK;
 }
 
@@ -799,6 +802,28 @@ int swb200_host_pack_tuning(const swb200_ctx* ctx, int device_index, int* lanes_
     return SWB200_OK;
 }
 
+int swb200_pair_path_stats(const swb200_ctx* ctx, uint64_t* server_launches, uint64_t* doorbell_calls, uint32_t* last_sweep_ns)
+{
+    if (!ctx || ctx->devs.empty()) return SWB200_ERR_ARG;
+    Device* d = ctx->devs[0];
+    PairSlot* ps = __atomic_load_n(&d->pair, __ATOMIC_ACQUIRE);
+    uint64_t launches = 0, calls = 0;
+    uint32_t ns = 0;
+    if (ps) {
+        std::lock_guard<std::mutex> lock(ps->mu);
+        launches = ps->server_launches;
+        calls = ps->doorbell_calls;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, d->id);
+        const uint32_t cycles = const_cast<const volatile PairMailbox*>(ps->h_mb)->sweep_ns;
+        ns = khz > 0 ? (uint32_t)((uint64_t)cycles * 1000000ull / (uint64_t)khz) : 0;
+    }
+    if (server_launches) *server_launches = launches;
+    if (doorbell_calls) *doorbell_calls = calls;
+    if (last_sweep_ns) *last_sweep_ns = ns;
+    return SWB200_OK;
+}
+
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes)
 {
     if ((!codes || !packed) && n_codes) return SWB200_ERR_ARG;
@@ -811,6 +836,7 @@ int swb200_set_latency_path(swb200_ctx* ctx, int on)
 {
     if (!ctx) return SWB200_ERR_ARG;
     ctx->latency_path = on ? 1 : 0;
+    ctx->pair_doorbell = (on != 2) ? 1 : 0;      // 2: the latency kernel with one launch per call, also for a single pair
     return SWB200_OK;
 }
 

@@ -42,7 +42,7 @@ ABI_SYMBOLS = (
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
     "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
-    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak", "swb200_host_pack_tuning",
+    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak", "swb200_host_pack_tuning", "swb200_pair_path_stats",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -149,6 +149,8 @@ def load_library():
     lib.swb200_set_host_pack_threads.argtypes = [vp, i32]
     lib.swb200_host_pack_stats.restype = i32
     lib.swb200_host_pack_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
+    lib.swb200_pair_path_stats.restype = i32
+    lib.swb200_pair_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.swb200_host_pack_tuning.restype = i32
     lib.swb200_host_pack_tuning.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
     lib.swb200_pack2bit_host.restype = i32
@@ -271,8 +273,15 @@ class Context:
         self._check(self._lib.swb200_measure_alu_peak(self._h, device_index, float(target_ms), C.byref(t), C.byref(ms)))
         return {"tinstr_per_s": float(t.value), "elapsed_ms": float(ms.value)}
 
-    def set_latency_path(self, on: bool):
-        """False: small host batches go through the throughput kernel instead of the one-warp-per-pair kernel (test hook)."""
+    def pair_path_stats(self) -> dict:
+        """The per-pair call's resident server: kernels launched, calls through its doorbell, the last call's sweep time."""
+        n, c, ns = C.c_uint64(), C.c_uint64(), C.c_uint32()
+        self._check(self._lib.swb200_pair_path_stats(self._h, C.byref(n), C.byref(c), C.byref(ns)))
+        return {"server_launches": int(n.value), "doorbell_calls": int(c.value), "last_sweep_us": ns.value * 1e-3}
+
+    def set_latency_path(self, on):
+        """False: small host batches go through the throughput kernel instead of the one-warp-per-pair kernels; 2: those
+        kernels with one launch per call even for a single pair (no resident server); True: the default (test hook)."""
         self._check(self._lib.swb200_set_latency_path(self._h, int(on)))
 
     def kernel_info(self, score_matrix, gap_penalty, device_index: int = 0, seq_len: int = SEQ_LEN) -> dict:

@@ -78,6 +78,53 @@ def test_per_pair_call_over_the_whole_domain(ctx, swb, oracle, golden):
     assert ctx.smith_waterman(bad, bad, swb.MATRIX_SPEEDTEST, 15) == 1280
 
 
+def test_per_pair_doorbell_resident_server(ctx, swb, oracle):
+    # swb200_score_pair rings the doorbell of a resident one-warp server kernel (csrc/sw_pair_kernel.cuh, pairpath.inc):
+    # a run of calls launches it once; after a pause longer than its linger time it has left and the next call launches
+    # a new one; matrices and gaps change from call to call; several threads may call at once; and every score equals
+    # the launch-per-call form of the same kernel (mode 2) and the oracle.
+    import threading, time
+    a, b = swb.counter_pairs(777, 600)
+    sets = [(swb.MATRIX_SPEEDTEST, 15), (swb.MATRIX_111, 1), (mm(127, -127), 127), (mm(5, 3), 0), (list(range(-8, 8)), 2)]
+    want = {k: oracle.score_batch(a, b, sm, g, threads=NCPU) for k, (sm, g) in enumerate(sets)}
+    ctx.smith_waterman(a[0], b[0], *sets[0])                  # a server is resident from here on
+    l0 = ctx.launch_count
+    got = [ctx.smith_waterman(a[i], b[i], *sets[0]) for i in range(600)]
+    assert got == [int(x) for x in want[0]]
+    assert ctx.launch_count - l0 <= 20, "a run of per-pair calls must not launch per call"
+    for i in range(120):                                      # parameters change with every call
+        k = i % len(sets)
+        assert ctx.smith_waterman(a[i], b[i], *sets[k]) == int(want[k][i]), (i, k)
+    l1 = ctx.launch_count
+    for i in range(12):                                       # the server leaves during the pause; the call launches the next one
+        time.sleep(0.004)
+        assert ctx.smith_waterman(a[i], b[i], *sets[1]) == int(want[1][i])
+    assert ctx.launch_count - l1 >= 6
+    errors = []
+    def worker(k):
+        try:
+            for i in range(k, 400, 4):
+                if ctx.smith_waterman(a[i], b[i], *sets[0]) != int(want[0][i]):
+                    errors.append(i)
+        except Exception as e:                                # pragma: no cover
+            errors.append(repr(e))
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors
+    try:
+        ctx.set_latency_path(2)                               # one launch per call, the pair in the launch parameters
+        l2 = ctx.launch_count
+        assert [ctx.smith_waterman(a[i], b[i], *sets[2]) for i in range(50)] == [int(x) for x in want[2][:50]]
+        assert ctx.launch_count - l2 == 50
+    finally:
+        ctx.set_latency_path(True)
+    # a batch call right after per-pair calls (the resident server is still there) is not held up by it for long
+    t0 = time.perf_counter()
+    assert np.array_equal(ctx.score_batch(a, b, *sets[0]), want[0])
+    assert time.perf_counter() - t0 < 0.5
+
+
 def test_latency_kernel_at_its_largest_batch(ctx, swb, oracle):
     # 2048 pairs = the most the one-warp-per-pair kernel takes; 2049 is the first batch of the throughput kernel
     a, b = swb.counter_pairs(424242, 2049)

@@ -17,6 +17,21 @@
 
 __global__ void floor_kernel(unsigned long long* out, unsigned seq) { out[0] = ((unsigned long long)seq << 32) | 80ull; }
 
+// PCIe read round trip as a kernel sees it: a chain of dependent loads of one word of mapped pinned host memory
+__global__ void rtt_kernel(const unsigned* host_word, unsigned long long* out_ns, int n)
+{
+    unsigned long long t0, t1;
+    unsigned off = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = 0; i < n; ++i) {
+        unsigned v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(host_word + off) : "memory");
+        off = v;                                   // (the host word holds 0: a true dependence the compiler cannot see through)
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out_ns[0] = (t1 - t0) / (unsigned long long)n + off;
+}
+
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char** argv)
@@ -32,6 +47,9 @@ int main(int argc, char** argv)
     double t0 = now_s();
     for (int i = 0; i < calls; ++i) swb200_score_pair(ctx, a.data(), b.data(), sm, 15, &score);
     const double per_pair_us = (now_s() - t0) / calls * 1e6;
+    uint64_t server_launches = 0, doorbell_calls = 0;
+    uint32_t sweep_ns = 0;
+    swb200_pair_path_stats(ctx, &server_launches, &doorbell_calls, &sweep_ns);
 
     // the floor: empty kernel, tagged mapped word, spin
     unsigned long long *h = nullptr, *d = nullptr;
@@ -50,6 +68,16 @@ int main(int argc, char** argv)
     for (int i = 0; i < calls; ++i) floor_call(1000u + (unsigned)i);
     const double floor_us = (now_s() - t0) / calls * 1e6;
 
+    // PCIe read round trip seen by a kernel (what a poll of the doorbell costs)
+    unsigned long long *h_rtt = nullptr, *d_rtt = nullptr;
+    cudaHostAlloc(&h_rtt, 64, cudaHostAllocMapped);
+    cudaHostGetDevicePointer(&d_rtt, h_rtt, 0);
+    h_rtt[0] = 0; h_rtt[1] = 0;
+    rtt_kernel<<<1, 1, 0, st>>>(reinterpret_cast<const unsigned*>(d_rtt + 1), d_rtt, 2000);
+    cudaStreamSynchronize(st);
+    const double rtt_us = (double)h_rtt[0] * 1e-3;
+    cudaFreeHost(h_rtt);
+
     // 10 000 distinct pairs: one call per pair, and one batch call
     std::vector<int32_t> s1(10000), s2(10000);
     t0 = now_s();
@@ -61,6 +89,14 @@ int main(int argc, char** argv)
     const double batch_us = (now_s() - t0) / 20 / 10000 * 1e6;
     const bool same = memcmp(s1.data(), s2.data(), 10000 * sizeof(int32_t)) == 0;
 
+    // the same call with one launch of the latency kernel per call (no resident server): what the doorbell saves
+    swb200_set_latency_path(ctx, 2);
+    for (int i = 0; i < 500; ++i) swb200_score_pair(ctx, a.data(), b.data(), sm, 15, &score);
+    t0 = now_s();
+    for (int i = 0; i < calls; ++i) swb200_score_pair(ctx, a.data(), b.data(), sm, 15, &score);
+    const double launch_us = (now_s() - t0) / calls * 1e6;
+    swb200_set_latency_path(ctx, 1);
+
     // the same per-pair call through the chunk pipeline of the throughput kernel (what round 1 did for n = 1: two H2D
     // copies, a launch, a D2H copy, an event wait), for the record
     swb200_set_latency_path(ctx, 0);
@@ -71,10 +107,12 @@ int main(int argc, char** argv)
     swb200_set_latency_path(ctx, 1);
 
     printf("{\"shape\": \"SpeedTest (source.cpp:3036-3054): one fixed pair, %d calls, C++ loop\", \"us_per_call\": %.3f, \"ms_per_1M_calls\": %.1f, "
-           "\"score\": %d, \"score_expected\": 80, \"floor_us_per_call\": %.3f, \"floor\": \"empty kernel + tagged mapped word + spin (launch, PCIe write, poll)\", "
+           "\"score\": %d, \"score_expected\": 80, \"path\": \"doorbell of the resident one-warp server kernel (no launch per call)\", "
+           "\"server_kernels_launched\": %llu, \"doorbell_calls\": %llu, \"sweep_us_measured_by_the_server\": %.3f, "
+           "\"one_launch_per_call_us\": %.3f, \"pcie_read_round_trip_us\": %.3f, \"floor_us_per_call\": %.3f, \"floor\": \"of any launch-per-call path: empty kernel + tagged mapped word + spin (launch, PCIe write, poll)\", "
            "\"distinct_pairs_us_per_call\": %.3f, \"batch_of_10000_us_per_pair\": %.4f, \"per_pair_equals_batch\": %s, "
            "\"through_the_throughput_kernel_us_per_call\": %.3f}\n",
-           calls, per_pair_us, per_pair_us * 1e3, score, floor_us, distinct_us, batch_us, same ? "true" : "false", chunk_us);
+           calls, per_pair_us, per_pair_us * 1e3, score, (unsigned long long)server_launches, (unsigned long long)doorbell_calls, sweep_ns * 1e-3, launch_us, rtt_us, floor_us, distinct_us, batch_us, same ? "true" : "false", chunk_us);
     cudaFreeHost(h);
     cudaStreamDestroy(st);
     swb200_shutdown(ctx);
