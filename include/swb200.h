@@ -236,6 +236,9 @@ int swb200_pair_path_stats(const swb200_ctx* ctx, uint64_t* server_launches, uin
 /* The packer itself (inverse of the reference's `unpack`, source.cpp:1580-1583), for callers
  * that want to feed swb200_score_batch_packed: n_codes bytes (a multiple of 8) -> n_codes/4. */
 int swb200_pack2bit_host(const uint8_t* codes, uint8_t* packed, uint64_t n_codes);
+/* Replaces `void unpack(const uint8_t* src, uint8_t* dest, int n)` and its SIMD forms unpack_simd1..4
+ * (source.cpp:1580-1774) on the host: codes[4i + j] = (packed[i] >> 2j) & 3 for n_codes codes (any count). */
+int swb200_unpack2bit_host(const uint8_t* packed, uint8_t* codes, uint64_t n_codes);
 
 /* The integer-ALU issue peak of GPU `device_index`, measured now: independent chains of VIADDMNMX.S16x2 (the hot
  * loop's own instruction) on every SM for about target_ms milliseconds; *tinstr_per_s = thread-level instructions per

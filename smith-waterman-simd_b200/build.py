@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libswb200.so")
 SOURCES = [os.path.join(CSRC, "swb200_api.cu"), os.path.join(CSRC, "pairgen.cpp"), os.path.join(CSRC, "hostpack.cpp"), os.path.join(CSRC, "hostprobe.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("sw_core.cuh", "sw_kernel.cuh", "sg_kernel.cuh", "sg2_core.cuh", "sg_host.inc", "sg_abi.inc", "sw_params.h", "sw_feed_kernel.cuh", "sw_pair_kernel.cuh", "feed.inc", "pairpath.inc", "peakprobe.inc")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("sw_core.cuh", "sw_kernel.cuh", "sg_kernel.cuh", "sg2_core.cuh", "sg_host.inc", "sg_pipe.inc", "sg_abi.inc", "sw_params.h", "sw_feed_kernel.cuh", "sw_pair_kernel.cuh", "feed.inc", "pairpath.inc", "peakprobe.inc")] + [
     os.path.join(ROOT, "include", "swb200.h"), os.path.abspath(__file__)]
 
 NVCC_FLAGS = [

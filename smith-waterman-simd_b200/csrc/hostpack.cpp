@@ -86,6 +86,69 @@ static void pack2bit_avx2(const uint8_t* codes, uint8_t* packed, size_t n_codes)
 }
 #endif
 
+// ---------------------------------------------------------------------------------------------------------------
+// The other direction, the reference's `unpack` itself (source.cpp:1580-1583) on the host: the semi-global aligner's
+// move strings cross the link four to a byte and are expanded into the caller's byte rows here (sg_pipe.inc).
+static void unpack2bit_plain(const uint8_t* packed, uint8_t* codes, size_t n_codes)
+{
+    for (size_t i = 0; i < n_codes / 4; ++i) {
+        const uint32_t b = packed[i];
+        const uint32_t w = (b & 3u) | ((b & 0x0cu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
+        memcpy(codes + 4 * i, &w, 4);
+    }
+    for (size_t j = n_codes & ~(size_t)3; j < n_codes; ++j) codes[j] = (packed[j / 4] >> (2 * (j & 3))) & 3u;
+}
+
+#if defined(__x86_64__)
+// 32 packed bytes -> 128 codes per iteration: the four 2-bit fields of every byte as four vectors (shift, mask), then two
+// rounds of interleaves put field j of byte i at 4i + j; the interleaves work inside 128-bit halves, four half-swaps
+// restore the order.  19 vector operations per 128 bytes written.
+template <bool STREAM>
+__attribute__((target("avx2")))
+static void unpack2bit_avx2_body(const uint8_t* packed, uint8_t* codes, size_t n_codes)
+{
+    const __m256i m3 = _mm256_set1_epi8(3);
+    size_t i = 0;
+    for (; i + 128 <= n_codes; i += 128) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(packed + i / 4));
+        const __m256i v0 = _mm256_and_si256(v, m3);
+        const __m256i v1 = _mm256_and_si256(_mm256_srli_epi16(v, 2), m3);
+        const __m256i v2 = _mm256_and_si256(_mm256_srli_epi16(v, 4), m3);
+        const __m256i v3 = _mm256_and_si256(_mm256_srli_epi16(v, 6), m3);
+        const __m256i a_lo = _mm256_unpacklo_epi8(v0, v1), a_hi = _mm256_unpackhi_epi8(v0, v1);     // (field 0, field 1) of bytes 0-7 | 16-23, 8-15 | 24-31
+        const __m256i b_lo = _mm256_unpacklo_epi8(v2, v3), b_hi = _mm256_unpackhi_epi8(v2, v3);
+        const __m256i c0 = _mm256_unpacklo_epi16(a_lo, b_lo), c1 = _mm256_unpackhi_epi16(a_lo, b_lo);   // bytes 0-3 | 16-19, 4-7 | 20-23
+        const __m256i c2 = _mm256_unpacklo_epi16(a_hi, b_hi), c3 = _mm256_unpackhi_epi16(a_hi, b_hi);   // bytes 8-11 | 24-27, 12-15 | 28-31
+        const __m256i o0 = _mm256_permute2x128_si256(c0, c1, 0x20), o1 = _mm256_permute2x128_si256(c2, c3, 0x20);
+        const __m256i o2 = _mm256_permute2x128_si256(c0, c1, 0x31), o3 = _mm256_permute2x128_si256(c2, c3, 0x31);
+        if (STREAM) {
+            _mm256_stream_si256((__m256i*)(codes + i), o0);      _mm256_stream_si256((__m256i*)(codes + i + 32), o1);
+            _mm256_stream_si256((__m256i*)(codes + i + 64), o2); _mm256_stream_si256((__m256i*)(codes + i + 96), o3);
+        } else {
+            _mm256_storeu_si256((__m256i*)(codes + i), o0);      _mm256_storeu_si256((__m256i*)(codes + i + 32), o1);
+            _mm256_storeu_si256((__m256i*)(codes + i + 64), o2); _mm256_storeu_si256((__m256i*)(codes + i + 96), o3);
+        }
+    }
+    if (STREAM) _mm_sfence();
+    if (i < n_codes) unpack2bit_plain(packed + i / 4, codes + i, n_codes - i);
+}
+#endif
+
+// codes[4i + j] = (packed[i] >> 2j) & 3 for n_codes codes (any count; the last packed byte may be partly used).
+void unpack2bit_host(const uint8_t* packed, uint8_t* codes, size_t n_codes)
+{
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) {
+        // non-temporal stores when the destination allows: the expanded rows are the caller's, this core will not read them
+        if ((((uintptr_t)codes) & 31u) == 0 && n_codes >= 4096) unpack2bit_avx2_body<true>(packed, codes, n_codes);
+        else unpack2bit_avx2_body<false>(packed, codes, n_codes);
+        return;
+    }
+#endif
+    unpack2bit_plain(packed, codes, n_codes);
+}
+
 // n_codes must be a multiple of 8 (sequences are multiples of 128).
 void pack2bit_host(const uint8_t* codes, uint8_t* packed, size_t n_codes)
 {

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <exception>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -29,7 +30,10 @@
 #include "sw_kernel.cuh"
 #include "sw_params.h"
 
-namespace swb { void pack2bit_host(const uint8_t* codes, uint8_t* packed, size_t n_codes); }   // hostpack.cpp
+namespace swb {                  // hostpack.cpp
+void pack2bit_host(const uint8_t* codes, uint8_t* packed, size_t n_codes);
+void unpack2bit_host(const uint8_t* packed, uint8_t* codes, size_t n_codes);
+}
 
 namespace {
 
@@ -57,6 +61,7 @@ struct Slot {
 
 struct FeedState;                    // feed.inc: the persistent-kernel batch packer
 struct PairSlot;                     // pairpath.inc: the per-pair call's mapped slots
+struct SgPipe;                       // sg_pipe.inc: the semi-global aligner's compressed-wire host pipeline
 
 struct Device {
     int id = -1;
@@ -79,6 +84,7 @@ struct Device {
     uint64_t chunk_pairs = 0;        // chunk pipeline: pairs of 128 bases per chunk (whole waves), set by setup_device
     FeedState* feed = nullptr;       // persistent-kernel batch packer (feed.inc)
     PairSlot* pair = nullptr;        // per-pair path (pairpath.inc), created on first use
+    SgPipe* sg_pipe = nullptr;       // semi-global host pipeline (sg_pipe.inc), created on first use
 };
 
 } // namespace
@@ -242,6 +248,7 @@ cudaError_t launch_unpack(const uint8_t* d_packed, uint8_t* d_codes, uint64_t n_
 }
 
 FeedState* feed_create();        // feed.inc
+cudaError_t sg_pipe_prepare_kernels(int carveout);   // sg_pipe.inc
 
 int setup_device(swb200_ctx* ctx, Device* d)
 {
@@ -259,6 +266,22 @@ int setup_device(swb200_ctx* ctx, Device* d)
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
     SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
     SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    // ONE shared-memory carve-out for every kernel of the semi-global aligner.  An SM changes its L1 / shared-memory split
+    // only when it is empty: with the default (the forward kernel uses no shared memory, the traceback 32 KiB per block) a
+    // traceback launched beside the forward kernels of other chunks waited until every SM had drained -- measured in the
+    // host pipeline (sg_pipe.inc): a 3 ms traceback took 16 ms, ending with the last forward kernel.
+    {
+        const int carve = cudaSharedmemCarveoutMaxShared;
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<true, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(sg_left_align_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, cudaFuncSetAttribute(unpack2bit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, sg_pipe_prepare_kernels(carve));
+    }
     {
         // keep freed stream-ordered allocations (the L = 512 FIFO slots) in the pool across syncs
         cudaMemPool_t pool;
@@ -517,6 +540,7 @@ void swb200_shutdown(swb200_ctx* ctx)
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         cudaFree(d->d_bad);
+        sg_pipe_shutdown(d);
         cudaFree(d->sg_dev.traces);
         for (auto& g : d->sg_slots) {
             if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
@@ -821,6 +845,13 @@ int swb200_pair_path_stats(const swb200_ctx* ctx, uint64_t* server_launches, uin
     if (server_launches) *server_launches = launches;
     if (doorbell_calls) *doorbell_calls = calls;
     if (last_sweep_ns) *last_sweep_ns = ns;
+    return SWB200_OK;
+}
+
+int swb200_unpack2bit_host(const uint8_t* packed, uint8_t* codes, uint64_t n_codes)
+{
+    if ((!codes || !packed) && n_codes) return SWB200_ERR_ARG;
+    unpack2bit_host(packed, codes, (size_t)n_codes);
     return SWB200_OK;
 }
 

@@ -42,7 +42,7 @@ ABI_SYMBOLS = (
     "swb200_gen_reference_stream", "swb200_gen_counter_pairs", "swb200_gen_counter_pairs_packed",
     "swb200_fnv1a64_i32", "swb200_score_batch_len", "swb200_score_batch_len_device", "swb200_kernel_info_len", "swb200_score_one_vs_many",
     "swb200_score_batch_111", "swb200_semiglobal_xdrop_batch", "swb200_semiglobal_xdrop_batch_device",
-    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak", "swb200_host_pack_tuning", "swb200_pair_path_stats",
+    "swb200_semiglobal_kernel_info", "swb200_gen_related_pairs", "swb200_set_host_pack_threads", "swb200_host_pack_stats", "swb200_pack2bit_host", "swb200_set_latency_path", "swb200_host_read_bandwidth", "swb200_measure_alu_peak", "swb200_host_pack_tuning", "swb200_pair_path_stats", "swb200_unpack2bit_host",
 )
 
 ERR_ARG, ERR_DOMAIN, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_TICKET = -1, -2, -3, -4, -5, -6
@@ -153,6 +153,8 @@ def load_library():
     lib.swb200_pair_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.swb200_host_pack_tuning.restype = i32
     lib.swb200_host_pack_tuning.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
+    lib.swb200_unpack2bit_host.restype = i32
+    lib.swb200_unpack2bit_host.argtypes = [vp, vp, u64]
     lib.swb200_pack2bit_host.restype = i32
     lib.swb200_pack2bit_host.argtypes = [vp, vp, u64]
     _lib = lib
@@ -560,6 +562,21 @@ def pack2bit(codes: np.ndarray) -> np.ndarray:
     rc = load_library().swb200_pack2bit_host(c.ctypes.data, out.ctypes.data, c.size)
     if rc != 0:
         raise SwbError(rc, "swb200_pack2bit_host")
+    return out
+
+
+def unpack2bit(packed: np.ndarray, n_codes: int | None = None) -> np.ndarray:
+    """The reference's `unpack` (source.cpp:1580-1583): [..., k] packed bytes -> [..., 4k] byte codes (1-D: the first n_codes)."""
+    p = np.ascontiguousarray(packed, dtype=np.uint8)
+    if n_codes is not None:
+        if p.ndim != 1 or n_codes > 4 * p.size:
+            raise ValueError("n_codes needs a 1-D input holding at least n_codes/4 bytes")
+        out = np.empty(n_codes, np.uint8)
+    else:
+        out = np.empty(p.shape[:-1] + (p.shape[-1] * 4,), np.uint8)
+    rc = load_library().swb200_unpack2bit_host(p.ctypes.data, out.ctypes.data, out.size)
+    if rc != 0:
+        raise SwbError(rc, "swb200_unpack2bit_host")
     return out
 
 

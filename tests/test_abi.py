@@ -162,6 +162,31 @@ def test_host_packer_alignments_tails_and_the_streaming_store_path(swb):
                 assert (out_buf[:j] == 0xAA).all() and (out_buf[j + n_codes // 4:] == 0xAA).all(), (n_codes, off_in, off_out)
 
 
+def test_host_unpacker_is_the_references_unpack(swb):
+    # swb200_unpack2bit_host = `unpack` (source.cpp:1580-1583): dest[4i + j] = (src[i] >> 2j) & 3, for any count of codes,
+    # any alignment (non-temporal stores when the destination is 32-byte aligned and long enough), never a byte outside
+    # its output; and it is the inverse of the host packer.
+    import ctypes as C
+    lib = swb.load_library()
+    rng = np.random.default_rng(14)
+    for n_codes in (1, 3, 4, 5, 127, 128, 129, 4096, 4096 + 128, 4096 + 131, 32768, 100003):
+        packed = rng.integers(0, 256, (n_codes + 3) // 4 + 8, dtype=np.uint8)
+        want = ((packed[:, None] >> (2 * np.arange(4, dtype=np.uint8))[None, :]) & 3).reshape(-1)[:n_codes]
+        for off_in in (0, 1):
+            for off_out in (0, 1, 32):
+                out_buf = np.full(n_codes + 160, 0xAA, np.uint8)
+                base = out_buf.ctypes.data
+                j = (-base) % 32 + off_out
+                src = np.ascontiguousarray(np.concatenate([np.zeros(off_in, np.uint8), packed]))[off_in:]
+                rc = lib.swb200_unpack2bit_host(C.c_void_p(src.ctypes.data), C.c_void_p(base + j), C.c_uint64(n_codes))
+                assert rc == 0
+                assert np.array_equal(out_buf[j:j + n_codes], want), (n_codes, off_in, off_out)
+                assert (out_buf[:j] == 0xAA).all() and (out_buf[j + n_codes:] == 0xAA).all(), (n_codes, off_in, off_out)
+    codes = rng.integers(0, 4, (64, 16384), dtype=np.uint8)
+    assert np.array_equal(swb.unpack2bit(swb.pack2bit(codes)), codes)
+    assert np.array_equal(swb.unpack2bit(swb.pack2bit(codes).reshape(-1), 1001), codes.reshape(-1)[:1001])
+
+
 def test_the_product_never_touches_the_oracle_and_bench_only_in_its_baseline_legs():
     # The oracle is test infrastructure: nothing under smith-waterman-simd_b200/ or include/ may import, link or load it,
     # libswb200.so must not depend on it, and bench.py may reach it only inside the cpu_baseline / --impl reference legs.

@@ -251,3 +251,35 @@ def test_score_only_calls_allocate_no_round_record_scratch(swb):
         assert np.array_equal(out[0].cpu().numpy(), s["score"])
         used = free0 - free1
         assert used < (3 << 29), f"{used / 2**20:.0f} MiB taken by a score-only batch: the round-record scratch was allocated"
+
+
+def test_host_pipeline_on_the_compressed_wire(ctx, swb, oracle, monkeypatch):
+    # Large host batches cross the link four to a byte in both directions (csrc/sg_pipe.inc): lanes pack the sequences,
+    # the device expands them, aligns, packs the move strings, lanes expand those into the caller's rows.  Test knobs make
+    # a 700-pair batch of 1024-mers run as eleven chunks round a ring of three slots (every staging buffer is reused),
+    # from PAGEABLE arrays; results equal the oracle, the plain chunk pipeline, and the score-only form.
+    a, b = swb.related_pairs(4242, 700, 1024)
+    monkeypatch.setenv("SWB200_SG_CHUNK_PAIRS", "64")
+    monkeypatch.setenv("SWB200_SG_SLOTS", "3")
+    l0 = ctx.launch_count
+    r = ctx.semiglobal_xdrop(a, b)
+    assert ctx.launch_count - l0 == 11 * 6          # per chunk: two expansions, forward, traceback, left-align, move packing
+    check_against_oracle(oracle, r, a, b)
+    l1 = ctx.launch_count
+    s = ctx.semiglobal_xdrop(a, b, traceback=False)
+    assert ctx.launch_count - l1 == 11 * 3          # two expansions and the forward kernel
+    for k in ("score", "end_y", "end_x"):
+        assert np.array_equal(s[k], r[k]), k
+    monkeypatch.setenv("SWB200_SG_PIPE", "0")
+    l2 = ctx.launch_count
+    q = ctx.semiglobal_xdrop(a, b)
+    assert ctx.launch_count - l2 < 11 * 6           # the plain chunk pipeline: a few large chunks
+    for k in ("score", "end_y", "end_x", "n_ops"):
+        assert np.array_equal(q[k], r[k]), k
+    for i in range(700):
+        assert np.array_equal(q["ops"][i, :q["n_ops"][i]], r["ops"][i, :r["n_ops"][i]]), i
+    # a ragged last chunk and a last piece shorter than 32 pairs; two lanes only
+    monkeypatch.delenv("SWB200_SG_PIPE")
+    monkeypatch.setenv("SWB200_SG_THREADS", "2")
+    a2, b2 = a[:64 * 2 + 13], b[:64 * 2 + 13]
+    check_against_oracle(oracle, ctx.semiglobal_xdrop(a2, b2), a2, b2)
