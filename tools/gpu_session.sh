@@ -28,7 +28,7 @@ for step in "$@"; do
     refarm)   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$out/reference_arm.json" 2> "$out/reference_arm.err" ;;
     sgtests)  timeout 900 python -m pytest tests/test_semiglobal_gpu.py -x -q -m gpu > "$out/sgtests.log" 2>&1 ;;
     sgbench)  timeout 600 python bench.py --workload semiglobal --no-cpu-baseline --steps 5 > "$out/sgbench.json" 2> "$out/sgbench.err" ;;
-    sgbench_tl) SWB200_SG_TIMELINE=1 timeout 600 python bench.py --workload semiglobal --no-cpu-baseline --steps 2 > "$out/sgbench_tl.json" 2> "$out/sgbench_tl.err" ;;
+    sgbench_tl) SWB200_SG_TIMELINE=1 timeout 600 python bench.py --workload semiglobal --no-cpu-baseline --steps 6 > "$out/sgbench_tl.json" 2> "$out/sgbench_tl.err" ;;
     sgbench_depths) for dd in ${SG_DEPTHS:-8 4}; do echo "== forward depth $dd" >> "$out/sgbench_depths.txt"; SWB200_SG_FWD_DEPTH=$dd SWB200_SG_TIMELINE=1 timeout 300 python bench.py --workload semiglobal --no-cpu-baseline --steps 2 2>&1 >/dev/null | grep "sg pipeline" | tail -17 >> "$out/sgbench_depths.txt"; done ;;
     sgbench_large) SWB200_SG_TIMELINE=1 timeout 900 python bench.py --workload semiglobal --no-cpu-baseline --steps 3 --pairs 151552 > "$out/sgbench_large.json" 2> "$out/sgbench_large.err" ;;
     sgbench_plain) SWB200_SG_PIPE=0 timeout 600 python bench.py --workload semiglobal --no-cpu-baseline --steps 5 > "$out/sgbench_plain.json" 2> "$out/sgbench_plain.err" ;;
