@@ -530,6 +530,74 @@ def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
     return res
 
 
+SG_LEG_PAIRS, SG_LEG_LEN = 148 * 256, 16384      # the semi-global leg of the default line (the dry-run test shrinks it)
+
+
+def leg_semiglobal(R: "Ranks", swb200, ctx, steps: int = 3) -> dict:
+    """SURVEY.md 8(f4) in the default line: the adaptive-banded X-drop semi-global aligner (score + traceback) on 37888
+    pairs of 16384-mers with TestSemiGlobal's 10/10/10 % edits (source.cpp:2750-2771) -- device-resident, and end to end
+    through swb200_semiglobal_xdrop_batch with host arrays (both directions cross the link four to a byte, csrc/sg_pipe.inc);
+    the whole batch is compared with the oracle's committed sums (tests/golden/semiglobal_batch_sums.json).
+    `bench.py --workload semiglobal` is the full arm (roofline of the forward kernel, CPU reference beside it)."""
+    torch = R.torch
+    n, L = SG_LEG_PAIRS, SG_LEG_LEN
+    pa, pb = swb200.PinnedArray((n, L), np.uint8), swb200.PinnedArray((n, L), np.uint8)
+    swb200.related_pairs(0, n, L, out=(pa.array, pb.array))
+    h_meta = [np.zeros(n, np.int32) for _ in range(4)]
+    h_ops = swb200.PinnedArray((n, 2 * L), np.uint8)
+    d_a, d_b = torch.from_numpy(pa.array).cuda(), torch.from_numpy(pb.array).cuda()
+    d_meta = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(4)]
+    d_ops = torch.empty((n, 2 * L), dtype=torch.uint8, device="cuda")
+    l0 = ctx.launch_count
+    for _ in range(2):
+        ctx.semiglobal_xdrop_device(d_a, d_b, d_meta[0], d_meta[1], d_meta[2], d_meta[3], d_ops)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.semiglobal_xdrop_device(d_a, d_b, d_meta[0], d_meta[1], d_meta[2], d_meta[3], d_ops)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    dev_scores, dev_nops = d_meta[0].cpu().numpy(), d_meta[3].cpu().numpy()
+    del d_ops, d_a, d_b
+    torch.cuda.empty_cache()
+
+    def e2e():
+        ctx._check(ctx._lib.swb200_semiglobal_xdrop_batch(ctx._h, pa.array.ctypes.data, pb.array.ctypes.data, L, n, h_meta[0].ctypes.data,
+                                                          h_meta[1].ctypes.data, h_meta[2].ctypes.data, h_meta[3].ctypes.data, h_ops.array.ctypes.data))
+    for _ in range(2):
+        e2e()
+    l1 = ctx.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    launches_e2e = (ctx.launch_count - l1) / steps
+    sums_ok = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "semiglobal_batch_sums.json")) as f:
+            want = json.load(f)["prefix"].get(str(n))
+        if want is not None:
+            got = {k: int(h_meta[j].sum(dtype=np.int64)) for j, k in enumerate(("score", "end_y", "end_x", "n_ops"))}
+            got["ops_weighted"] = sg_weighted_ops_sum(h_ops.array, h_meta[3])
+            sums_ok = bool(got == {k: int(v) for k, v in want.items()})
+    except Exception as ex:
+        sums_ok = f"{type(ex).__name__}: {ex}"
+    return {"workload": f"SURVEY.md 8(f4): adaptive-banded X-drop semi-global aligner (band 32, X 70, 1/1/1), score + traceback, {n} pairs of {L}-mers, "
+                        "10/10/10 % mismatch/insert/delete (source.cpp:2750-2771)",
+            "pairs": n, "seq_len": L,
+            "device_resident": {"alignments_per_s": n / (dev_ms * 1e-3), "ms_per_step": dev_ms, "gpu_launches_per_step": 3,
+                                "api": "swb200_semiglobal_xdrop_batch_device (forward, traceback, left-align kernels)"},
+            "e2e": {"alignments_per_s": n / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "gpu_launches_per_step": launches_e2e,
+                    "host_bytes_in_per_step": 2 * n * L, "host_bytes_out_per_step": n * (16 + 2 * L), "h2d_bytes_per_step": n * L // 2, "d2h_bytes_per_step": n * (16 + L // 2),
+                    "api": "swb200_semiglobal_xdrop_batch (host byte arrays in; scores, end cells and move strings out; host lanes pack the sequences to 2 bits "
+                           "and expand the 2-bit move strings, chunks of one forward warp per SM round 16 slots)",
+                    "bound": "latency: a forward warp is a serial chain of 32768 rounds (15-18 ms) that cannot start before its chunk has been packed and copied"},
+            "verified": {"e2e_scores_and_lengths_equal_device": bool(np.array_equal(h_meta[0], dev_scores) and np.array_equal(h_meta[3], dev_nops)),
+                         "whole_batch_sums_equal_oracle": sums_ok}}
+
+
 def leg_sweep(R: "Ranks", swb200, ctx, matrix, gap, steps: int, peak_tinstr: float) -> list:
     """BASELINE.json configs[3], in the default line: L = 128 / 256 / 512 on whole-wave batches of the counter stream
     re-cut to length L, device-resident, each with the oracle's committed score sum."""
@@ -753,7 +821,7 @@ def run_b200_arm(args):
         inproc = leg_inproc(R, swb200, n, matrix, gap, steps=min(args.steps, 10), restore_affinity=cpu_share["before"])
 
     # ================= N = 1 only: length sweep, per-pair call, CPU baseline
-    sweep = per_pair = None
+    sweep = per_pair = semiglobal = None
     peak_t = peak_live.get("tinstr_per_s") if isinstance(peak_live, dict) else None
     if world == 1 and not args.quick:
         try:
@@ -764,6 +832,11 @@ def run_b200_arm(args):
             per_pair = leg_per_pair(swb200, ctx, pa.array, pb.array, matrix, gap)
         except Exception as ex:
             per_pair = {"error": f"{type(ex).__name__}: {ex}"}
+        if not getattr(args, "no_semiglobal", False):
+            try:
+                semiglobal = leg_semiglobal(R, swb200, ctx)
+            except Exception as ex:
+                semiglobal = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---- roofline of the dominant kernel, from this rank's live CUDA-event launch times
     peaks = load_peaks()
@@ -840,7 +913,7 @@ def run_b200_arm(args):
             "stream": (None if stream_legs is None else dict(stream_legs, pairs=args.stream_pairs,
                        workload=f"configs[2]/[4]: {args.stream_pairs} counter-stream pairs sharded by contiguous index range over {world} rank(s); host threads -> pinned ring -> swb200_submit[_packed]")),
             "e2e_inproc": inproc,
-            "sweep": sweep, "per_pair": per_pair,
+            "sweep": sweep, "per_pair": per_pair, "semiglobal": semiglobal,
             "gpu_launches": int(launches_dev), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,
             "verified": {"fnv1a64_ae56a1e6a1d57492_and_sum_75478815": verified, "e2e_equals_device": all_ok, "e2e_packed_equals_device": bool(pk_ok),
@@ -1343,6 +1416,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--batch-pairs", type=int, default=1 << 21)
     ap.add_argument("--packed", action="store_true", help="stream the 2-bit packed wire format (64 B/pair)")
+    ap.add_argument("--no-semiglobal", action="store_true", help="batch1m at N = 1: skip the semi-global aligner leg (SURVEY.md 8(f4))")
     ap.add_argument("--quick", action="store_true", help="batch1m: only the device-resident and the two end-to-end legs (no host ceiling, stream, in-process, sweep, per-pair)")
     ap.add_argument("--stream-pairs", type=int, default=100_000_000, help="batch1m: pairs of the sharded streaming leg (configs[2]/[4])")
     args = ap.parse_args()

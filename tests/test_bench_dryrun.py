@@ -167,6 +167,8 @@ def bench(monkeypatch, oracle):
     monkeypatch.setattr(swb200, "PinnedArray", _FakePinned)
     monkeypatch.setattr(mod, "PAIRS_PER_GPU", 3000)
     monkeypatch.setattr(mod, "HOST_PROBE_MB", 8)
+    monkeypatch.setattr(mod, "SG_LEG_PAIRS", 6)
+    monkeypatch.setattr(mod, "SG_LEG_LEN", 256)
     mod.real_sweep_pairs = mod.sweep_pairs
     monkeypatch.setattr(mod, "sweep_pairs", lambda L, info: 64)       # the default line carries the sweep: keep the oracle's share small
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
@@ -194,6 +196,10 @@ def test_b200_arm_assembles_its_line(bench):
     assert line["roofline"]["peak_live"]["tinstr_per_s"] == 18.4 and line["roofline"]["peak"] == 18.4 and 0 < line["roofline"]["alu_pipe_busy"]["model"]
     assert [r["seq_len"] for r in line["sweep"]] == [128, 256, 512] and all(r["pairs"] == 64 for r in line["sweep"])
     assert line["per_pair"]["score"] == 80 and line["per_pair"]["us_per_call"] > 0 and line["per_pair"]["gpu_launches_per_call"] == 1
+    sg = line["semiglobal"]                                          # SURVEY.md 8(f4) in the default line (shrunk to 6 pairs of 256 here)
+    assert "error" not in sg, sg
+    assert sg["pairs"] == 6 and sg["device_resident"]["alignments_per_s"] > 0 and sg["e2e"]["alignments_per_s"] > 0
+    assert sg["verified"]["e2e_scores_and_lengths_equal_device"] is True and sg["verified"]["whole_batch_sums_equal_oracle"] is None
     assert line["stream"]["packed"]["pairs"] == 5000 and line["stream"]["bytes"]["score_sum"] == line["stream"]["packed"]["score_sum"]
     hc = line["host_ceiling"]
     assert "error" not in hc, hc
@@ -304,7 +310,7 @@ def test_b200_arm_two_ranks_on_gloo(tmp_path, oracle):
     assert line["value"] == pytest.approx(2 * 1500 * 16384 / (line["ms_per_step"] * 1e-3) / 1e9)
     assert line["verified"]["e2e_equals_device"] is True
     assert line["verified"]["other_ranks_checked"] == 0 and line["verified"]["other_ranks_score_sums_equal_reference"] is None   # 1500-pair blocks have no golden
-    assert "cpu_baseline" not in line and line["sweep"] is None and line["per_pair"] is None      # N = 1 only
+    assert "cpu_baseline" not in line and line["sweep"] is None and line["per_pair"] is None and line["semiglobal"] is None     # N = 1 only
     assert line["e2e"]["packed_input"]["scores_equal_device_leg"] is True                           # at every N
     inproc = line["e2e_inproc"]                                                                      # rank 0 alone drives both "GPUs"
     assert inproc["n_gpus"] == 2 and inproc["pairs_per_step"] == 3000 and inproc["bytes"]["value"] > 0 and inproc["packed"]["value"] > 0
