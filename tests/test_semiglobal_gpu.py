@@ -283,3 +283,20 @@ def test_host_pipeline_on_the_compressed_wire(ctx, swb, oracle, monkeypatch):
     monkeypatch.setenv("SWB200_SG_THREADS", "2")
     a2, b2 = a[:64 * 2 + 13], b[:64 * 2 + 13]
     check_against_oracle(oracle, ctx.semiglobal_xdrop(a2, b2), a2, b2)
+
+
+def test_all_visible_gpus_run_the_compressed_wire_pipeline(swb, oracle, monkeypatch):
+    # the host pipeline (csrc/sg_pipe.inc) under the library's own sharding layer: every visible GPU takes a contiguous index
+    # range and runs its own ring of slots with its own lanes, all writing slices of the caller's (pageable) arrays
+    import torch
+    g = torch.cuda.device_count()
+    monkeypatch.setenv("SWB200_SG_CHUNK_PAIRS", "96")
+    monkeypatch.setenv("SWB200_SG_SLOTS", "2")
+    monkeypatch.setenv("SWB200_SG_THREADS", "3")
+    n, length = 96 * 5 * g + 37, 512
+    a, b = swb.related_pairs(99, n, length)
+    with swb.Context(n_devices=g) as c:
+        l0 = c.launch_count
+        r = c.semiglobal_xdrop(a, b)
+        assert c.launch_count - l0 >= 6 * 5 * g              # the pipeline ran: six launches per chunk, at least five chunks per GPU
+    check_against_oracle(oracle, r, a, b, list(range(0, n, 5)) + list(range(n - 40, n)))
