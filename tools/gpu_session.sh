@@ -37,6 +37,7 @@ for step in "$@"; do
               n=${step#bench}
               timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n > "$out/bench_n$n.json" 2> "$out/bench_n$n.err" ;;
     ncu_launches) SWB200_FEED_NO_RELAY=1 SWB200_FEED_TIMEOUT_MS=60000 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sw_ -c 400 --csv --log-file "$out/ncu_launches.csv" python bench.py --quick --no-cpu-baseline --steps 3 --warmup 3 > "$out/ncu_launches.out" 2>&1 ;;
+    ncu_pair) timeout 600 ncu --set full --clock-control none --import-source on -k regex:sw_pair_kernel -s 200 -c 1 -o "$out/ncu_full_sw_pair_kernel" tools/speedtest_b200 3000 > "$out/ncu_pair.out" 2>&1 ;;
     packbench) timeout 300 tools/packbench 64 > "$out/packbench.jsonl" 2>&1 ;;
     speedtest) timeout 120 tools/speedtest_b200 20000 > "$out/speedtest.json" 2>&1 ;;
     speedtest_gaps) for g in 0 300 500 700 1000 1500; do SWB200_PAIR_POLL_GAP_NS=$g timeout 120 tools/speedtest_b200 20000 2>&1 | sed "s/^{/{\"poll_gap_ns\": $g, /" >> "$out/speedtest_gaps.jsonl"; done ;;
