@@ -179,7 +179,12 @@ int swb200_validate_codes_device(swb200_ctx* ctx, int device_index, const uint8_
  * ops[p][0..n_ops[p]) = the traceback as moves in forward order from (0,0): 0 = diagonal (y+1,x+1),
  * 1 = down (y+1), 2 = right (x+1) -- the vector itself is the running sum of the moves, (0,0) first
  * (host/smith_waterman_b200.hpp rebuilds it).  ops is [n][2*seq_len]; ops and n_ops may both be NULL
- * (score and end cell only; the traceback is then skipped on the device as well). */
+ * (score and end cell only; the traceback is then skipped on the device as well).  Bytes of a row past
+ * n_ops[p] are unspecified.
+ * Large batches (two chunks of sm_count x 32 pairs or more, seq_len a multiple of 16) cross the PCIe link
+ * four to a byte in both directions: host threads pack the sequences to the reference's 2-bit format
+ * (source.cpp:1580-1583) and expand the 2-bit move strings into `ops`; the arrays need not be pinned.
+ * SWB200_SG_PIPE=0 (environment) keeps the plain chunked copies. */
 int swb200_semiglobal_xdrop_batch(swb200_ctx* ctx, const uint8_t* seq1, const uint8_t* seq2, int32_t seq_len, uint64_t n,
                                   int32_t* scores, int32_t* end_y, int32_t* end_x, int32_t* n_ops, uint8_t* ops);
 /* The kernel launch alone on DEVICE arrays (same meaning), stream-ordered on `cuda_stream`.  Launches
