@@ -533,7 +533,7 @@ def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
 SG_LEG_PAIRS, SG_LEG_LEN = 148 * 256, 16384      # the semi-global leg of the default line (the dry-run test shrinks it)
 
 
-def leg_semiglobal(R: "Ranks", swb200, ctx, steps: int = 3) -> dict:
+def leg_semiglobal(R: "Ranks", swb200, ctx, steps: int = 5) -> dict:
     """SURVEY.md 8(f4) in the default line: the adaptive-banded X-drop semi-global aligner (score + traceback) on 37888
     pairs of 16384-mers with TestSemiGlobal's 10/10/10 % edits (source.cpp:2750-2771) -- device-resident, and end to end
     through swb200_semiglobal_xdrop_batch with host arrays (both directions cross the link four to a byte, csrc/sg_pipe.inc);
@@ -569,10 +569,12 @@ def leg_semiglobal(R: "Ranks", swb200, ctx, steps: int = 3) -> dict:
     for _ in range(2):
         e2e()
     l1 = ctx.launch_count
-    t0 = time.perf_counter()
+    per_call = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         e2e()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+        per_call.append(1e3 * (time.perf_counter() - t0))
+    e2e_ms = sum(per_call) / steps
     launches_e2e = (ctx.launch_count - l1) / steps
     sums_ok = None
     try:
@@ -589,7 +591,7 @@ def leg_semiglobal(R: "Ranks", swb200, ctx, steps: int = 3) -> dict:
             "pairs": n, "seq_len": L,
             "device_resident": {"alignments_per_s": n / (dev_ms * 1e-3), "ms_per_step": dev_ms, "gpu_launches_per_step": 3,
                                 "api": "swb200_semiglobal_xdrop_batch_device (forward, traceback, left-align kernels)"},
-            "e2e": {"alignments_per_s": n / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "gpu_launches_per_step": launches_e2e,
+            "e2e": {"alignments_per_s": n / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "ms_per_call": [round(t, 2) for t in per_call], "gpu_launches_per_step": launches_e2e,
                     "host_bytes_in_per_step": 2 * n * L, "host_bytes_out_per_step": n * (16 + 2 * L), "h2d_bytes_per_step": n * L // 2, "d2h_bytes_per_step": n * (16 + L // 2),
                     "api": "swb200_semiglobal_xdrop_batch (host byte arrays in; scores, end cells and move strings out; host lanes pack the sequences to 2 bits "
                            "and expand the 2-bit move strings, chunks of one forward warp per SM round 16 slots)",
