@@ -1163,6 +1163,11 @@ def run_semiglobal_arm(args):
         ctx._check(ctx._lib.swb200_semiglobal_xdrop_batch(ctx._h, pa.array.ctypes.data, pb.array.ctypes.data, SG_LEN, n,
                                                           h_meta[0].array.ctypes.data, h_meta[1].array.ctypes.data, h_meta[2].array.ctypes.data,
                                                           h_meta[3].array.ctypes.data, h_ops.array.ctypes.data))
+    # The clock sampler (nvidia-smi -lms 100) covers the device-resident timed region above and stops here: every NVML query
+    # holds up the CUDA calls of the moment for 10-40 ms, and this call's calling thread enqueues chunks and polls events all
+    # the way through -- with the sampler running, calls took 41 or 113 ms at random (the default line's semi-global leg,
+    # which runs after its sampler has stopped: 39-48 ms).
+    sampler.stop()
     for _ in range(2):
         e2e()
     barrier()
@@ -1172,7 +1177,6 @@ def run_semiglobal_arm(args):
         e2e()
     e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps, ddist)
     launches_e2e = ctx.launch_count - launches1
-    sampler.stop()
     if rank != 0:
         ctx.close()
         if world > 1:

@@ -137,7 +137,13 @@ __device__ __forceinline__ void sg_cp_async16(uint4* smem_dst, const uint4* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
 }
 
-template <int NW>               // the forward kernel's words per lane: the record layout
+// The moves leave the walker EIGHT AT A TIME (WIDE: rows of a multiple of 8 bytes at an 8-byte aligned base, i.e. every
+// length that is a multiple of 4).  A walker's moves go to descending addresses of its own row, so a byte store per step
+// is 32 lanes writing one byte each into 32 different sectors: 680 M partial-sector writes for the 37 888-pair batch, as
+// many L2 requests as the record stream itself has sectors -- the stores, not the 20 GB of records, were what the kernel
+// waited for.  The last eight moves now ride in a 64-bit register (shift in at the bottom: the first of them ends up in the
+// top byte = the highest address) and go out as one aligned 8-byte store; the row's last partial word is flushed bytewise.
+template <int NW, bool WIDE>    // NW: the forward kernel's words per lane (the record layout)
 __global__ void __launch_bounds__(SG_TB_THREADS)
 sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsigned long long n, const SgOut out)
 {
@@ -169,6 +175,7 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     uint32_t n_ops = 0;
+    unsigned long long acc = 0ull;              // WIDE: the moves since the last 8-byte store, newest in the low byte
 #pragma unroll 1
     for (int rb = rtop; rb >= 1; rb -= 8) {
         asm volatile("cp.async.wait_group %0;" :: "n"(SG_TB_DEPTH / 8 - 1) : "memory");      // this block of rounds has landed
@@ -181,7 +188,12 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
             const bool act = rw == r && r >= 1 && n_ops < cap;
             int o2 = o, r2 = rw;
             const uint32_t op = sg2_tb_step<NW>(rec[q].x, rec[q].y, rec[q].z, rec[q].w, o2, r2);                                 // 0 = diagonal, 1 = down, 2 = right
-            if (act) row[cap - 1u - n_ops] = (uint8_t)op;
+            if (WIDE) {
+                acc = act ? ((acc << 8) | (unsigned long long)op) : acc;
+                if (act && (n_ops & 7u) == 7u) *reinterpret_cast<unsigned long long*>(row + (cap - 1u - n_ops)) = acc;   // moves n_ops-7 .. n_ops: bytes cap-1-n_ops .. +7
+            } else {
+                if (act) row[cap - 1u - n_ops] = (uint8_t)op;
+            }
             o = act ? o2 : o;
             rw = act ? r2 : rw;
             n_ops += act ? 1u : 0u;
@@ -194,6 +206,10 @@ sg_traceback_kernel(const uint4* __restrict__ traces, const int len, const unsig
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (WIDE && live) {                          // the last n_ops % 8 moves: the low bytes of acc, oldest on top
+        const uint32_t r = n_ops & 7u;
+        for (uint32_t k = 0; k < r; ++k) row[cap - n_ops + k] = (uint8_t)(acc >> (8u * k));
+    }
     if (live) out.n_ops[p] = (int32_t)n_ops;
 }
 

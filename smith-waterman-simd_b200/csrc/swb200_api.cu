@@ -264,8 +264,10 @@ int setup_device(swb200_ctx* ctx, Device* d)
     d->chunk_pairs = kChunkWaves * (uint64_t)d->prop.multiProcessorCount * LenCfg<128>::MINB * LenCfg<128>::NT * 2;
     d->feed = feed_create();
     SWB_CUDA(ctx, cudaMalloc(&d->d_bad, sizeof(unsigned long long)));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
-    SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM));
+    SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM)));
+    SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM)));
+    SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM)));
+    SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_TB_SMEM)));
     // ONE shared-memory carve-out for every kernel of the semi-global aligner.  An SM changes its L1 / shared-memory split
     // only when it is empty: with the default (the forward kernel uses no shared memory, the traceback 32 KiB per block) a
     // traceback launched beside the forward kernels of other chunks waited until every SM had drained -- measured in the
@@ -276,8 +278,10 @@ int setup_device(swb200_ctx* ctx, Device* d)
         SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<true, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         SWB_CUDA(ctx, cudaFuncSetAttribute(sg2_xdrop_kernel<false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        SWB_CUDA(ctx, cudaFuncSetAttribute(sg_traceback_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)));
+        SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)));
+        SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)));
+        SWB_CUDA(ctx, (cudaFuncSetAttribute(sg_traceback_kernel<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)));
         SWB_CUDA(ctx, cudaFuncSetAttribute(sg_left_align_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         SWB_CUDA(ctx, cudaFuncSetAttribute(unpack2bit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         SWB_CUDA(ctx, sg_pipe_prepare_kernels(carve));
