@@ -43,7 +43,10 @@ static void pack2bit_swar(const uint8_t* codes, uint8_t* packed, size_t n_codes)
 // A core streams from DRAM at what its fill buffers allow (~7-10 GB/s on the hosts measured, 8 threads saturate at
 // 56 GB/s, profiles/r01/hostpack_rate_16core_box.jsonl), so the input is also prefetched 2 KiB ahead of the loads.
 // In the authoring container (one thread, 128 MB): 6.4 GB/s for the previous 64-byte loop, 8.0 with this loop shape,
-// 9.1 with the prefetch, 9.8 with the non-temporal store as well; not yet re-measured on a GPU box.
+// 9.1 with the prefetch, 9.8 with the non-temporal store as well.  On the B200 box (tools/packbench, profiles/r02/
+// packbench_b200_box.jsonl): prefetching into L2 (T1) 8-16 KiB ahead instead of into L1 2 KiB ahead lifts one thread from
+// 16.3 to 27-28 GB/s and eight from 101 to 117 (a core's L1 has ~a dozen fill buffers, its L2 several times as many
+// requests in flight); fifteen threads sit at the box's DRAM bandwidth either way (140 -> 144 GB/s).
 template <bool STREAM>
 __attribute__((target("avx2")))
 static void pack2bit_avx2_body(const uint8_t* codes, uint8_t* packed, size_t n_codes)
@@ -54,8 +57,8 @@ static void pack2bit_avx2_body(const uint8_t* codes, uint8_t* packed, size_t n_c
     const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);   // undoes the in-lane interleave of the two packs
     size_t i = 0;
     for (; i + 128 <= n_codes; i += 128) {
-        _mm_prefetch((const char*)(codes + i + 2048), _MM_HINT_T0);
-        _mm_prefetch((const char*)(codes + i + 2112), _MM_HINT_T0);
+        _mm_prefetch((const char*)(codes + i + 8192), _MM_HINT_T1);      // into L2, 8 KiB ahead: see the note above
+        _mm_prefetch((const char*)(codes + i + 8256), _MM_HINT_T1);
         __m256i a = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(codes + i)), m3);
         __m256i b = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(codes + i + 32)), m3);
         __m256i c = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(codes + i + 64)), m3);

@@ -22,8 +22,8 @@ uint64_t read_avx2(const uint8_t* p, size_t n)
     __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, a3 = a0;
     size_t i = 0;
     for (; i + 128 <= n; i += 128) {
-        _mm_prefetch((const char*)(p + i + 2048), _MM_HINT_T0);
-        _mm_prefetch((const char*)(p + i + 2112), _MM_HINT_T0);
+        _mm_prefetch((const char*)(p + i + 8192), _MM_HINT_T1);       // as the packer does (hostpack.cpp)
+        _mm_prefetch((const char*)(p + i + 8256), _MM_HINT_T1);
         a0 = _mm256_or_si256(a0, _mm256_loadu_si256((const __m256i*)(p + i)));
         a1 = _mm256_or_si256(a1, _mm256_loadu_si256((const __m256i*)(p + i + 32)));
         a2 = _mm256_or_si256(a2, _mm256_loadu_si256((const __m256i*)(p + i + 64)));
