@@ -125,6 +125,42 @@ def test_per_pair_doorbell_resident_server(ctx, swb, oracle):
     assert time.perf_counter() - t0 < 0.5
 
 
+def test_latency_kernels_on_random_parameters_of_the_whole_domain(ctx, swb, oracle):
+    # the one-warp sweep (offset frame in int32, score table in shared memory) over the reference's whole parameter domain:
+    # random 4 x 4 matrices with entries in [-127, 127] (asymmetric, all-positive, all-negative included), gaps in [0, 127],
+    # on random, identical, shifted and low-complexity pairs -- as a batch (sw_pair_kernel) and pair by pair through the
+    # doorbell (sw_pair_server), whose table of out-of-matrix scores depends on the gap and is rebuilt when it changes
+    rng = np.random.default_rng(20261018)
+    n = 384
+    a = rng.integers(0, 4, (n, 128), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, 128), dtype=np.uint8)
+    b[:64] = a[:64]
+    b[64:128] = np.roll(a[64:128], 7, axis=1)
+    a[128:160] = rng.integers(0, 2, (32, 128), dtype=np.uint8)
+    b[128:160] = rng.integers(0, 2, (32, 128), dtype=np.uint8)
+    for k in range(160, 224):
+        keep = rng.random(128) > 0.1
+        b[k] = np.concatenate([a[k][keep], rng.integers(0, 4, 128, dtype=np.uint8)])[:128]
+    for trial in range(60):
+        kind = trial % 4
+        if kind == 0:
+            sm = rng.integers(-127, 128, 16)
+        elif kind == 1:
+            sm = rng.integers(0, 128, 16)
+        elif kind == 2:
+            sm = rng.integers(-127, 1, 16)
+        else:
+            m, x = int(rng.integers(1, 128)), int(rng.integers(-127, 1))
+            sm = np.array(mm(m, x))
+        g = int(rng.integers(0, 128)) if trial % 5 else (0, 127)[trial % 2]
+        sm = [int(v) for v in sm]
+        want = oracle.score_batch(a, b, sm, g, threads=NCPU)
+        got = ctx.score_batch(a, b, sm, g)
+        assert np.array_equal(got, want), (trial, sm, g, int(np.flatnonzero(got != want)[0]))
+        for i in range(trial % 7, n, 29):
+            assert ctx.smith_waterman(a[i], b[i], sm, g) == int(want[i]), (trial, i, sm, g)
+
+
 def test_latency_kernel_at_its_largest_batch(ctx, swb, oracle):
     # 2048 pairs = the most the one-warp-per-pair kernel takes; 2049 is the first batch of the throughput kernel
     a, b = swb.counter_pairs(424242, 2049)
