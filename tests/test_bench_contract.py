@@ -94,3 +94,52 @@ def test_semiglobal_weighted_ops_sum_matches_the_golden_definition():
     with open(os.path.join(ROOT, "tests", "golden", "semiglobal_batch_sums.json")) as f:
         g = json.load(f)["prefix"]
     assert set(g) == {"2048", "37888"} and g["37888"]["score"] > g["2048"]["score"] > 0
+
+
+R02 = os.path.join(ROOT, "profiles", "r02")
+
+
+def _line2(name):
+    with open(os.path.join(R02, name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("name,n", [("bench_n1.json", 1), ("bench_n2_2gpu_box.json", 2), ("bench_n4_8gpu_box_final.json", 4),
+                                    ("bench_n8_8gpu_box_final.json", 8)])
+def test_round2_lines_carry_the_multi_gpu_legs(name, n):
+    # the default line of round 2 at N = 1, 2, 4, 8 (recorded from the final tree): contract keys, the legs the round-1
+    # verdict asked for at every N, and every recorded check green
+    d = _line2(name)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "host_ceiling", "stream", "packed_resident"):
+        assert k in d, k
+    assert d["n_gpus"] == n and d["scaling"] == "weak" and d["vs_baseline"] is None and d["warmup"] >= 3
+    cells = d["config"]["pairs_per_gpu"] * n * d["config"]["cells_per_pair"]
+    assert d["value"] == pytest.approx(cells / (d["ms_per_step"] * 1e-3) / 1e9, rel=1e-6)
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    pk = e["packed_input"]
+    assert e["value"] < pk["value"] < d["value"] and pk["scores_equal_device_leg"] is True      # the wire format pays at every N
+    assert d["roofline"]["peak_live"]["tinstr_per_s"] > 17 and 0.9 < d["roofline"]["frac"] < 1.05
+    v = d["verified"]
+    assert v["e2e_equals_device"] is True and v["e2e_packed_equals_device"] is True
+    st = d["stream"]
+    for fmt in ("packed", "bytes"):
+        assert st[fmt]["pairs"] == 100_000_000 and st[fmt]["score_sum"] == 7_546_733_630 and st[fmt]["score_sum_equals_reference"] is True
+    hc = d["host_ceiling"]
+    assert hc["h2d_pinned_gbs"] > 0 and hc["host_read_gbs"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        assert v["fnv1a64_ae56a1e6a1d57492_and_sum_75478815"] is True
+        assert [r["seq_len"] for r in d["sweep"]] == [128, 256, 512] and all(r["score_sum_equals_oracle"] is True for r in d["sweep"])
+        pp = d["per_pair"]
+        assert pp["score"] == 80 and pp["us_per_call"] < 10 and pp["gpu_launches_per_call"] < 0.01      # the doorbell: no launch per call
+        assert pp["cpp_loop"]["server_kernels_launched"] <= 3 and pp["cpp_loop"]["per_pair_equals_batch"] is True
+        sg = d["semiglobal"]
+        assert sg["verified"] == {"e2e_scores_and_lengths_equal_device": True, "whole_batch_sums_equal_oracle": True}
+        assert sg["e2e"]["alignments_per_s"] < sg["device_resident"]["alignments_per_s"]
+        assert d["cpu_baseline"]["kind"] == "reference"
+    else:
+        assert v["other_ranks_score_sums_equal_reference"] is True and v["other_ranks_checked"] == n - 1
+        ip = d["e2e_inproc"]                                                                         # ONE call drives all N GPUs
+        assert ip["n_gpus"] == n and ip["packed"]["value"] > ip["bytes"]["value"] > 0
