@@ -513,8 +513,12 @@ def leg_per_pair(swb200, ctx, a, b, matrix, gap, calls: int = 10_000) -> dict:
     for _ in range(calls):
         pass
     loop_overhead = time.perf_counter() - t1
+    try:
+        pstats = ctx.pair_path_stats()     # the resident server kernel: launched once, rung `calls` times
+    except Exception:
+        pstats = None
     res = {"us_per_call": 1e6 * dt / calls, "ms_per_1M_calls": 1e3 * dt / calls * 1e6, "calls": calls, "score": int(out[0]), "score_expected": 80,
-           "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
+           "gpu_launches_per_call": (ctx.launch_count - l0) / calls, "resident_server": pstats, "python_loop_overhead_us": 1e6 * loop_overhead / calls,
            "timed_from": "a Python loop of direct ctypes calls of swb200_score_pair",
            "api": "swb200_score_pair: the call writes the pair into a 320-byte doorbell in mapped pinned memory; a resident one-warp server kernel polls it across PCIe, scores the pair and stores a tagged word into mapped pinned memory the call spins on (no launch per call; the server leaves by itself after 200 us without a call)",
            "shape": "SpeedTest (source.cpp:3036-3054): one fixed pair, repeated calls"}
