@@ -300,3 +300,27 @@ def test_all_visible_gpus_run_the_compressed_wire_pipeline(swb, oracle, monkeypa
         r = c.semiglobal_xdrop(a, b)
         assert c.launch_count - l0 >= 6 * 5 * g              # the pipeline ran: six launches per chunk, at least five chunks per GPU
     check_against_oracle(oracle, r, a, b, list(range(0, n, 5)) + list(range(n - 40, n)))
+
+
+def test_pipeline_ring_reuse_at_its_default_geometry(ctx, swb, oracle):
+    # the default chunk size (one forward warp per SM) and slot count: twenty chunks round sixteen slots, so the ring is reused
+    # with real events in flight; short sequences keep it quick.  Pinned and pageable callers' arrays give the same results.
+    info = ctx.semiglobal_kernel_info()
+    chunk = info["sm_count"] * 32
+    n, length = chunk * 20 + 333, 64
+    a, b = swb.related_pairs(777, n, length)
+    l0 = ctx.launch_count
+    r = ctx.semiglobal_xdrop(a, b)
+    assert ctx.launch_count - l0 == 21 * 6
+    idx = list(range(0, n, 997)) + list(range(chunk * 16 - 20, chunk * 16 + 20)) + list(range(n - 50, n))
+    check_against_oracle(oracle, r, a, b, idx)
+    pa, pb = swb.PinnedArray((n, length), np.uint8), swb.PinnedArray((n, length), np.uint8)
+    pa.array[:] = a
+    pb.array[:] = b
+    q = ctx.semiglobal_xdrop(pa.array, pb.array)
+    for k in ("score", "end_y", "end_x", "n_ops"):
+        assert np.array_equal(q[k], r[k]), k
+    rows = np.arange(n)[:, None]
+    mask = np.arange(2 * length)[None, :] < r["n_ops"][:, None]
+    assert np.array_equal(np.where(mask, q["ops"], 0), np.where(mask, r["ops"], 0))
+    pa.free(); pb.free()
